@@ -1,0 +1,24 @@
+"""dpomp-b200: the particle-filter hot path of DiscretePOMP.jl on B200 (hand-written CUDA for sm_100a behind a C ABI).
+
+The package directory is named after the reference (`discretepomp.jl_b200`), which is not an importable identifier;
+import it through the repo-root shim module `dpomp_b200`:
+
+    import dpomp_b200 as dp
+    model = dp.generate_model("SIS", [100, 1])
+    y = dp.get_observations("tests/golden/pooley.csv")
+    f = dp.get_particle_filter_lpdf(model, y, np=200)
+    f([0.003, 0.1])
+
+Exported names are those of the reference's public API that lie on the path (src/DiscretePOMP.jl:59-67).
+"""
+from .structs import (DPOMPModel, Event, HiddenMarkovModel, ImportanceSample, MCMCSample, Observation, Particle,
+                      RejectionSample, SimResults)
+from .examples import (GaussianObsModel, UniformProduct, dmy_obs_fn, generate_custom_model, generate_model,
+                       generate_trans_fn, generate_weak_prior, partial_gaussian_obs_model)
+from .rate_table import ModelCompileError, compile_obs_table, compile_rate_table
+from .utils import get_observations
+from .particle_filter import (C_DF_ESS_CRIT, C_DF_PF_P, DeviceModel, ParticleFilter, compile_model, compute_ess,
+                              device_model, estimate_likelihood, get_log_pdf_fn, get_particle_filter_lpdf,
+                              get_private_model)
+from .resample import rs_multinomial, rs_stratified, rs_systematic, rsp_indices
+from . import _capi

@@ -1,0 +1,527 @@
+// capi.cu -- the C ABI of libdpomp (include/dpomp.h): opaque handles, device memory ownership, launch sequencing.
+// Host logic only; every numeric step of the path runs in the kernels of pf_sim.cuh / pf_kernels.cu.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dpomp_dev.cuh"
+#include "dpomp_internal.cuh"
+
+using namespace dpomp;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(DPOMP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+struct dpomp_model {
+    ModelHost h;
+};
+
+struct dpomp_pf {
+    const dpomp_model* model = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long n = 0, n_pad = 0;
+    int n_batch = 0, ntiles = 0, items = 4, tile = 1024;
+    int rs_type = DPOMP_RS_SYSTEMATIC, sim_precision = DPOMP_SIM_F32;
+    long long max_events = 1ll << 20;
+    uint64_t seed = 0, call_index = 0, forced_key = 0;
+    bool key_forced = false;
+    long long batch_offset = 0;
+    int n_comp = 0, n_params = 0, n_obs = 0;
+    int32_t* pop[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* logw = nullptr;
+    double* cw = nullptr;
+    int32_t* anc = nullptr;
+    bool record_anc = false, initialised = false, last_resampled = false;
+    double *theta_dev = nullptr, *tile_m = nullptr, *tile_s = nullptr, *tile_f = nullptr, *tile_off = nullptr;
+    double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
+    unsigned int* tile_counter = nullptr;
+    unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
+    double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
+    int64_t* slots_dev = nullptr;            // 2 * n_batch
+    double* h_theta = nullptr;               // pinned staging
+    double* h_ll = nullptr;
+    int64_t* h_slots = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    long long last_events = 0;
+};
+
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t call_key(const dpomp_pf* pf) {
+    return pf->key_forced ? pf->forced_key : splitmix64(pf->seed ^ splitmix64(pf->call_index));
+}
+
+extern "C" {
+
+const char* dpomp_last_error(void) { return g_err.c_str(); }
+int dpomp_version(void) { return 100; }
+
+int dpomp_device_count(int* out_count) {
+    if (!out_count) return fail(DPOMP_ERR_ARG, "out_count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out_count = 0;
+        return fail(DPOMP_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *out_count = n;
+    return DPOMP_OK;
+}
+
+int dpomp_model_create(const dpomp_model_desc* d, dpomp_model** out_model) {
+    if (!d || !out_model) return fail(DPOMP_ERR_ARG, "null argument");
+    if (d->n_compartments < 1 || d->n_compartments > DPOMP_MAX_COMPARTMENTS || d->n_events < 1 ||
+        d->n_events > DPOMP_MAX_EVENTS || d->n_params < 1 || d->n_params > DPOMP_MAX_PARAMS)
+        return fail(DPOMP_ERR_MODEL, "model dimensions outside the device table limits");
+    if (d->t0_index < 0 || d->t0_index > d->n_params) return fail(DPOMP_ERR_MODEL, "t0_index out of range");
+    if (d->n_obs < 1 || !d->obs_time || !d->obs_id || !d->obs_val) return fail(DPOMP_ERR_MODEL, "no observations");
+    if (d->n_obs_vals < 1 || d->n_obs_vals > DPOMP_MAX_OBS_VALS) return fail(DPOMP_ERR_MODEL, "n_obs_vals out of range");
+    if (!(d->obs_sigma > 0.0)) return fail(DPOMP_ERR_MODEL, "obs_sigma must be positive");
+    for (int e = 0; e < d->n_events; ++e)
+        if (d->rate_par[e] >= d->n_params) return fail(DPOMP_ERR_MODEL, "rate_par out of range");
+    for (int c = 0; c < d->n_compartments; ++c)
+        if (d->initial_condition[c] < 0 || d->initial_condition[c] > 0x7fffffffll)
+            return fail(DPOMP_ERR_MODEL, "initial condition outside int32 range");
+    for (int t = 1; t < d->n_obs; ++t)
+        if (d->obs_time[t] < d->obs_time[t - 1]) return fail(DPOMP_ERR_MODEL, "observations are not sorted by time");
+    dpomp_model* m = new (std::nothrow) dpomp_model();
+    if (!m) return fail(DPOMP_ERR_ARG, "out of host memory");
+    m->h.desc = *d;
+    m->h.obs_time.assign(d->obs_time, d->obs_time + d->n_obs);
+    m->h.obs_id.assign(d->obs_id, d->obs_id + d->n_obs);
+    m->h.obs_val.assign(d->obs_val, d->obs_val + (size_t)d->n_obs * d->n_obs_vals);
+    m->h.obs_ysum.resize(d->n_obs);
+    for (int t = 0; t < d->n_obs; ++t) {
+        int64_t s = 0;
+        for (int v = 0; v < d->n_obs_vals; ++v) s += (int64_t)d->obs_ymask[v] * d->obs_val[(size_t)t * d->n_obs_vals + v];
+        m->h.obs_ysum[t] = (double)s;
+    }
+    m->h.desc.obs_time = m->h.obs_time.data();
+    m->h.desc.obs_id = m->h.obs_id.data();
+    m->h.desc.obs_val = m->h.obs_val.data();
+    *out_model = m;
+    return DPOMP_OK;
+}
+
+int dpomp_model_destroy(dpomp_model* model) {
+    delete model;
+    return DPOMP_OK;
+}
+
+static void pf_free(dpomp_pf* pf) {
+    if (!pf) return;
+    cudaSetDevice(pf->device);
+    cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->cw); cudaFree(pf->anc);
+    cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
+    cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
+    cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev);
+    cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
+    if (pf->ev0) cudaEventDestroy(pf->ev0);
+    if (pf->ev1) cudaEventDestroy(pf->ev1);
+    if (pf->stream) cudaStreamDestroy(pf->stream);
+    delete pf;
+}
+
+int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_batch, int32_t rs_type, uint64_t seed,
+                    int32_t device, dpomp_pf** out_pf) {
+    if (!model || !out_pf) return fail(DPOMP_ERR_ARG, "null argument");
+    if (n_particles < 1 || n_particles > 0x7fffffffll) return fail(DPOMP_ERR_ARG, "n_particles out of range");
+    if (n_batch < 1) return fail(DPOMP_ERR_ARG, "n_batch must be >= 1");
+    if (rs_type < 1 || rs_type > 3) return fail(DPOMP_ERR_ARG, "rs_type must be 1, 2 or 3");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(DPOMP_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail(DPOMP_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    const dpomp_model_desc& d = model->h.desc;
+    if (!sim_kernel_supported(d.n_compartments, d.n_events)) return fail(DPOMP_ERR_MODEL, "no kernel instantiation covers the model");
+
+    dpomp_pf* pf = new (std::nothrow) dpomp_pf();
+    if (!pf) return fail(DPOMP_ERR_ARG, "out of host memory");
+    pf->model = model;
+    pf->device = device;
+    pf->n = n_particles;
+    pf->n_batch = n_batch;
+    pf->rs_type = rs_type;
+    pf->seed = seed;
+    pf->items = n_particles <= 256 ? 1 : 4;  // scan-tree geometry: 256-particle tiles for tiny filters, 1024 otherwise
+    pf->tile = kBlockThreads * pf->items;
+    pf->ntiles = (int)((n_particles + pf->tile - 1) / pf->tile);
+    pf->n_pad = (long long)pf->ntiles * pf->tile;
+    pf->n_comp = d.n_compartments;
+    pf->n_params = d.n_params;
+    pf->n_obs = d.n_obs;
+    if ((long long)n_batch * pf->ntiles > 0x7fffffffll) { delete pf; return fail(DPOMP_ERR_ARG, "n_batch * tiles exceeds the grid limit"); }
+
+    const size_t B = (size_t)n_batch, NP = (size_t)pf->n_pad, NT = (size_t)pf->ntiles;
+#define ALLOC(ptr, bytes)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                                 \
+        if (_e != cudaSuccess) {                                                                              \
+            pf_free(pf);                                                                                      \
+            return fail(DPOMP_ERR_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(_e));       \
+        }                                                                                                     \
+    } while (0)
+    ALLOC(pf->pop[0], B * pf->n_comp * NP * sizeof(int32_t));
+    ALLOC(pf->pop[1], B * pf->n_comp * NP * sizeof(int32_t));
+    ALLOC(pf->logw, B * NP * sizeof(double));
+    if (rs_type == DPOMP_RS_MULTINOMIAL) ALLOC(pf->cw, B * NP * sizeof(double));
+    ALLOC(pf->theta_dev, B * pf->n_params * sizeof(double));
+    ALLOC(pf->tile_m, B * NT * sizeof(double));
+    ALLOC(pf->tile_s, B * NT * sizeof(double));
+    ALLOC(pf->tile_f, B * NT * sizeof(double));
+    ALLOC(pf->tile_off, B * (NT + 1) * sizeof(double));
+    ALLOC(pf->filt_m, B * sizeof(double));
+    ALLOC(pf->filt_s, B * sizeof(double));
+    ALLOC(pf->ll_acc, B * sizeof(double));
+    ALLOC(pf->tile_counter, B * sizeof(unsigned int));
+    ALLOC(pf->counters, 2 * sizeof(unsigned long long));
+    ALLOC(pf->obs_time_dev, (size_t)d.n_obs * sizeof(double));
+    ALLOC(pf->obs_ysum_dev, (size_t)d.n_obs * sizeof(double));
+    ALLOC(pf->slots_dev, 2 * B * sizeof(int64_t));
+#undef ALLOC
+    bool ok = cudaMallocHost((void**)&pf->h_theta, B * pf->n_params * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost((void**)&pf->h_ll, B * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost((void**)&pf->h_slots, 2 * B * sizeof(int64_t)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pf->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&pf->ev0) == cudaSuccess && cudaEventCreate(&pf->ev1) == cudaSuccess &&
+              cudaMemsetAsync(pf->pop[0], 0, B * pf->n_comp * NP * sizeof(int32_t), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->pop[1], 0, B * pf->n_comp * NP * sizeof(int32_t), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->tile_counter, 0, B * sizeof(unsigned int), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->counters, 0, 2 * sizeof(unsigned long long), pf->stream) == cudaSuccess &&
+              cudaMemcpyAsync(pf->obs_time_dev, model->h.obs_time.data(), (size_t)d.n_obs * sizeof(double),
+                              cudaMemcpyHostToDevice, pf->stream) == cudaSuccess &&
+              cudaMemcpyAsync(pf->obs_ysum_dev, model->h.obs_ysum.data(), (size_t)d.n_obs * sizeof(double),
+                              cudaMemcpyHostToDevice, pf->stream) == cudaSuccess &&
+              cudaStreamSynchronize(pf->stream) == cudaSuccess;
+    if (!ok) {
+        std::string msg = std::string("pf setup: ") + cudaGetErrorString(cudaGetLastError());
+        pf_free(pf);
+        return fail(DPOMP_ERR_CUDA, msg);
+    }
+    *out_pf = pf;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_destroy(dpomp_pf* pf) {
+    pf_free(pf);
+    return DPOMP_OK;
+}
+
+int dpomp_pf_set_sim_precision(dpomp_pf* pf, int32_t p) {
+    if (!pf || (p != DPOMP_SIM_F32 && p != DPOMP_SIM_F64)) return fail(DPOMP_ERR_ARG, "bad sim precision");
+    pf->sim_precision = p;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t m) {
+    if (!pf || m < 1 || m > 0x7fffffffll) return fail(DPOMP_ERR_ARG, "max_events out of range");
+    pf->max_events = m;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t off) {
+    if (!pf || off < 0 || off + pf->n_batch > 0xffffffffll) return fail(DPOMP_ERR_ARG, "batch_offset out of range");
+    pf->batch_offset = off;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    pf->forced_key = key;
+    pf->key_forced = true;
+    return DPOMP_OK;
+}
+int dpomp_pf_get_stream_key(dpomp_pf* pf, uint64_t* out_key) {
+    if (!pf || !out_key) return fail(DPOMP_ERR_ARG, "null argument");
+    *out_key = call_key(pf);
+    return DPOMP_OK;
+}
+int dpomp_pf_geometry(const dpomp_pf* pf, int32_t* out_tile, int32_t* out_items) {
+    if (!pf || !out_tile || !out_items) return fail(DPOMP_ERR_ARG, "null argument");
+    *out_tile = pf->tile;
+    *out_items = pf->items;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_record_ancestors(dpomp_pf* pf, int32_t on) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    CK(cudaSetDevice(pf->device));
+    if (on && !pf->anc) CK(cudaMalloc((void**)&pf->anc, (size_t)pf->n_batch * pf->n_pad * sizeof(int32_t)));
+    pf->record_anc = on != 0;
+    return DPOMP_OK;
+}
+
+// the launch sequence of partial_log_likelihood! (src/hmm_particle_filter.jl:39-76), batched over filters
+static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax, double* out,
+                       bool out_on_device) {
+    if (!pf || !theta || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    if (nb < 1 || nb > pf->n_batch) return fail(DPOMP_ERR_ARG, "n_batch_used out of range");
+    if (ymin < 1 || ymax < ymin || ymax > pf->n_obs) return fail(DPOMP_ERR_ARG, "observation range out of bounds");
+    if (ymin > 1 && !pf->initialised) return fail(DPOMP_ERR_STATE, "ymin > 1 on a filter that has never been run from ymin == 1");
+    CK(cudaSetDevice(pf->device));
+    const ModelHost& mh = pf->model->h;
+    const uint64_t key = call_key(pf);
+    pf->key_forced = false;
+    pf->call_index += 1;
+    cudaStream_t st = pf->stream;
+    CK(cudaEventRecord(pf->ev0, st));
+    const size_t th_bytes = (size_t)nb * pf->n_params * sizeof(double);
+    if (theta_on_device) {
+        CK(cudaMemcpyAsync(pf->theta_dev, theta, th_bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+        memcpy(pf->h_theta, theta, th_bytes);
+        CK(cudaMemcpyAsync(pf->theta_dev, pf->h_theta, th_bytes, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemsetAsync(pf->ll_acc, 0, (size_t)nb * sizeof(double), st));
+    CK(cudaMemsetAsync(pf->counters, 0, sizeof(unsigned long long), st));
+    int launches = 0;
+    for (int oi = ymin; oi <= ymax; ++oi) {
+        const int t = oi - 1;
+        const int has_lik = mh.obs_id[t] > 0;
+        const int do_rs = has_lik && oi < pf->n_obs;  // src/hmm_particle_filter.jl:58,62
+        SimLaunch a{};
+        a.pop = pf->pop[pf->cur];
+        a.logw = pf->logw;
+        a.theta = pf->theta_dev;
+        a.obs_time = pf->obs_time_dev;
+        a.obs_ysum = pf->obs_ysum_dev;
+        a.tile_m = pf->tile_m; a.tile_s = pf->tile_s; a.tile_f = pf->tile_f; a.tile_off = pf->tile_off;
+        a.filt_m = pf->filt_m; a.filt_s = pf->filt_s; a.ll_acc = pf->ll_acc;
+        a.tile_counter = pf->tile_counter;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1;
+        a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
+        a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
+        a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
+        CK(launch_sim_weight(mh, pf->sim_precision, pf->items, a, st));
+        ++launches;
+        if (do_rs) {
+            ResampleLaunch r{};
+            r.pop_src = pf->pop[pf->cur]; r.pop_dst = pf->pop[pf->cur ^ 1];
+            r.logw = pf->logw; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;
+            r.anc = pf->record_anc ? pf->anc : nullptr;
+            r.cw = pf->cw;
+            r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;
+            r.t = t; r.rs_type = pf->rs_type; r.key = key; r.filter0 = (uint32_t)pf->batch_offset;
+            CK(launch_resample(pf->items, r, st));
+            launches += (pf->rs_type == DPOMP_RS_MULTINOMIAL) ? 2 : 1;
+            pf->cur ^= 1;
+        }
+        pf->last_resampled = do_rs != 0;
+    }
+    if (out_on_device) {
+        CK(cudaMemcpyAsync(out, pf->ll_acc, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(cudaMemcpyAsync(pf->h_ll, pf->ll_acc, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long h_cnt = 0;
+    CK(cudaMemcpyAsync(&h_cnt, pf->counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(pf->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (!out_on_device) memcpy(out, pf->h_ll, (size_t)nb * sizeof(double));
+    CK(cudaEventElapsedTime(&pf->last_ms, pf->ev0, pf->ev1));
+    pf->last_launches = launches;
+    pf->last_events = (long long)h_cnt;
+    pf->initialised = true;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_loglik(dpomp_pf* pf, const double* theta, int32_t nb, double* out_ll) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    return run_partial(pf, theta, false, nb, 1, pf->n_obs, out_ll, false);
+}
+int dpomp_pf_loglik_device(dpomp_pf* pf, const double* theta_dev, int32_t nb, double* out_ll_dev) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    return run_partial(pf, theta_dev, true, nb, 1, pf->n_obs, out_ll_dev, true);
+}
+int dpomp_pf_partial(dpomp_pf* pf, const double* theta, int32_t nb, int32_t ymin, int32_t ymax, double* out_gx) {
+    return run_partial(pf, theta, false, nb, ymin, ymax, out_gx, false);
+}
+
+static int upload_slots(dpomp_pf* pf, const int64_t* a, const int64_t* b, int n, int limit_a, int limit_b) {
+    for (int i = 0; i < n; ++i) {
+        if (a && (a[i] < 1 || a[i] > limit_a)) return fail(DPOMP_ERR_ARG, "filter index out of range");
+        if (b && (b[i] < 1 || b[i] > limit_b)) return fail(DPOMP_ERR_ARG, "filter index out of range");
+        if (a) pf->h_slots[i] = a[i];
+        if (b) pf->h_slots[pf->n_batch + i] = b[i];
+    }
+    CK(cudaMemcpyAsync(pf->slots_dev, pf->h_slots, 2 * (size_t)pf->n_batch * sizeof(int64_t), cudaMemcpyHostToDevice, pf->stream));
+    return DPOMP_OK;
+}
+
+int dpomp_pf_permute(dpomp_pf* pf, const int64_t* nidx, int32_t n) {
+    if (!pf || !nidx) return fail(DPOMP_ERR_ARG, "null argument");
+    if (n < 1 || n > pf->n_batch) return fail(DPOMP_ERR_ARG, "n out of range");
+    CK(cudaSetDevice(pf->device));
+    int rc = upload_slots(pf, nullptr, nidx, n, 0, pf->n_batch);
+    if (rc) return rc;
+    const long long stride = (long long)pf->n_comp * pf->n_pad;
+    CK(launch_gather_filters(pf->pop[pf->cur ^ 1], pf->pop[pf->cur], nullptr, pf->slots_dev + pf->n_batch, n, stride, pf->stream));
+    if (n < pf->n_batch)  // filters beyond n keep their state
+        CK(cudaMemcpyAsync(pf->pop[pf->cur ^ 1] + (size_t)n * stride, pf->pop[pf->cur] + (size_t)n * stride,
+                           (size_t)(pf->n_batch - n) * stride * sizeof(int32_t), cudaMemcpyDeviceToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->cur ^= 1;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_copy_filters(dpomp_pf* dst, const dpomp_pf* src, const int64_t* dst_slots, const int64_t* src_slots, int32_t n) {
+    if (!dst || !src || !dst_slots || !src_slots) return fail(DPOMP_ERR_ARG, "null argument");
+    if (n == 0) return DPOMP_OK;
+    if (n < 0 || n > dst->n_batch) return fail(DPOMP_ERR_ARG, "n out of range");
+    if (dst->n_pad != src->n_pad || dst->n_comp != src->n_comp || dst->device != src->device)
+        return fail(DPOMP_ERR_ARG, "filters have different geometry or device");
+    CK(cudaSetDevice(dst->device));
+    int rc = upload_slots(dst, dst_slots, src_slots, n, dst->n_batch, src->n_batch);
+    if (rc) return rc;
+    const long long stride = (long long)dst->n_comp * dst->n_pad;
+    CK(launch_gather_filters(dst->pop[dst->cur], src->pop[src->cur], dst->slots_dev, dst->slots_dev + dst->n_batch, n, stride, dst->stream));
+    CK(cudaStreamSynchronize(dst->stream));
+    dst->initialised = true;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_get_pop(dpomp_pf* pf, int32_t b, int64_t* out) {
+    if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    if (b < 1 || b > pf->n_batch) return fail(DPOMP_ERR_ARG, "filter index out of range");
+    CK(cudaSetDevice(pf->device));
+    const size_t words = (size_t)pf->n_comp * pf->n_pad;
+    std::vector<int32_t> tmp(words);
+    CK(cudaMemcpyAsync(tmp.data(), pf->pop[pf->cur] + (size_t)(b - 1) * words, words * sizeof(int32_t), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    for (int c = 0; c < pf->n_comp; ++c)
+        for (long long p = 0; p < pf->n; ++p) out[(size_t)c * pf->n + p] = tmp[(size_t)c * pf->n_pad + p];
+    return DPOMP_OK;
+}
+
+int dpomp_pf_set_pop(dpomp_pf* pf, int32_t b, const int64_t* in) {
+    if (!pf || !in) return fail(DPOMP_ERR_ARG, "null argument");
+    if (b < 1 || b > pf->n_batch) return fail(DPOMP_ERR_ARG, "filter index out of range");
+    CK(cudaSetDevice(pf->device));
+    const size_t words = (size_t)pf->n_comp * pf->n_pad;
+    std::vector<int32_t> tmp(words, 0);
+    for (int c = 0; c < pf->n_comp; ++c)
+        for (long long p = 0; p < pf->n; ++p) tmp[(size_t)c * pf->n_pad + p] = (int32_t)in[(size_t)c * pf->n + p];
+    CK(cudaMemcpyAsync(pf->pop[pf->cur] + (size_t)(b - 1) * words, tmp.data(), words * sizeof(int32_t), cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->initialised = true;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_get_last_logw(dpomp_pf* pf, int32_t b, double* out) {
+    if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    if (b < 1 || b > pf->n_batch) return fail(DPOMP_ERR_ARG, "filter index out of range");
+    CK(cudaSetDevice(pf->device));
+    CK(cudaMemcpyAsync(out, pf->logw + (size_t)(b - 1) * pf->n_pad, (size_t)pf->n * sizeof(double), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    return DPOMP_OK;
+}
+
+int dpomp_pf_get_last_ancestors(dpomp_pf* pf, int32_t b, int64_t* out) {
+    if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    if (b < 1 || b > pf->n_batch) return fail(DPOMP_ERR_ARG, "filter index out of range");
+    if (!pf->record_anc || !pf->anc) return fail(DPOMP_ERR_STATE, "ancestor recording is off");
+    CK(cudaSetDevice(pf->device));
+    std::vector<int32_t> tmp((size_t)pf->n);
+    CK(cudaMemcpyAsync(tmp.data(), pf->anc + (size_t)(b - 1) * pf->n_pad, (size_t)pf->n * sizeof(int32_t), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    for (long long p = 0; p < pf->n; ++p) out[p] = (int64_t)tmp[(size_t)p] + 1;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_overflow_count(dpomp_pf* pf, int64_t* out) {
+    if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    CK(cudaSetDevice(pf->device));
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, pf->counters + 1, sizeof(v), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    *out = (int64_t)v;
+    return DPOMP_OK;
+}
+int dpomp_pf_last_event_count(dpomp_pf* pf, int64_t* out) {
+    if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
+    *out = pf->last_events;
+    return DPOMP_OK;
+}
+int dpomp_pf_last_timing(dpomp_pf* pf, float* out_ms, int32_t* out_launches) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    if (out_ms) *out_ms = pf->last_ms;
+    if (out_launches) *out_launches = pf->last_launches;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_export_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, void* device_dst) {
+    if (!pf || !slots || !device_dst) return fail(DPOMP_ERR_ARG, "null argument");
+    if (n < 1 || n > pf->n_batch) return fail(DPOMP_ERR_ARG, "n out of range");
+    CK(cudaSetDevice(pf->device));
+    int rc = upload_slots(pf, slots, nullptr, n, pf->n_batch, 0);
+    if (rc) return rc;
+    CK(launch_pack_filters((int32_t*)device_dst, pf->pop[pf->cur], pf->slots_dev, n, (long long)pf->n_comp * pf->n_pad, 0, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    return DPOMP_OK;
+}
+int dpomp_pf_import_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, const void* device_src) {
+    if (!pf || !slots || !device_src) return fail(DPOMP_ERR_ARG, "null argument");
+    if (n < 1 || n > pf->n_batch) return fail(DPOMP_ERR_ARG, "n out of range");
+    CK(cudaSetDevice(pf->device));
+    int rc = upload_slots(pf, slots, nullptr, n, pf->n_batch, 0);
+    if (rc) return rc;
+    CK(launch_pack_filters((int32_t*)device_src, pf->pop[pf->cur], pf->slots_dev, n, (long long)pf->n_comp * pf->n_pad, 1, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->initialised = true;
+    return DPOMP_OK;
+}
+
+int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double* w, int64_t n, const double* u, int64_t n_u,
+                           int64_t n_out, int64_t* out_idx, int32_t device) {
+    if (!w || !u || !out_idx) return fail(DPOMP_ERR_ARG, "null argument");
+    if (rs_type < 1 || rs_type > 3) return fail(DPOMP_ERR_ARG, "rs_type must be 1, 2 or 3");
+    if (n < 1 || n_out < 1) return fail(DPOMP_ERR_ARG, "empty input");
+    if (rs_type != DPOMP_RS_MULTINOMIAL && n_out != n) return fail(DPOMP_ERR_ARG, "systematic/stratified produce n offspring");
+    const int64_t need_u = rs_type == DPOMP_RS_SYSTEMATIC ? 1 : n_out;
+    if (n_u < need_u) return fail(DPOMP_ERR_ARG, "not enough uniforms");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) return fail(DPOMP_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device >= 0) CK(cudaSetDevice(device));
+    std::vector<double> cw(w, w + n);
+    if (!on_cumulative)  // cumsum / cumsum! (src/hmm_resample.jl:5,45,67): sequential f64, bit-exact by construction
+        for (int64_t i = 1; i < n; ++i) cw[(size_t)i] = cw[(size_t)i - 1] + cw[(size_t)i];
+    double *cw_d = nullptr, *u_d = nullptr;
+    int64_t* out_d = nullptr;
+    CK(cudaMalloc((void**)&cw_d, (size_t)n * sizeof(double)));
+    cudaError_t e1 = cudaMalloc((void**)&u_d, (size_t)need_u * sizeof(double));
+    cudaError_t e2 = cudaMalloc((void**)&out_d, (size_t)n_out * sizeof(int64_t));
+    int rc = DPOMP_OK;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(DPOMP_ERR_CUDA, "cudaMalloc failed in dpomp_resample_indices");
+    if (!rc) {
+        cudaError_t s = cudaMemcpy(cw_d, cw.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+        if (s == cudaSuccess) s = cudaMemcpy(u_d, u, (size_t)need_u * sizeof(double), cudaMemcpyHostToDevice);
+        if (s == cudaSuccess) s = launch_search_hook(rs_type, cw_d, n, u_d, n_out, out_d, 0);
+        if (s == cudaSuccess) s = cudaMemcpy(out_idx, out_d, (size_t)n_out * sizeof(int64_t), cudaMemcpyDeviceToHost);
+        if (s != cudaSuccess) rc = fail(DPOMP_ERR_CUDA, std::string("dpomp_resample_indices: ") + cudaGetErrorString(s));
+    }
+    cudaFree(cw_d); cudaFree(u_d); cudaFree(out_d);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// dpomp_dev.cuh -- device-side building blocks shared by the particle-filter kernels (sm_100a).
+//   * Philox4x32-10 counter-based RNG and the stream layout of DESIGN.md ("random streams")
+//   * the deterministic block scan tree (DESIGN.md "deterministic scan tree")
+//   * the counting form of the systematic / stratified search with the reference's exact f64 expressions
+//     (src/hmm_pf_resample.jl:24-42, src/hmm_resample.jl:66-83 of the reference)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dpomp.h"
+
+namespace dpomp {
+
+constexpr int kBlockThreads = 256;
+constexpr uint32_t kTagSim = 0u;
+constexpr uint32_t kTagResample = 1u;
+
+// ------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  ctr = (particle, filter, observation, tag<<30 | block), key = 64-bit call key.
+// ------------------------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t w0, w1, w2, w3;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 stream_draw(uint64_t key, uint32_t particle, uint32_t filter, uint32_t obs,
+                                               uint32_t tag, uint32_t block) {
+    return philox4x32_10(particle, filter, obs, (tag << 30) | block, (uint32_t)key, (uint32_t)(key >> 32));
+}
+
+// (0,1) with 32-bit resolution; f64 value is exact, f32 value is the rounding of it
+__device__ __forceinline__ double u32_open_f64(uint32_t w) { return ((double)w + 0.5) * 0x1.0p-32; }
+__device__ __forceinline__ float u32_open_f32(uint32_t w) { return fmaf(__uint2float_rn(w), 0x1.0p-32f, 0x1.0p-33f); }
+// [0,1) with 53-bit resolution (Julia's rand() range) for the resampling draws
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return (double)(((uint64_t)hi << 21) | (uint64_t)(lo >> 11)) * 0x1.0p-53;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Deterministic tile scan.  Thread `tid` (lane l of warp w) owns ITEMS consecutive values a[0..ITEMS).
+//   r_k   = a_0 + ... + a_k          (left to right)
+//   I_l   = Kogge-Stone inclusive scan over lanes of r_{ITEMS-1}
+//   P_w   = W_0 + ... + W_{w-1}      (left to right over warps, W_w = I_31 of warp w)
+//   incl_k = (P_w + I_{l-1}) + r_k ,  excl_k = (P_w + I_{l-1}) + r_{k-1}
+// Returns the tile total P_{nw-1} + W_{nw-1}.  All adds are round-to-nearest f64, never contracted.
+// `warp_tot` is shared scratch of kBlockThreads/32 doubles.  Contains two __syncthreads().
+// ------------------------------------------------------------------------------------------------------------
+template <int ITEMS>
+__device__ __forceinline__ double tile_scan(const double (&a)[ITEMS], double (&incl)[ITEMS], double (&excl)[ITEMS],
+                                            double* warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double r[ITEMS];
+    r[0] = a[0];
+#pragma unroll
+    for (int k = 1; k < ITEMS; ++k) r[k] = __dadd_rn(r[k - 1], a[k]);
+    double inc = r[ITEMS - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = __dadd_rn(y, inc);
+    }
+    double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = 0.0;
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    double prefix = 0.0, total = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlockThreads / 32; ++w) {
+        if (w == warp) prefix = total;
+        total = __dadd_rn(total, warp_tot[w]);
+    }
+    const double base = __dadd_rn(prefix, prev);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        incl[k] = __dadd_rn(base, r[k]);
+        excl[k] = __dadd_rn(base, k > 0 ? r[k - 1] : 0.0);
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ double block_max(double v, double* warp_scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if (lane == 0) warp_scratch[warp] = v;
+    __syncthreads();
+    double m = warp_scratch[0];
+#pragma unroll
+    for (int w = 1; w < kBlockThreads / 32; ++w) m = fmax(m, warp_scratch[w]);
+    __syncthreads();
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Resampling uniforms in the reference's expression order and the counting form of the search.
+//   systematic: u_i = ((r/N) + ((i-1)/N)) * S          (src/hmm_pf_resample.jl:27-32)
+//   stratified: u_i = ((r_i/N) + ((i-1)/N)) * S        (src/hmm_resample.jl:69-73)
+//   E(v) = #{ i in 1..N : u_i <= v }   -- u_i is non-decreasing in i, so ancestor(i) = first j with E(cw_j) >= i,
+//   which is exactly the walk `while u[i] > cw[j]; j += 1`.
+// ------------------------------------------------------------------------------------------------------------
+struct ResampleCtx {
+    int rs_type;
+    long long n;
+    double dn;        // (double) n
+    double inv_n;     // exact iff n is a power of two
+    bool pow2;
+    double s;         // cw[end]
+    double inv_s;     // only used for the (inexact) initial guess
+    double r1_over_n; // systematic: r / N
+    uint64_t key;
+    uint32_t filter, obs;
+};
+
+__device__ __forceinline__ double div_by_n(const ResampleCtx& c, double v) {
+    return c.pow2 ? v * c.inv_n : __ddiv_rn(v, c.dn);
+}
+
+__device__ __forceinline__ double resample_u(const ResampleCtx& c, long long i /*1-based*/) {
+    const double q = div_by_n(c, (double)(i - 1));
+    double r = c.r1_over_n;
+    if (c.rs_type == DPOMP_RS_STRATIFIED) {
+        const Philox4 p = stream_draw(c.key, (uint32_t)(i - 1), c.filter, c.obs, kTagResample, 1u);
+        r = div_by_n(c, u53(p.w0, p.w1));
+    }
+    return __dmul_rn(__dadd_rn(r, q), c.s);
+}
+
+__device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, double v) {
+    if (!(c.s > 0.0)) return c.n;
+    double g = (c.rs_type == DPOMP_RS_STRATIFIED) ? floor(v * c.inv_s * c.dn)
+                                                  : floor((v * c.inv_s - c.r1_over_n) * c.dn) + 1.0;
+    g = fmin(fmax(g, 0.0), c.dn);
+    long long e = (long long)g;
+    while (e < c.n && resample_u(c, e + 1) <= v) ++e;
+    while (e > 0 && resample_u(c, e) > v) --e;
+    return e;
+}
+
+__device__ __forceinline__ ResampleCtx make_resample_ctx(int rs_type, long long n, double s, uint64_t key,
+                                                         uint32_t filter, uint32_t obs, double r_systematic) {
+    ResampleCtx c;
+    c.rs_type = rs_type;
+    c.n = n;
+    c.dn = (double)n;
+    c.pow2 = (n & (n - 1)) == 0;
+    c.inv_n = 1.0 / c.dn;
+    c.s = s;
+    c.inv_s = (s > 0.0) ? 1.0 / s : 0.0;
+    c.key = key;
+    c.filter = filter;
+    c.obs = obs;
+    c.r1_over_n = div_by_n(c, r_systematic);
+    return c;
+}
+
+}  // namespace dpomp

@@ -1,0 +1,97 @@
+// dpomp_internal.cuh -- host-side handle layouts and the launcher interface between capi.cu and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dpomp.h"
+
+namespace dpomp {
+
+// Rate / observation table in the arithmetic of the event loop (Real = float or double), padded to the
+// instantiated (C, E).  Passed to kernels by value (constant bank).
+template <typename Real, int C, int E>
+struct DevModel {
+    int par[E];       // parameter index or -1
+    Real f1[E][C], k1[E];
+    Real f2[E][C], k2[E];
+    Real dn[E][C], kd[E];
+    int has_den[E];
+    int any_den;
+    Real trans[E][C];
+    Real xmask[C];
+    int ic[C];
+    double obs_tmp1, obs_tmp2;  // log(1/(sqrt(2 pi) sigma)), 2 sigma^2 (src/hmm_examples.jl:61-62)
+    int t0_index;
+    int n_params;
+};
+
+// Everything one launch of the simulate+weight kernel needs besides the model.
+struct SimLaunch {
+    int32_t* pop;            // [B][C][n_pad] current populations (read unless fresh, written)
+    double* logw;            // [B][n_pad]
+    const double* theta;     // [B][n_params] device
+    const double* obs_time;  // [T]
+    const double* obs_ysum;  // [T]  sum_v ymask[v] * y.val[v]
+    double* tile_m;          // [B][ntiles]
+    double* tile_s;          // [B][ntiles]
+    double* tile_f;          // [B][ntiles]
+    double* tile_off;        // [B][ntiles + 1]
+    double* filt_m;          // [B]
+    double* filt_s;          // [B]
+    double* ll_acc;          // [B]
+    unsigned int* tile_counter;      // [B]
+    unsigned long long* ev_count;    // [1]
+    unsigned long long* ovf_count;   // [1]
+    long long n;             // particles per filter
+    long long n_pad;         // ntiles * tile
+    int ntiles;
+    int n_filters;           // filters in this launch
+    int n_comp;              // real C (<= instantiated C)
+    int t;                   // 0-based observation index
+    int fresh;               // 1: start from the initial condition at t_prev = 0 / theta[t0_index]
+    int has_lik;             // obs_id[t] > 0
+    uint64_t key;
+    uint32_t filter0;        // global id of local filter 0
+    long long max_events;
+};
+
+struct ResampleLaunch {
+    const int32_t* pop_src;  // [B][C][n_pad]
+    int32_t* pop_dst;
+    const double* logw;
+    const double* tile_m;
+    const double* tile_f;
+    const double* tile_off;
+    const double* filt_s;
+    int32_t* anc;            // [B][n_pad] 0-based ancestors, or nullptr
+    double* cw;              // [B][n_pad] cumulative weights (multinomial only), or nullptr
+    long long n, n_pad;
+    int ntiles, n_filters, n_comp;
+    int t, rs_type;
+    uint64_t key;
+    uint32_t filter0;
+};
+
+struct ModelHost {
+    dpomp_model_desc desc;  // pointers re-targeted to the vectors below
+    std::vector<double> obs_time;
+    std::vector<int32_t> obs_id;
+    std::vector<int64_t> obs_val;
+    std::vector<double> obs_ysum;
+};
+
+// launchers implemented in the kernel TUs; all asynchronous on `stream`; return cudaGetLastError()
+cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, const SimLaunch& a, cudaStream_t stream);
+cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream);
+cudaError_t launch_gather_filters(int32_t* dst, const int32_t* src, const int64_t* dst_slots_dev,
+                                  const int64_t* src_slots_dev, int n, long long filter_stride_words, cudaStream_t stream);
+cudaError_t launch_pack_filters(int32_t* dst_packed, const int32_t* pop, const int64_t* slots_dev, int n,
+                                long long filter_stride_words, int unpack, cudaStream_t stream);
+cudaError_t launch_search_hook(int rs_type, const double* cw_dev, long long n, const double* u_dev, long long n_out,
+                               int64_t* out_dev, cudaStream_t stream);
+int sim_kernel_supported(int n_comp, int n_events);
+
+}  // namespace dpomp

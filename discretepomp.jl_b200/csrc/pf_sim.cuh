@@ -1,0 +1,332 @@
+// pf_sim.cuh -- kernel 1 of the particle filter: per-particle Gillespie simulation between two observation times,
+// observation log-weight, and the per-tile / per-filter log-sum-exp partials.
+//
+// Replaces iterate_particles! (src/hmm_particle_filter.jl:9-33) with choose_event (src/hmm_cmn.jl:4-10), the rate
+// closures (src/hmm_examples.jl:103-168) and the Gaussian observation model (src/hmm_examples.jl:59-67) of the
+// reference, plus the `log(cum_weight[end]/N)` accumulation of partial_log_likelihood! (src/hmm_particle_filter.jl:60).
+//
+// Mapping: one CTA of 256 threads per (filter, tile of 256*ITEMS particles).  Each lane owns ITEMS particles and runs
+// them back to back in ONE flat event loop ("lane refill"): a lane that finishes a particle immediately starts its next
+// one, so a warp iterates max_lanes(sum of attempts) times instead of sum(max_lanes(attempts)).  Compartment counts live
+// in registers as Real during the loop; the tile's int32 states are staged in shared memory so the refill never waits
+// on HBM.  One Philox4x32-10 call feeds two event attempts (waiting time + event type each).
+#pragma once
+#include "dpomp_dev.cuh"
+#include "dpomp_internal.cuh"
+
+namespace dpomp {
+
+template <typename Real> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+};
+template <> struct Arith<double> {  // round-to-nearest, never contracted: the reference's f64 expressions bit for bit
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename Real, int C, int E, int ITEMS>
+__global__ void __launch_bounds__(kBlockThreads)
+pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
+    constexpr int TILE = kBlockThreads * ITEMS;
+    constexpr bool kF32 = sizeof(Real) == 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lw_s = reinterpret_cast<double*>(smem_raw);   // [TILE] log weights of the tile
+    int* st_s = reinterpret_cast<int*>(lw_s + TILE);      // [C][TILE] staged compartment counts
+    __shared__ double warp_scratch[kBlockThreads / 32];
+    __shared__ int is_last_s;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x % a.ntiles;
+    const int b = blockIdx.x / a.ntiles;
+    const long long base_n = (long long)tile * TILE;
+    const uint32_t gfilter = a.filter0 + (uint32_t)b;
+    const double* th = a.theta + (size_t)b * m.n_params;
+
+    Real par[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) par[e] = m.par[e] >= 0 ? (Real)th[m.par[e]] : (Real)1;
+    const double t_obs = a.obs_time[a.t];
+    const double t_prev = a.fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : a.obs_time[a.t - 1];
+    const double ysum = a.obs_ysum[a.t];
+    int32_t* pop_b = a.pop + (size_t)b * a.n_comp * a.n_pad;
+    const uint32_t max_ev = (uint32_t)a.max_events;
+
+    if (!a.fresh) {  // stage this thread's particles (coalesced); each lane only ever touches its own slots
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (c < a.n_comp) {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r)
+                    st_s[c * TILE + r * kBlockThreads + tid] = pop_b[(size_t)c * a.n_pad + base_n + r * kBlockThreads + tid];
+            }
+    }
+
+    Real x[C];
+    Real tm = 0;          // f32: remaining time to the observation; f64: absolute time
+    uint32_t k = 0;       // events so far of the current particle
+    int r = -1, q = 0;
+    long long n_idx = 0;
+    bool active = false;
+    unsigned long long ev_local = 0, ovf_local = 0;
+
+    auto next_particle = [&]() {
+        active = false;
+        while (++r < ITEMS) {
+            q = r * kBlockThreads + tid;
+            n_idx = base_n + q;
+            if (n_idx < a.n) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    x[c] = (c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
+                tm = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;
+                k = 0;
+                active = true;
+                break;
+            }
+            lw_s[q] = -INFINITY;
+        }
+    };
+    next_particle();
+
+    while (active) {
+        const Philox4 w = stream_draw(a.key, (uint32_t)n_idx, gfilter, (uint32_t)a.t, kTagSim, k >> 1);
+        bool just_started = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (active && !just_started) {
+                // rate_function + cumsum! (src/hmm_particle_filter.jl:20-21)
+                Real cum[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    Real l1 = m.k1[e], l2 = m.k2[e];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        l1 += m.f1[e][c] * x[c];
+                        l2 += m.f2[e][c] * x[c];
+                    }
+                    Real rate = Arith<Real>::mul(Arith<Real>::mul(par[e], l1), l2);
+                    if (m.any_den && m.has_den[e]) {
+                        Real dn = m.kd[e];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) dn += m.dn[e][c] * x[c];
+                        rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
+                    }
+                    cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+                }
+                const Real rtot = cum[E - 1];
+                bool fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
+                bool ovf = false;
+                if (!fin) {
+                    if (k >= max_ev) {  // event cap: documented divergence, the reference loop is unbounded
+                        fin = true;
+                        ovf = true;
+                    } else {
+                        const uint32_t wa = h ? w.w2 : w.w0, wb = h ? w.w3 : w.w1;
+                        Real etc;
+                        if constexpr (kF32) {
+                            // time -= log(rand()) / R  (:23) tracked as remaining time; lg2.approx + rcp.approx on the XU pipe
+                            tm = fmaf(__log2f(u32_open_f32(wa)), __fdividef(0.693147180559945f, rtot), tm);
+                            fin = tm < 0.0f;  // `time > tmax && break` (:24)
+                            etc = u32_open_f32(wb) * rtot;
+                        } else {
+                            tm = tm - log(u32_open_f64(wa)) / rtot;
+                            fin = tm > t_obs;
+                            etc = __dmul_rn(u32_open_f64(wb), rtot);
+                        }
+                        if (!fin) {
+                            // choose_event (src/hmm_cmn.jl:4-10) + `ptemp .+= fn_transition(et)` (:26)
+                            Real dx[C];
+#pragma unroll
+                            for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
+#pragma unroll
+                            for (int i = E - 2; i >= 0; --i) {
+                                const bool hit = cum[i] > etc;
+#pragma unroll
+                                for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < C; ++c) x[c] += dx[c];
+                            ++k;
+                        }
+                    }
+                }
+                if (fin) {
+                    // exp(obs_model(...)) is deferred: store log g (src/hmm_examples.jl:63-65)
+                    Real xs = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xs += m.xmask[c] * x[c];
+                    const double d = ysum - (double)xs;
+                    lw_s[q] = ovf ? -INFINITY : m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (c < a.n_comp) st_s[c * TILE + q] = (int)x[c];
+                    ev_local += k;
+                    ovf_local += ovf ? 1u : 0u;
+                    next_particle();
+                    just_started = true;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // write back states and log weights (coalesced)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if (c < a.n_comp) {
+#pragma unroll
+            for (int rr = 0; rr < ITEMS; ++rr) {
+                const int qq = rr * kBlockThreads + tid;
+                if (base_n + qq < a.n) pop_b[(size_t)c * a.n_pad + base_n + qq] = st_s[c * TILE + qq];
+            }
+        }
+    double* lw_b = a.logw + (size_t)b * a.n_pad + base_n;
+#pragma unroll
+    for (int rr = 0; rr < ITEMS; ++rr) lw_b[rr * kBlockThreads + tid] = lw_s[rr * kBlockThreads + tid];
+
+    // event statistics: one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
+        ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
+    }
+    if ((tid & 31) == 0) {
+        if (ev_local) atomicAdd(a.ev_count, ev_local);
+        if (ovf_local) atomicAdd(a.ovf_count, ovf_local);
+    }
+
+    // tile partials (m_b, s_b) in the blocked item order of the scan tree
+    double it[ITEMS], av[ITEMS], incl[ITEMS], excl[ITEMS];
+    double mloc = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < ITEMS; ++kk) {
+        it[kk] = lw_s[tid * ITEMS + kk];
+        mloc = fmax(mloc, it[kk]);
+    }
+    const double m_b = block_max(mloc, warp_scratch);
+    const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
+#pragma unroll
+    for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
+    const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
+
+    if (tid == 0) {
+        a.tile_m[(size_t)b * a.ntiles + tile] = m_b;
+        a.tile_s[(size_t)b * a.ntiles + tile] = s_b;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&a.tile_counter[b], 1u);
+        is_last_s = (ticket == (unsigned int)(a.ntiles - 1));
+    }
+    __syncthreads();
+    if (!is_last_s) return;
+
+    // ---- last tile of this filter: combine partials -> M, S, tile scale factors and tile offsets, log-lik increment
+    __threadfence();
+    const double* tm_b = a.tile_m + (size_t)b * a.ntiles;
+    const double* ts_b = a.tile_s + (size_t)b * a.ntiles;
+    double mm = -INFINITY;
+    for (int i = tid; i < a.ntiles; i += kBlockThreads) mm = fmax(mm, __ldcg(tm_b + i));
+    const double big_m = block_max(mm, warp_scratch);
+    double carry = 0.0;
+    for (int c0 = 0; c0 < a.ntiles; c0 += TILE) {
+        double tb[ITEMS];
+#pragma unroll
+        for (int kk = 0; kk < ITEMS; ++kk) {
+            const int i = c0 + tid * ITEMS + kk;
+            tb[kk] = 0.0;
+            if (i < a.ntiles) {
+                const double mb = __ldcg(tm_b + i);
+                const double f = (mb == -INFINITY) ? 0.0 : exp(mb - big_m);
+                a.tile_f[(size_t)b * a.ntiles + i] = f;
+                tb[kk] = __dmul_rn(f, __ldcg(ts_b + i));
+            }
+        }
+        const double tot = tile_scan<ITEMS>(tb, incl, excl, warp_scratch);
+#pragma unroll
+        for (int kk = 0; kk < ITEMS; ++kk) {
+            const int i = c0 + tid * ITEMS + kk;
+            if (i < a.ntiles) a.tile_off[(size_t)b * (a.ntiles + 1) + i] = __dadd_rn(carry, excl[kk]);
+        }
+        carry = __dadd_rn(carry, tot);
+    }
+    if (tid == 0) {
+        a.tile_off[(size_t)b * (a.ntiles + 1) + a.ntiles] = carry;
+        a.filt_s[b] = carry;
+        a.filt_m[b] = big_m;
+        if (a.has_lik) a.ll_acc[b] += big_m + log(carry / (double)a.n);  // log(cum_weight[end] / N) (:60), as LSE
+        a.tile_counter[b] = 0u;
+    }
+}
+
+// ---- host-side model padding and dispatch ---------------------------------------------------------------------
+template <typename Real, int C, int E>
+static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
+    const dpomp_model_desc& d = mh.desc;
+    DevModel<Real, C, E> m{};
+    const int e_real = d.n_events;
+    m.any_den = 0;
+    for (int e = 0; e < E; ++e) {
+        const int src = e < e_real ? e : e_real - 1;  // padded events: zero rate, transition row of the last real event
+        const bool pad = e >= e_real;
+        m.par[e] = pad ? -1 : d.rate_par[src];
+        m.k1[e] = pad ? (Real)0 : (Real)d.rate_k1[src];
+        m.k2[e] = pad ? (Real)0 : (Real)d.rate_k2[src];
+        m.kd[e] = pad ? (Real)1 : (Real)d.rate_kd[src];
+        m.has_den[e] = pad ? 0 : d.rate_has_den[src];
+        m.any_den |= m.has_den[e];
+        for (int c = 0; c < C; ++c) {
+            const bool cpad = c >= d.n_compartments;
+            m.f1[e][c] = (pad || cpad) ? (Real)0 : (Real)d.rate_f1[src][c];
+            m.f2[e][c] = (pad || cpad) ? (Real)0 : (Real)d.rate_f2[src][c];
+            m.dn[e][c] = (pad || cpad) ? (Real)0 : (Real)d.rate_dn[src][c];
+            m.trans[e][c] = cpad ? (Real)0 : (Real)d.trans[src][c];
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+        const bool cpad = c >= d.n_compartments;
+        m.xmask[c] = cpad ? (Real)0 : (Real)d.obs_xmask[c];
+        m.ic[c] = cpad ? 0 : (int)d.initial_condition[c];
+    }
+    m.obs_tmp1 = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * d.obs_sigma));
+    m.obs_tmp2 = 2.0 * d.obs_sigma * d.obs_sigma;
+    m.t0_index = d.t0_index;
+    m.n_params = d.n_params;
+    return m;
+}
+
+template <typename Real, int C, int E, int ITEMS>
+static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream) {
+    constexpr int TILE = kBlockThreads * ITEMS;
+    const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
+    const size_t smem = (size_t)TILE * (sizeof(double) + C * sizeof(int));
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    kern<<<(unsigned)(a.n_filters * a.ntiles), kBlockThreads, smem, stream>>>(m, a);
+    return cudaGetLastError();
+}
+
+// the instantiated (C, E) shapes; a model runs on the smallest shape that covers it
+#define DPOMP_SIM_SHAPES(X) X(2, 1) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(4, 3) X(4, 6) X(8, 8)
+
+template <typename Real>
+static cudaError_t launch_sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStream_t stream) {
+    const int c = mh.desc.n_compartments, e = mh.desc.n_events;
+#define X(CC, EE)                                                                             \
+    if (c <= CC && e <= EE) {                                                                 \
+        return items == 1 ? launch_sim_inst<Real, CC, EE, 1>(mh, a, stream)                   \
+                          : launch_sim_inst<Real, CC, EE, 4>(mh, a, stream);                  \
+    }
+    DPOMP_SIM_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dpomp

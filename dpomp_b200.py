@@ -1,0 +1,11 @@
+"""Import shim: loads the package directory `discretepomp.jl_b200/` (not a valid Python identifier) as `dpomp_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "discretepomp.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    "dpomp_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["dpomp_b200"] = _mod
+_spec.loader.exec_module(_mod)

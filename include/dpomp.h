@@ -1,0 +1,185 @@
+/*
+ * dpomp.h -- C ABI of libdpomp: the B200 (sm_100a) particle-filter hot path of DiscretePOMP.jl.
+ *
+ * Every entry point below replaces a plain Julia function value of the reference (there is no FFI in the
+ * reference; the Julia shim in discretepomp.jl_b200/julia/ binds these with `ccall`, the Python host in
+ * discretepomp.jl_b200/ binds them with ctypes).  Citations are path:line under the reference repository.
+ *
+ * Conventions
+ *   - every function returns DPOMP_OK (0) or a negative dpomp_status; nothing throws across the ABI;
+ *     dpomp_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns all host buffers; the library owns device memory behind opaque handles.
+ *   - a handle is bound to one device and one stream and is NOT thread-safe; distinct handles are.
+ *   - all index arrays crossing the ABI are 1-based int64 (Julia convention); observation indices
+ *     ymin/ymax are 1-based inclusive exactly as in partial_log_likelihood! (src/hmm_particle_filter.jl:39).
+ *   - every call is synchronous on return unless its name ends in _async.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with DPOMP_ERR_CUDA.
+ */
+#ifndef DPOMP_H
+#define DPOMP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPOMP_MAX_COMPARTMENTS 8
+#define DPOMP_MAX_EVENTS 8
+#define DPOMP_MAX_PARAMS 16
+#define DPOMP_MAX_OBS_VALS 8
+
+typedef enum dpomp_status {
+    DPOMP_OK = 0,
+    DPOMP_ERR_ARG = -1,      /* bad argument (null pointer, out-of-range size, unknown enum)        */
+    DPOMP_ERR_CUDA = -2,     /* CUDA runtime failure / no device (message has the CUDA error string) */
+    DPOMP_ERR_MODEL = -3,    /* model descriptor not representable as a device rate table             */
+    DPOMP_ERR_STATE = -4,    /* call sequence error (e.g. partial with ymin>1 on a never-run filter)  */
+    DPOMP_ERR_OVERFLOW = -5  /* reserved; event-cap overflow is reported by dpomp_pf_overflow_count    */
+} dpomp_status;
+
+/* rs_type as in get_log_pdf_fn (src/hmm_particle_filter.jl:87-94): 1 systematic, 2 stratified, 3 multinomial */
+#define DPOMP_RS_SYSTEMATIC 1
+#define DPOMP_RS_STRATIFIED 2
+#define DPOMP_RS_MULTINOMIAL 3
+
+/* arithmetic of the Gillespie event loop.  Weights, cumulative weights and log-likelihoods are always f64. */
+#define DPOMP_SIM_F32 0 /* rates/time in f32, lg2.approx + rcp on the XU pipe (default, fast)          */
+#define DPOMP_SIM_F64 1 /* rates/time in f64 with the reference's expressions: draw-for-draw oracle parity */
+
+/*
+ * Device rate table: what the reference's closures rate_function / fn_transition / obs_model
+ * (src/hmm_structs.jl:119-130; predefined models src/hmm_examples.jl:103-208) are compiled to.
+ *
+ *   rate[e](x, theta) = P * L1 * L2 / D
+ *       P  = rate_par[e] >= 0 ? theta[rate_par[e]] : 1          (0-based parameter index)
+ *       L1 = rate_k1[e] + sum_c rate_f1[e][c] * x[c]
+ *       L2 = rate_k2[e] + sum_c rate_f2[e][c] * x[c]
+ *       D  = rate_has_den[e] ? rate_kd[e] + sum_c rate_dn[e][c] * x[c] : 1   (D == 0  =>  rate 0)
+ *   evaluated as ((P*L1)*L2)/D, the association of the reference's mass-action expressions
+ *   (src/hmm_examples.jl:107-121,126-144,149-154).
+ *
+ *   transition: x += trans[e][:]  (row = event; Julia's m_transition is column-major E x C, the shim transposes)
+ *
+ *   observation model (Gaussian, partial_gaussian_obs_model src/hmm_examples.jl:59-67):
+ *       log g = log(1/(sqrt(2 pi) sigma)) - (sum_v obs_ymask[v]*y.val[v] - sum_c obs_xmask[c]*x[c])^2 / (2 sigma^2)
+ */
+typedef struct dpomp_model_desc {
+    int32_t n_compartments;                                   /* C, 1..DPOMP_MAX_COMPARTMENTS */
+    int32_t n_events;                                         /* E, 1..DPOMP_MAX_EVENTS       */
+    int32_t n_params;                                         /* length of theta              */
+    int32_t t0_index;                                         /* 1-based index into theta of the initial time, 0 = fixed 0.0 (src/hmm_structs.jl:129) */
+    int32_t rate_par[DPOMP_MAX_EVENTS];
+    int32_t rate_f1[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS];
+    int32_t rate_k1[DPOMP_MAX_EVENTS];
+    int32_t rate_f2[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS];
+    int32_t rate_k2[DPOMP_MAX_EVENTS];
+    int32_t rate_has_den[DPOMP_MAX_EVENTS];
+    int32_t rate_dn[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS];
+    int32_t rate_kd[DPOMP_MAX_EVENTS];
+    int32_t trans[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS];
+    int64_t initial_condition[DPOMP_MAX_COMPARTMENTS];       /* fn_initial_condition() (src/DiscretePOMP.jl:96-99) */
+    double obs_sigma;
+    int32_t obs_xmask[DPOMP_MAX_COMPARTMENTS];
+    int32_t n_obs_vals;                                       /* V = length(y.val), 1..DPOMP_MAX_OBS_VALS */
+    int32_t obs_ymask[DPOMP_MAX_OBS_VALS];
+    /* observations (struct Observation, src/hmm_structs.jl:30-35), sorted by time */
+    int32_t n_obs;                                            /* T */
+    const double* obs_time;                                   /* [T]   */
+    const int32_t* obs_id;                                    /* [T]   <1: not a likelihood/resampling step */
+    const int64_t* obs_val;                                   /* [T*V] row t = y[t].val */
+} dpomp_model_desc;
+
+typedef struct dpomp_model dpomp_model;
+typedef struct dpomp_pf dpomp_pf;
+
+const char* dpomp_last_error(void);
+/* library/ABI version and the geometry of the deterministic scan tree (needed by the parity oracle) */
+int dpomp_version(void);
+int dpomp_device_count(int* out_count);
+
+/* replaces get_private_model (src/DiscretePOMP.jl:96-99): validates the descriptor, copies observations */
+int dpomp_model_create(const dpomp_model_desc* desc, dpomp_model** out_model);
+int dpomp_model_destroy(dpomp_model* model);
+
+/*
+ * A batch of n_batch independent bootstrap filters of n_particles each on one device
+ * (the `pop::Array{Int64,2}` workspaces of estimate_likelihood src/hmm_particle_filter.jl:79-84 and of
+ * run_pibis src/hmm_ibis.jl:26-35, resident in HBM as int32 SoA [batch][compartment][particle]).
+ * seed selects the Philox4x32-10 key stream; device < 0 = current device.
+ */
+int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_batch, int32_t rs_type,
+                    uint64_t seed, int32_t device, dpomp_pf** out_pf);
+int dpomp_pf_destroy(dpomp_pf* pf);
+
+/* options (all optional; defaults in parentheses) */
+int dpomp_pf_set_sim_precision(dpomp_pf* pf, int32_t sim_precision);  /* (DPOMP_SIM_F32) */
+int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t max_events);        /* per particle per interval (1<<20); the
+                                                                         reference PF has no cap (src/hmm_particle_filter.jl:19-27) */
+int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t batch_offset);    /* global id of local filter 0 (0): makes the
+                                                                         random streams independent of the sharding  */
+int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key);              /* force the Philox key of the NEXT call (tests) */
+int dpomp_pf_get_stream_key(dpomp_pf* pf, uint64_t* out_key);         /* key the next fresh call will use            */
+int dpomp_pf_geometry(const dpomp_pf* pf, int32_t* out_tile, int32_t* out_items_per_thread);
+
+/*
+ * estimate_likelihood (src/hmm_particle_filter.jl:79-84), batched: theta is n_params x n_batch_used
+ * column-major (one theta vector per filter, contiguous), out_ll[n_batch_used].
+ */
+int dpomp_pf_loglik(dpomp_pf* pf, const double* theta, int32_t n_batch_used, double* out_ll);
+
+/*
+ * partial_log_likelihood! (src/hmm_particle_filter.jl:39-76), batched over filters with device-resident
+ * populations: runs observations ymin..ymax (1-based, inclusive).  ymin == 1 re-initialises the populations
+ * from the initial condition (t_prev = 0 or theta[t0_index]); otherwise continues from the stored state.
+ * Resampling after observation i happens iff obs_id[i] > 0 and i < T (global last), as in the reference.
+ * out_gx[n_batch_used] receives the log-likelihood increments.
+ */
+int dpomp_pf_partial(dpomp_pf* pf, const double* theta, int32_t n_batch_used, int32_t ymin, int32_t ymax,
+                     double* out_gx);
+
+/* outer-layer resample gather (src/hmm_ibis.jl:71-79): filter p <- filter nidx[p] (1-based), p = 1..n */
+int dpomp_pf_permute(dpomp_pf* pf, const int64_t* nidx, int32_t n);
+/* accepted mutation proposals (src/hmm_ibis.jl:105-108): dst filter dst_slots[k] <- src filter src_slots[k] (1-based) */
+int dpomp_pf_copy_filters(dpomp_pf* dst, const dpomp_pf* src, const int64_t* dst_slots,
+                          const int64_t* src_slots, int32_t n);
+/* read back one population as the reference's Matrix{Int64} (n_particles x C, column-major) */
+int dpomp_pf_get_pop(dpomp_pf* pf, int32_t b /*1-based*/, int64_t* out);
+int dpomp_pf_set_pop(dpomp_pf* pf, int32_t b /*1-based*/, const int64_t* in);
+/* diagnostics of the LAST partial/loglik call: per-particle log weights and ancestors (1-based) of the last
+ * observation processed, for filter b; out_anc may be NULL.  Ancestors are valid only if that observation resampled. */
+int dpomp_pf_get_last_logw(dpomp_pf* pf, int32_t b, double* out_logw);
+int dpomp_pf_get_last_ancestors(dpomp_pf* pf, int32_t b, int64_t* out_anc);
+int dpomp_pf_set_record_ancestors(dpomp_pf* pf, int32_t on);
+/* number of (filter, particle, interval) simulations that hit the event cap since creation (sticky) */
+int dpomp_pf_overflow_count(dpomp_pf* pf, int64_t* out_count);
+/* total Gillespie events simulated by the last call (all filters) -- for events/s reporting */
+int dpomp_pf_last_event_count(dpomp_pf* pf, int64_t* out_events);
+/* device time (ms, CUDA events on the handle's stream) and kernel launches of the last call */
+int dpomp_pf_last_timing(dpomp_pf* pf, float* out_ms, int32_t* out_launches);
+
+/* migration of whole filters between devices (multi-GPU SMC^2): pack / unpack the int32 SoA state of the
+ * listed filters (1-based) to / from a caller-provided DEVICE buffer of n * C * n_particles int32 */
+int dpomp_pf_export_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, void* device_dst);
+int dpomp_pf_import_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, const void* device_src);
+
+/* device-resident variant used by bench.py's kernel-only arm: theta and out_ll are DEVICE pointers,
+ * nothing crosses PCIe inside the call; synchronises the handle's stream before returning */
+int dpomp_pf_loglik_device(dpomp_pf* pf, const double* theta_dev, int32_t n_batch_used, double* out_ll_dev);
+
+/*
+ * Bit-exactness hook for the resampling searches (host buffers).
+ *   on_cumulative = 1: `w` is already cumulative  -> rsp_* semantics (src/hmm_pf_resample.jl:24-42, and the
+ *                      intended semantics of the broken rsp_stratified/rsp_multinomial :46-63, :5-20)
+ *   on_cumulative = 0: `w` are raw weights, cumulated sequentially in f64 on the host exactly as
+ *                      cumsum/cumsum! -> rs_* semantics (src/hmm_resample.jl:4-20,44-62,66-83)
+ *   u: the raw rand() draws the reference would consume: 1 (systematic), n_out (stratified, n_out == n), n_out (multinomial)
+ *   out_idx[n_out]: 1-based ancestors.  The search itself runs on the GPU.
+ */
+int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double* w, int64_t n, const double* u,
+                           int64_t n_u, int64_t n_out, int64_t* out_idx, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPOMP_H */

@@ -1,0 +1,558 @@
+/*
+ * dpomp_oracle.c -- CPU restatement of DiscretePOMP.jl's particle-filter hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product (libdpomp.so) never links or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" at function level -- the reference (pure Julia; no Julia toolchain in this
+ * image) ships no known-answer vectors for this path.  The restatement is pinned only to
+ * Monte-Carlo accuracy by the reference's seeded end-to-end numbers (test/runtests.jl:35,51) and the surveyor's
+ * anchors (PF log-lik -15.69 +- 0.01 on data/pooley.csv); tests/test_oracle_anchors.py checks those.
+ *
+ * Each function cites the reference file:line it follows (paths relative to the reference repository).
+ * Uniform random numbers come from Philox4x32-10 with the counter layout of DESIGN.md ("random streams") so
+ * that the GPU path and this oracle consume IDENTICAL draws; the reference uses Julia's global RNG, whose
+ * stream is version dependent, so draw-level parity with the reference itself is impossible.
+ *
+ * Two arithmetic modes for the weight normalisation / resampling part:
+ *   ORC_MODE_LITERAL (0): exactly the reference: running linear-domain cumulative sum of exp(log g),
+ *                         log(cw[end]/N), sequential walk `while u[i] > cw[j]` (src/hmm_particle_filter.jl:29-30,60,
+ *                         src/hmm_pf_resample.jl:24-42).
+ *   ORC_MODE_DEVICE  (1): same mathematics evaluated in the device's deterministic order: log-sum-exp with the
+ *                         tile-relative scaling, the fixed scan tree and the counting form of the search
+ *                         (DESIGN.md "deterministic scan tree").  Used for bit-exact ancestor parity.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/dpomp.h"
+
+#define ORC_MODE_LITERAL 0
+#define ORC_MODE_DEVICE 1
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants).                                         */
+/* ------------------------------------------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4]) {
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define ORC_TAG_SIM 0u
+#define ORC_TAG_RESAMPLE 1u
+
+static inline void stream_draw(uint64_t key, uint32_t particle, uint32_t filter, uint32_t obs, uint32_t tag,
+                               uint32_t block, uint32_t out[4]) {
+    uint32_t ctr[4] = {particle, filter, obs, (tag << 30) | block};
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    orc_philox4x32_10(ctr, k, out);
+}
+static inline double u32_open(uint32_t w) { return ((double)w + 0.5) * 0x1.0p-32; }               /* (0,1)  */
+static inline double u53(uint32_t hi, uint32_t lo) {                                                /* [0,1)  */
+    return (double)(((uint64_t)hi << 21) | (uint64_t)(lo >> 11)) * 0x1.0p-53;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Model closures.                                                                                              */
+/* ------------------------------------------------------------------------------------------------------------ */
+/* rate_function + cumsum! (src/hmm_particle_filter.jl:20-21; rate expressions src/hmm_examples.jl:103-168) */
+static void cum_rates(const dpomp_model_desc* m, const double* th, const int64_t* x, double* cum) {
+    double acc = 0.0;
+    for (int e = 0; e < m->n_events; ++e) {
+        int64_t l1 = m->rate_k1[e], l2 = m->rate_k2[e], dn = m->rate_kd[e];
+        for (int c = 0; c < m->n_compartments; ++c) {
+            l1 += (int64_t)m->rate_f1[e][c] * x[c];
+            l2 += (int64_t)m->rate_f2[e][c] * x[c];
+            dn += (int64_t)m->rate_dn[e][c] * x[c];
+        }
+        double p = m->rate_par[e] >= 0 ? th[m->rate_par[e]] : 1.0;
+        double r = (p * (double)l1) * (double)l2;
+        if (m->rate_has_den[e]) r = (dn == 0) ? 0.0 : r / (double)dn; /* reference gives NaN on 0/0 and hangs */
+        acc = (e == 0) ? r : acc + r;
+        cum[e] = acc;
+    }
+}
+
+/* choose_event (src/hmm_cmn.jl:4-10): 0-based event */
+static int choose_event(const double* cum, int n_events, double u) {
+    double etc = u * cum[n_events - 1];
+    for (int i = 0; i < n_events - 1; ++i)
+        if (cum[i] > etc) return i;
+    return n_events - 1;
+}
+
+/* partial_gaussian_obs_model / gom2 (src/hmm_examples.jl:59-67) */
+static double obs_model(const dpomp_model_desc* m, int t, const int64_t* x) {
+    double tmp1 = log(1.0 / (sqrt(2.0 * M_PI) * m->obs_sigma));
+    double tmp2 = 2.0 * m->obs_sigma * m->obs_sigma;
+    int64_t ys = 0, xs = 0;
+    for (int v = 0; v < m->n_obs_vals; ++v) ys += (int64_t)m->obs_ymask[v] * m->obs_val[(int64_t)t * m->n_obs_vals + v];
+    for (int c = 0; c < m->n_compartments; ++c) xs += (int64_t)m->obs_xmask[c] * x[c];
+    int64_t d = ys - xs;
+    return tmp1 - ((double)(d * d) / tmp2);
+}
+
+/* the event loop of iterate_particles! (src/hmm_particle_filter.jl:19-27) for ONE particle over (t, tmax].
+ * Event k uses Philox block k/2, words 2(k%2) (waiting time) and 2(k%2)+1 (event type). */
+static int64_t sim_interval(const dpomp_model_desc* m, const double* th, int64_t* x, double time, double tmax,
+                            uint64_t key, uint32_t particle, uint32_t filter, uint32_t obs, int64_t max_events,
+                            int* overflow) {
+    double cum[DPOMP_MAX_EVENTS];
+    uint32_t w[4] = {0, 0, 0, 0};
+    int64_t k = 0;
+    *overflow = 0;
+    for (;;) {
+        cum_rates(m, th, x, cum);
+        if (!(cum[m->n_events - 1] > 0.0)) break; /* `== 0.0 && break` (:22); rates are >= 0 here */
+        if (k >= max_events) { *overflow = 1; break; } /* event cap: documented divergence (no cap in the reference) */
+        if ((k & 1) == 0) stream_draw(key, particle, filter, obs, ORC_TAG_SIM, (uint32_t)(k >> 1), w);
+        double u_wait = u32_open(w[2 * (k & 1)]), u_evt = u32_open(w[2 * (k & 1) + 1]);
+        time -= log(u_wait) / cum[m->n_events - 1]; /* :23 */
+        if (time > tmax) break;                     /* :24 */
+        int e = choose_event(cum, m->n_events, u_evt);
+        for (int c = 0; c < m->n_compartments; ++c) x[c] += m->trans[e][c]; /* :26 */
+        ++k;
+    }
+    return k;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Resamplers on raw weights: rs_* (src/hmm_resample.jl).  `u` holds the rand() draws in consumption order.      */
+/* out: 1-based ancestors.  w is cumulated in place like cumsum!/cumsum.                                         */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void walk_search(const double* cw, int64_t n, const double* u, int64_t n_out, int64_t* out) {
+    /* `j = 1; for i: while u[i] > cw[j] j += 1; output[i] = j` (src/hmm_resample.jl:55-60, src/hmm_pf_resample.jl:34-40) */
+    int64_t j = 0;
+    for (int64_t i = 0; i < n_out; ++i) {
+        while (j < n - 1 && u[i] > cw[j]) ++j; /* j<n-1 guard: the reference would throw a BoundsError instead */
+        out[i] = j + 1;
+    }
+}
+
+/* rs_systematic (src/hmm_resample.jl:44-62) / rsp_systematic (src/hmm_pf_resample.jl:24-42) given cumulative weights */
+void orc_search_systematic(const double* cw, int64_t n, double r, int64_t* out) {
+    double* u = (double*)malloc(sizeof(double) * (size_t)n);
+    u[0] = r / (double)n;
+    for (int64_t i = 1; i < n; ++i) u[i] = u[0] + ((double)i / (double)n);
+    for (int64_t i = 0; i < n; ++i) u[i] *= cw[n - 1];
+    walk_search(cw, n, u, n, out);
+    free(u);
+}
+/* rs_stratified (src/hmm_resample.jl:66-83); also the intended rsp_stratified (src/hmm_pf_resample.jl:46-63, broken F6) */
+void orc_search_stratified(const double* cw, int64_t n, const double* r, int64_t* out) {
+    double* u = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) u[i] = r[i] / (double)n;
+    for (int64_t i = 0; i < n; ++i) u[i] += ((double)i / (double)n);
+    for (int64_t i = 0; i < n; ++i) u[i] *= cw[n - 1];
+    walk_search(cw, n, u, n, out);
+    free(u);
+}
+/* rs_multinomial (src/hmm_resample.jl:4-20); also the intended rsp_multinomial (src/hmm_pf_resample.jl:5-20, broken F6) */
+void orc_search_multinomial(const double* cw, int64_t n, const double* r, int64_t n_out, int64_t* out) {
+    for (int64_t p = 0; p < n_out; ++p) {
+        out[p] = n;
+        double chs = r[p] * cw[n - 1];
+        for (int64_t p2 = 0; p2 < n - 1; ++p2) {
+            if (chs < cw[p2]) { out[p] = p2 + 1; break; }
+        }
+    }
+}
+static void cumsum_inplace(double* w, int64_t n) {
+    for (int64_t i = 1; i < n; ++i) w[i] = w[i - 1] + w[i];
+}
+/* rs_type 1/2/3 on RAW weights (w is overwritten with its cumulative sum, as in the reference) */
+void orc_rs(int rs_type, double* w, int64_t n, const double* r, int64_t n_out, int64_t* out) {
+    cumsum_inplace(w, n);
+    if (rs_type == DPOMP_RS_STRATIFIED) orc_search_stratified(w, n, r, out);
+    else if (rs_type == DPOMP_RS_MULTINOMIAL) orc_search_multinomial(w, n, r, n_out, out);
+    else orc_search_systematic(w, n, r[0], out);
+}
+/* same searches on ALREADY cumulative weights (rsp_* semantics) */
+void orc_rsp(int rs_type, const double* cw, int64_t n, const double* r, int64_t n_out, int64_t* out) {
+    if (rs_type == DPOMP_RS_STRATIFIED) orc_search_stratified(cw, n, r, out);
+    else if (rs_type == DPOMP_RS_MULTINOMIAL) orc_search_multinomial(cw, n, r, n_out, out);
+    else orc_search_systematic(cw, n, r[0], out);
+}
+
+/* compute_ess (src/hmm_particle_filter.jl:4-6) */
+double orc_compute_ess(const double* w, int64_t n) {
+    double s = 0.0, s2 = 0.0;
+    for (int64_t i = 0; i < n; ++i) { s += w[i]; s2 += w[i] * w[i]; }
+    return s * s / s2;
+}
+
+/* compute_is_mu_covar! (src/cmn.jl:91-99); theta is n_theta x n column-major */
+void orc_compute_is_mu_covar(double* mu, double* cv, const double* theta, const double* w, int n_theta, int64_t n) {
+    double sw = 0.0;
+    for (int64_t p = 0; p < n; ++p) sw += w[p];
+    for (int i = 0; i < n_theta; ++i) {
+        double a = 0.0;
+        for (int64_t p = 0; p < n; ++p) a += w[p] * theta[p * n_theta + i];
+        mu[i] = a / sw;
+        double v = 0.0;
+        for (int64_t p = 0; p < n; ++p) { double d = theta[p * n_theta + i] - mu[i]; v += w[p] * (d * d); }
+        cv[i * n_theta + i] = v / sw;
+        for (int j = 0; j < i; ++j) {
+            double c = 0.0;
+            for (int64_t p = 0; p < n; ++p) c += w[p] * (theta[p * n_theta + i] - mu[i]) * (theta[p * n_theta + j] - mu[j]);
+            cv[i * n_theta + j] = cv[j * n_theta + i] = c / sw;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Device-order arithmetic (ORC_MODE_DEVICE): the fixed scan tree of DESIGN.md.                                  */
+/* A tile holds `tile` values; lane l of warp w owns items (w*32+l)*items .. +items-1.                           */
+/* ------------------------------------------------------------------------------------------------------------ */
+/* inclusive (incl) and exclusive (excl) tile-local scans and the tile total, in the device's association order */
+static double tile_scan(const double* a, int tile, int items, double* incl, double* excl) {
+    int nwarps = tile / (32 * items);
+    double warp_prefix = 0.0, total = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+        double lane_tot[32], scan[32];
+        for (int l = 0; l < 32; ++l) {
+            const double* q = a + ((size_t)w * 32 + l) * items;
+            double r = q[0];
+            for (int k = 1; k < items; ++k) r = r + q[k];
+            lane_tot[l] = r;
+            scan[l] = r;
+        }
+        for (int d = 1; d < 32; d <<= 1) { /* Kogge-Stone over lanes, as __shfl_up_sync rounds */
+            double nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = (l >= d) ? scan[l - d] + scan[l] : scan[l];
+            memcpy(scan, nxt, sizeof(scan));
+        }
+        for (int l = 0; l < 32; ++l) {
+            double base = warp_prefix + (l > 0 ? scan[l - 1] : 0.0);
+            const double* q = a + ((size_t)w * 32 + l) * items;
+            double r = 0.0;
+            for (int k = 0; k < items; ++k) {
+                size_t idx = ((size_t)w * 32 + l) * items + k;
+                if (excl) excl[idx] = base + r;
+                r = (k == 0) ? q[0] : r + q[k];
+                if (incl) incl[idx] = base + r;
+            }
+        }
+        total = warp_prefix + scan[31];
+        warp_prefix = total;
+        (void)lane_tot;
+    }
+    return total;
+}
+
+typedef struct {
+    int rs_type;
+    int64_t n;
+    double s;      /* grand total (cw[end]) */
+    double r1;     /* systematic: the single rand() */
+    uint64_t key;  /* stratified: per-offspring draws */
+    uint32_t filter, obs;
+} ecount_ctx;
+
+static inline double strat_draw(const ecount_ctx* c, int64_t i0 /*0-based offspring*/) {
+    uint32_t w[4];
+    stream_draw(c->key, (uint32_t)i0, c->filter, c->obs, ORC_TAG_RESAMPLE, 1u, w);
+    return u53(w[0], w[1]);
+}
+/* u_i of rsp_systematic / rs_stratified for 1-based i, exactly the reference's expression order */
+static inline double u_of(const ecount_ctx* c, int64_t i) {
+    double n = (double)c->n;
+    if (c->rs_type == DPOMP_RS_STRATIFIED) return ((strat_draw(c, i - 1) / n) + ((double)(i - 1) / n)) * c->s;
+    return ((c->r1 / n) + ((double)(i - 1) / n)) * c->s;
+}
+/* E(v) = #{ i in 1..n : u_i <= v }  (u_i is non-decreasing in i) */
+static int64_t ecount(const ecount_ctx* c, double v) {
+    if (!(c->s > 0.0)) return c->n;
+    double n = (double)c->n;
+    double g = (c->rs_type == DPOMP_RS_STRATIFIED) ? floor((v / c->s) * n) : floor(((v / c->s) - (c->r1 / n)) * n) + 1.0;
+    if (!(g >= 0.0)) g = 0.0;
+    if (g > n) g = n;
+    int64_t e = (int64_t)g;
+    while (e < c->n && u_of(c, e + 1) <= v) ++e;
+    while (e > 0 && u_of(c, e) > v) --e;
+    return e;
+}
+
+/* normalise + resample one filter in device order.  logw[n] -> returns log-lik increment; anc (1-based, may be NULL
+ * when do_resample == 0). */
+static double device_normalise_resample(const double* logw, int64_t n, int tile, int items, int do_resample,
+                                        int rs_type, uint64_t key, uint32_t filter, uint32_t obs, int64_t* anc) {
+    int64_t ntiles = (n + tile - 1) / tile;
+    double* a = (double*)malloc(sizeof(double) * (size_t)tile);
+    double* incl = (double*)malloc(sizeof(double) * (size_t)tile);
+    double* m_b = (double*)malloc(sizeof(double) * (size_t)ntiles);
+    double* s_b = (double*)malloc(sizeof(double) * (size_t)ntiles);
+    double* f_b = (double*)malloc(sizeof(double) * (size_t)ntiles);
+    double* off = (double*)malloc(sizeof(double) * (size_t)(ntiles + 1));
+    double big_m = -INFINITY;
+    for (int64_t b = 0; b < ntiles; ++b) {
+        double mb = -INFINITY;
+        for (int q = 0; q < tile; ++q) {
+            int64_t p = b * tile + q;
+            if (p < n && logw[p] > mb) mb = logw[p];
+        }
+        m_b[b] = mb;
+        double ref = (mb == -INFINITY) ? 0.0 : mb;
+        for (int q = 0; q < tile; ++q) {
+            int64_t p = b * tile + q;
+            a[q] = (p < n && logw[p] != -INFINITY) ? exp(logw[p] - ref) : 0.0;
+        }
+        s_b[b] = tile_scan(a, tile, items, NULL, NULL);
+        if (mb > big_m) big_m = mb;
+    }
+    /* tile offsets: scan of T_b = f_b * s_b, chunks of `tile` chained sequentially */
+    double carry = 0.0;
+    {
+        double* tb = (double*)malloc(sizeof(double) * (size_t)tile);
+        double* ex = (double*)malloc(sizeof(double) * (size_t)tile);
+        for (int64_t c0 = 0; c0 < ntiles; c0 += tile) {
+            for (int q = 0; q < tile; ++q) {
+                int64_t b = c0 + q;
+                if (b < ntiles) {
+                    f_b[b] = (m_b[b] == -INFINITY) ? 0.0 : exp(m_b[b] - big_m);
+                    tb[q] = f_b[b] * s_b[b];
+                } else tb[q] = 0.0;
+            }
+            double tot = tile_scan(tb, tile, items, NULL, ex);
+            for (int q = 0; q < tile; ++q)
+                if (c0 + q < ntiles) off[c0 + q] = carry + ex[q];
+            carry = carry + tot;
+        }
+        free(tb); free(ex);
+    }
+    double big_s = carry;
+    off[ntiles] = big_s;
+    double ll = big_m + log(big_s / (double)n);
+    if (do_resample && rs_type != DPOMP_RS_MULTINOMIAL) {
+        uint32_t w4[4];
+        stream_draw(key, 0u, filter, obs, ORC_TAG_RESAMPLE, 0u, w4);
+        ecount_ctx ctx = {rs_type, n, big_s, u53(w4[0], w4[1]), key, filter, obs};
+        int64_t* e = (int64_t*)malloc(sizeof(int64_t) * (size_t)tile);
+        for (int64_t b = 0; b < ntiles; ++b) {
+            double ref = (m_b[b] == -INFINITY) ? 0.0 : m_b[b];
+            for (int q = 0; q < tile; ++q) {
+                int64_t p = b * tile + q;
+                a[q] = (p < n && logw[p] != -INFINITY) ? exp(logw[p] - ref) : 0.0;
+            }
+            tile_scan(a, tile, items, incl, NULL);
+            int64_t lo = (b == 0) ? 0 : ecount(&ctx, off[b]);
+            int64_t hi = (b == ntiles - 1) ? n : ecount(&ctx, off[b + 1]);
+            int64_t nvalid = (n - b * tile < tile) ? (n - b * tile) : tile;
+            for (int q = 0; q < nvalid; ++q) {
+                int64_t ev = ecount(&ctx, off[b] + f_b[b] * incl[q]);
+                if (ev < lo) ev = lo;
+                if (ev > hi) ev = hi;
+                e[q] = ev;
+            }
+            e[nvalid - 1] = hi;
+            int q = 0;
+            for (int64_t i = lo + 1; i <= hi; ++i) {
+                while (e[q] < i) ++q;
+                anc[i - 1] = b * tile + q + 1;
+            }
+        }
+        free(e);
+    } else if (do_resample) {
+        /* multinomial: offspring i draws chs = r_i * S; ancestor = first p2 < n with chs < cw[p2], else n
+         * (src/hmm_resample.jl:9-16), on the device-order cumulative weights */
+        double* cw = (double*)malloc(sizeof(double) * (size_t)n);
+        for (int64_t b = 0; b < ntiles; ++b) {
+            double ref = (m_b[b] == -INFINITY) ? 0.0 : m_b[b];
+            for (int q = 0; q < tile; ++q) {
+                int64_t p = b * tile + q;
+                a[q] = (p < n && logw[p] != -INFINITY) ? exp(logw[p] - ref) : 0.0;
+            }
+            tile_scan(a, tile, items, incl, NULL);
+            for (int q = 0; q < tile; ++q)
+                if (b * tile + q < n) cw[b * tile + q] = off[b] + f_b[b] * incl[q];
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            uint32_t w4[4];
+            stream_draw(key, (uint32_t)i, filter, obs, ORC_TAG_RESAMPLE, 1u, w4);
+            double chs = u53(w4[0], w4[1]) * big_s;
+            /* first p2 in [0, n-1) with chs < cw[p2]: cw is non-decreasing within a tile but tile seams may be off by
+             * an ulp, so search tiles by their offsets first exactly like the device does */
+            int64_t lo_t = 0, hi_t = ntiles; /* first tile whose END offset (off[b+1]) is > chs */
+            while (lo_t < hi_t) { int64_t mid = (lo_t + hi_t) / 2; if (chs < off[mid + 1]) hi_t = mid; else lo_t = mid + 1; }
+            int64_t res = n;
+            if (lo_t < ntiles) {
+                int64_t b = lo_t, base = b * tile;
+                int64_t nvalid = (n - base < tile) ? (n - base) : tile;
+                int64_t lo_q = 0, hi_q = nvalid;
+                while (lo_q < hi_q) { int64_t mid = (lo_q + hi_q) / 2; if (chs < cw[base + mid]) hi_q = mid; else lo_q = mid + 1; }
+                if (lo_q >= nvalid) lo_q = nvalid - 1; /* seam: chs < off[b+1] but not < last cw of the tile */
+                res = base + lo_q + 1;
+            }
+            if (res > n) res = n;
+            anc[i] = res;
+        }
+        free(cw);
+    }
+    free(a); free(incl); free(m_b); free(s_b); free(f_b); free(off);
+    return ll;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* partial_log_likelihood! (src/hmm_particle_filter.jl:39-76) with iterate_particles! (:9-33) inlined.           */
+/*   pop: n x C column-major int64 (the reference's Matrix{Int64}); ymin/ymax 1-based inclusive.                 */
+/*   threads: 1 = faithful single thread; >1 = OpenMP over particles (particles are independent given           */
+/*            counter-based draws; the running weight sum stays sequential).                                     */
+/*   Optional outputs (may be NULL): logw_last[n], anc_last[n] (1-based, of the last observation if it resampled)*/
+/* ------------------------------------------------------------------------------------------------------------ */
+int orc_pf_partial(const dpomp_model_desc* m, const double* theta, int64_t n, int64_t* pop, int ymin, int ymax,
+                   int rs_type, uint64_t key, uint32_t filter, int mode, int tile, int items, int64_t max_events,
+                   int threads, double* out_ll, double* logw_last, int64_t* anc_last, int64_t* n_events,
+                   int64_t* n_overflow) {
+    const int C = m->n_compartments;
+    double t_prev;
+    if (ymin == 1) { /* :41-45 */
+        for (int64_t p = 0; p < n; ++p)
+            for (int c = 0; c < C; ++c) pop[c * n + p] = m->initial_condition[c];
+        t_prev = (m->t0_index == 0) ? 0.0 : theta[m->t0_index - 1];
+    } else {
+        t_prev = m->obs_time[ymin - 2]; /* :47 */
+    }
+    int64_t* old_p = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n * C));
+    double* cw = (double*)malloc(sizeof(double) * (size_t)n);
+    double* lw = (double*)malloc(sizeof(double) * (size_t)n);
+    int64_t* anc = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    double output = 0.0;
+    int64_t ev_total = 0, ovf_total = 0;
+    (void)threads;
+    for (int oi = ymin; oi <= ymax; ++oi) { /* :54 */
+        const int t = oi - 1;
+        const double tmax = m->obs_time[t];
+        /* iterate_particles! (:9-33) */
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(+ : ev_total, ovf_total) if (threads > 1)
+        for (int64_t p = 0; p < n; ++p) {
+            int64_t x[DPOMP_MAX_COMPARTMENTS];
+            for (int c = 0; c < C; ++c) x[c] = pop[c * n + p];
+            int ovf = 0;
+            ev_total += sim_interval(m, theta, x, t_prev, tmax, key, (uint32_t)p, filter, (uint32_t)t, max_events, &ovf);
+            ovf_total += ovf;
+            lw[p] = ovf ? -INFINITY : obs_model(m, t, x);
+            for (int c = 0; c < C; ++c) pop[c * n + p] = x[c];
+        }
+        const int has_lik = m->obs_id[t] > 0;                    /* :58 */
+        const int do_rs = has_lik && (oi < m->n_obs);            /* :62 */
+        if (mode == ORC_MODE_LITERAL) {
+            double total = 0.0;
+            for (int64_t p = 0; p < n; ++p) { total += exp(lw[p]); cw[p] = total; } /* :29-30 */
+            if (has_lik) {
+                output += log(cw[n - 1] / (double)n);             /* :60 */
+                if (do_rs) {
+                    memcpy(old_p, pop, sizeof(int64_t) * (size_t)(n * C)); /* :66 */
+                    if (rs_type == DPOMP_RS_SYSTEMATIC) {
+                        uint32_t w4[4];
+                        stream_draw(key, 0u, filter, (uint32_t)t, ORC_TAG_RESAMPLE, 0u, w4);
+                        orc_search_systematic(cw, n, u53(w4[0], w4[1]), anc);
+                    } else {
+                        double* r = (double*)malloc(sizeof(double) * (size_t)n);
+                        for (int64_t i = 0; i < n; ++i) {
+                            uint32_t w4[4];
+                            stream_draw(key, (uint32_t)i, filter, (uint32_t)t, ORC_TAG_RESAMPLE, 1u, w4);
+                            r[i] = u53(w4[0], w4[1]);
+                        }
+                        if (rs_type == DPOMP_RS_STRATIFIED) orc_search_stratified(cw, n, r, anc);
+                        else orc_search_multinomial(cw, n, r, n, anc);
+                        free(r);
+                    }
+                }
+            }
+        } else {
+            double inc = device_normalise_resample(lw, n, tile, items, do_rs, rs_type, key, filter, (uint32_t)t, anc);
+            if (has_lik) output += inc;
+            if (do_rs) memcpy(old_p, pop, sizeof(int64_t) * (size_t)(n * C));
+        }
+        if (do_rs) { /* m_pop[i,:] .= old_p[j,:] (src/hmm_pf_resample.jl:38) */
+            for (int c = 0; c < C; ++c)
+                for (int64_t i = 0; i < n; ++i) pop[c * n + i] = old_p[c * n + (anc[i] - 1)];
+        }
+        if (oi == ymax) {
+            if (logw_last) memcpy(logw_last, lw, sizeof(double) * (size_t)n);
+            if (anc_last && do_rs) memcpy(anc_last, anc, sizeof(int64_t) * (size_t)n);
+        }
+        t_prev = tmax; /* :72 */
+    }
+    free(old_p); free(cw); free(lw); free(anc);
+    *out_ll = output;
+    if (n_events) *n_events = ev_total;
+    if (n_overflow) *n_overflow = ovf_total;
+    return 0;
+}
+
+/* estimate_likelihood (src/hmm_particle_filter.jl:79-84) */
+int orc_pf_loglik(const dpomp_model_desc* m, const double* theta, int64_t n, int rs_type, uint64_t key,
+                  uint32_t filter, int mode, int tile, int items, int64_t max_events, int threads, double* out_ll,
+                  int64_t* n_events) {
+    int64_t* pop = (int64_t*)calloc((size_t)(n * m->n_compartments), sizeof(int64_t));
+    int rc = orc_pf_partial(m, theta, n, pop, 1, m->n_obs, rs_type, key, filter, mode, tile, items, max_events,
+                            threads, out_ll, NULL, NULL, n_events, NULL);
+    free(pop);
+    return rc;
+}
+
+/* a batch of independent filters (the loop of run_pibis src/hmm_ibis.jl:53-56), optionally OpenMP over filters.
+ * theta: n_params x B column-major; pops: B consecutive n x C matrices (may be NULL when ymin == 1 and state is not
+ * needed afterwards). */
+int orc_pf_partial_batch(const dpomp_model_desc* m, const double* theta, int32_t nb, int64_t n, int64_t* pops,
+                         int ymin, int ymax, int rs_type, uint64_t key, uint32_t filter0, int mode, int tile, int items,
+                         int64_t max_events, int threads, double* out_ll, int64_t* n_events) {
+    int64_t ev_total = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : ev_total) if (threads > 1)
+    for (int32_t b = 0; b < nb; ++b) {
+        int64_t* pop = pops ? pops + (size_t)b * n * m->n_compartments
+                            : (int64_t*)calloc((size_t)(n * m->n_compartments), sizeof(int64_t));
+        int64_t ev = 0;
+        orc_pf_partial(m, theta + (size_t)b * m->n_params, n, pop, ymin, ymax, rs_type, key, filter0 + (uint32_t)b,
+                       mode, tile, items, max_events, 1, &out_ll[b], NULL, NULL, &ev, NULL);
+        ev_total += ev;
+        if (!pops) free(pop);
+    }
+    if (n_events) *n_events = ev_total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Single-trajectory Gillespie simulation with the reference's draw order, for generating synthetic data:       */
+/* gillespie_sim (src/hmm_sim.jl:86-102) with iterate_particle! (:55-70) and dmy_obs_fn (src/hmm_examples.jl:6-8).*/
+/* out_states: T x C row-major final state at each observation time.                                             */
+/* ------------------------------------------------------------------------------------------------------------ */
+int orc_gillespie_sim(const dpomp_model_desc* m, const double* theta, uint64_t key, int64_t max_events,
+                      int64_t* out_states, int64_t* n_events) {
+    int64_t x[DPOMP_MAX_COMPARTMENTS];
+    for (int c = 0; c < m->n_compartments; ++c) x[c] = m->initial_condition[c];
+    double t = (m->t0_index == 0) ? 0.0 : theta[m->t0_index - 1];
+    int64_t ev = 0;
+    for (int i = 0; i < m->n_obs; ++i) {
+        int ovf = 0;
+        ev += sim_interval(m, theta, x, t, m->obs_time[i], key, 0u, 0u, (uint32_t)i, max_events, &ovf);
+        for (int c = 0; c < m->n_compartments; ++c) out_states[(size_t)i * m->n_compartments + c] = x[c];
+        t = m->obs_time[i];
+    }
+    if (n_events) *n_events = ev;
+    return 0;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

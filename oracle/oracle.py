@@ -1,0 +1,127 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+MODE_LITERAL, MODE_DEVICE = 0, 1
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("dpomp_oracle.c", "dpomp_oracle_ibis.c", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_compute_ess.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def philox(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32); k = np.asarray(key, dtype=np.uint32); out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+def pf_partial(desc, theta, n: int, pop: Optional[np.ndarray], ymin: int, ymax: int, rs_type: int = 1, key: int = 0,
+               filter_id: int = 0, mode: int = MODE_LITERAL, tile: int = 1024, items: int = 4,
+               max_events: int = 1 << 20, threads: int = 1):
+    """partial_log_likelihood!; pop is (n, C) int64 (Julia Matrix) and is updated in place.  Returns
+    (loglik, logw_last, ancestors_last(1-based), n_events, n_overflow)."""
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    c = desc.n_compartments
+    popf = np.zeros((c, n), dtype=np.int64) if pop is None else np.ascontiguousarray(np.asarray(pop, dtype=np.int64).T)
+    ll = C.c_double(); ev = C.c_int64(); ovf = C.c_int64()
+    lw = np.zeros(n); anc = np.zeros(n, dtype=np.int64)
+    rc = lib().orc_pf_partial(C.byref(desc), _p(th), C.c_int64(n), _p(popf), ymin, ymax, rs_type, C.c_uint64(key),
+                              C.c_uint32(filter_id), mode, tile, items, C.c_int64(max_events), threads, C.byref(ll),
+                              _p(lw), _p(anc), C.byref(ev), C.byref(ovf))
+    assert rc == 0
+    if pop is not None:
+        pop[...] = popf.T
+    return ll.value, lw, anc, ev.value, ovf.value, popf.T.copy()
+
+
+def pf_loglik(desc, theta, n: int, rs_type: int = 1, key: int = 0, filter_id: int = 0, mode: int = MODE_LITERAL,
+              tile: int = 1024, items: int = 4, max_events: int = 1 << 20, threads: int = 1) -> Tuple[float, int]:
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    ll = C.c_double(); ev = C.c_int64()
+    rc = lib().orc_pf_loglik(C.byref(desc), _p(th), C.c_int64(n), rs_type, C.c_uint64(key), C.c_uint32(filter_id), mode,
+                             tile, items, C.c_int64(max_events), threads, C.byref(ll), C.byref(ev))
+    assert rc == 0
+    return ll.value, ev.value
+
+
+def pf_partial_batch(desc, theta_cols, n: int, ymin: int, ymax: int, rs_type: int = 1, key: int = 0, filter0: int = 0,
+                     mode: int = MODE_LITERAL, tile: int = 1024, items: int = 4, max_events: int = 1 << 20,
+                     threads: int = 1, pops: Optional[np.ndarray] = None):
+    """theta_cols: (n_theta, B) Julia layout.  pops: optional (B, C, n) int64 state (updated in place)."""
+    th = np.ascontiguousarray(np.asarray(theta_cols, dtype=np.float64).T)
+    nb = th.shape[0]
+    out = np.zeros(nb); ev = C.c_int64()
+    rc = lib().orc_pf_partial_batch(C.byref(desc), _p(th), nb, C.c_int64(n), _p(pops), ymin, ymax, rs_type,
+                                    C.c_uint64(key), C.c_uint32(filter0), mode, tile, items, C.c_int64(max_events),
+                                    threads, _p(out), C.byref(ev))
+    assert rc == 0
+    return out, ev.value
+
+
+def rs(rs_type: int, w, r, n_out: Optional[int] = None) -> np.ndarray:
+    """rs_* on RAW weights (src/hmm_resample.jl); returns 1-based ancestors."""
+    w = np.array(w, dtype=np.float64); r = np.ascontiguousarray(np.atleast_1d(r), dtype=np.float64)
+    n_out = len(w) if n_out is None else n_out
+    out = np.zeros(n_out, dtype=np.int64)
+    lib().orc_rs(rs_type, _p(w), C.c_int64(len(w)), _p(r), C.c_int64(n_out), _p(out))
+    return out
+
+
+def rsp(rs_type: int, cw, r, n_out: Optional[int] = None) -> np.ndarray:
+    """rsp_* on CUMULATIVE weights (src/hmm_pf_resample.jl); returns 1-based ancestors."""
+    cw = np.ascontiguousarray(cw, dtype=np.float64); r = np.ascontiguousarray(np.atleast_1d(r), dtype=np.float64)
+    n_out = len(cw) if n_out is None else n_out
+    out = np.zeros(n_out, dtype=np.int64)
+    lib().orc_rsp(rs_type, _p(cw), C.c_int64(len(cw)), _p(r), C.c_int64(n_out), _p(out))
+    return out
+
+
+def compute_ess(w) -> float:
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    return lib().orc_compute_ess(_p(w), C.c_int64(len(w)))
+
+
+def compute_is_mu_covar(theta_cols, w):
+    th = np.ascontiguousarray(np.asarray(theta_cols, dtype=np.float64).T)  # (n, n_theta) row-major == Julia col-major
+    n, nt = th.shape
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    mu = np.zeros(nt); cv = np.zeros((nt, nt))
+    lib().orc_compute_is_mu_covar(_p(mu), _p(cv), _p(th), _p(w), nt, C.c_int64(n))
+    return mu, cv
+
+
+def gillespie_sim(desc, theta, key: int = 0, max_events: int = 1 << 24):
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    out = np.zeros((desc.n_obs, desc.n_compartments), dtype=np.int64); ev = C.c_int64()
+    lib().orc_gillespie_sim(C.byref(desc), _p(th), C.c_uint64(key), C.c_int64(max_events), _p(out), C.byref(ev))
+    return out, ev.value
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
