@@ -87,6 +87,8 @@ _SIGS = {
     "dpomp_pf_overflow_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "dpomp_pf_last_event_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "dpomp_pf_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "dpomp_pf_set_kernel_timing": (C.c_int, [_P, C.c_int32]),
+    "dpomp_pf_last_kernel_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dpomp_pf_export_filters": (C.c_int, [_P, _P, C.c_int32, _P]),
     "dpomp_pf_import_filters": (C.c_int, [_P, _P, C.c_int32, _P]),
     "dpomp_pf_loglik_device": (C.c_int, [_P, _P, C.c_int32, _P]),

@@ -60,6 +60,12 @@ struct dpomp_pf {
     float last_ms = 0.f;
     int last_launches = 0;
     long long last_events = 0;
+    // optional per-kernel timing (bench.py roofline): events around every launch of the last call
+    bool kernel_timing = false;
+    std::vector<cudaEvent_t> kev;      // 2 events per launch slot
+    std::vector<int> kev_kind;         // 0 = simulate+weight, 1 = resample
+    float kernel_ms[2] = {0.f, 0.f};
+    int kernel_launches[2] = {0, 0};
 };
 
 static uint64_t splitmix64(uint64_t x) {
@@ -137,6 +143,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev);
     cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
+    for (cudaEvent_t e : pf->kev) cudaEventDestroy(e);
     if (pf->ev0) cudaEventDestroy(pf->ev0);
     if (pf->ev1) cudaEventDestroy(pf->ev1);
     if (pf->stream) cudaStreamDestroy(pf->stream);
@@ -271,6 +278,22 @@ int dpomp_pf_set_record_ancestors(dpomp_pf* pf, int32_t on) {
     return DPOMP_OK;
 }
 
+// kind >= 0 opens a timed launch slot, kind < 0 closes the open one
+static cudaError_t kernel_event(dpomp_pf* pf, int kind, cudaStream_t st) {
+    if (kind >= 0) {
+        const size_t slot = pf->kev_kind.size();
+        while (pf->kev.size() < 2 * (slot + 1)) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            pf->kev.push_back(e);
+        }
+        pf->kev_kind.push_back(kind);
+        return cudaEventRecord(pf->kev[2 * slot], st);
+    }
+    return cudaEventRecord(pf->kev[2 * (pf->kev_kind.size() - 1) + 1], st);
+}
+
 // the launch sequence of partial_log_likelihood! (src/hmm_particle_filter.jl:39-76), batched over filters
 static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax, double* out,
                        bool out_on_device) {
@@ -295,6 +318,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
     CK(cudaMemsetAsync(pf->ll_acc, 0, (size_t)nb * sizeof(double), st));
     CK(cudaMemsetAsync(pf->counters, 0, sizeof(unsigned long long), st));
     int launches = 0;
+    pf->kev_kind.clear();
     for (int oi = ymin; oi <= ymax; ++oi) {
         const int t = oi - 1;
         const int has_lik = mh.obs_id[t] > 0;
@@ -312,7 +336,9 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
         a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
+        if (pf->kernel_timing) CK(kernel_event(pf, 0, st));
         CK(launch_sim_weight(mh, pf->sim_precision, pf->items, a, st));
+        if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
         ++launches;
         if (do_rs) {
             ResampleLaunch r{};
@@ -322,7 +348,9 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;
             r.t = t; r.rs_type = pf->rs_type; r.key = key; r.filter0 = (uint32_t)pf->batch_offset;
+            if (pf->kernel_timing) CK(kernel_event(pf, 1, st));
             CK(launch_resample(pf->items, r, st));
+            if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
             launches += (pf->rs_type == DPOMP_RS_MULTINOMIAL) ? 2 : 1;
             pf->cur ^= 1;
         }
@@ -341,6 +369,14 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
     CK(cudaEventElapsedTime(&pf->last_ms, pf->ev0, pf->ev1));
     pf->last_launches = launches;
     pf->last_events = (long long)h_cnt;
+    pf->kernel_ms[0] = pf->kernel_ms[1] = 0.f;
+    pf->kernel_launches[0] = pf->kernel_launches[1] = 0;
+    for (size_t i = 0; i < pf->kev_kind.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pf->kev[2 * i], pf->kev[2 * i + 1]));
+        pf->kernel_ms[pf->kev_kind[i]] += ms;
+        pf->kernel_launches[pf->kev_kind[i]] += 1;
+    }
     pf->initialised = true;
     return DPOMP_OK;
 }
@@ -466,6 +502,18 @@ int dpomp_pf_last_timing(dpomp_pf* pf, float* out_ms, int32_t* out_launches) {
     if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
     if (out_ms) *out_ms = pf->last_ms;
     if (out_launches) *out_launches = pf->last_launches;
+    return DPOMP_OK;
+}
+
+int dpomp_pf_set_kernel_timing(dpomp_pf* pf, int32_t on) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    pf->kernel_timing = on != 0;
+    return DPOMP_OK;
+}
+int dpomp_pf_last_kernel_timing(dpomp_pf* pf, float* out_ms2, int32_t* out_launches2) {
+    if (!pf || !out_ms2 || !out_launches2) return fail(DPOMP_ERR_ARG, "null argument");
+    out_ms2[0] = pf->kernel_ms[0]; out_ms2[1] = pf->kernel_ms[1];
+    out_launches2[0] = pf->kernel_launches[0]; out_launches2[1] = pf->kernel_launches[1];
     return DPOMP_OK;
 }
 

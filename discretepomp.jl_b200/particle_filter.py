@@ -198,6 +198,15 @@ class ParticleFilter:
         _capi.check(_capi.lib().dpomp_pf_last_timing(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def set_kernel_timing(self, on: bool) -> None:
+        _capi.check(_capi.lib().dpomp_pf_set_kernel_timing(self._h, 1 if on else 0))
+
+    def last_kernel_timing(self):
+        """((ms_sim, ms_resample), (launches_sim, launches_resample)) of the last call (kernel timing on)."""
+        ms = (C.c_float * 2)(); n = (C.c_int32 * 2)()
+        _capi.check(_capi.lib().dpomp_pf_last_kernel_timing(self._h, ms, n))
+        return (float(ms[0]), float(ms[1])), (int(n[0]), int(n[1]))
+
     def loglik_device(self, theta_dev_ptr: int, n_batch_used: int, out_dev_ptr: int) -> None:
         _capi.check(_capi.lib().dpomp_pf_loglik_device(self._h, C.c_void_p(theta_dev_ptr), int(n_batch_used),
                                                        C.c_void_p(out_dev_ptr)))

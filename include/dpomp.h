@@ -158,6 +158,11 @@ int dpomp_pf_last_event_count(dpomp_pf* pf, int64_t* out_events);
 /* device time (ms, CUDA events on the handle's stream) and kernel launches of the last call */
 int dpomp_pf_last_timing(dpomp_pf* pf, float* out_ms, int32_t* out_launches);
 
+/* per-kernel device time of the last call, measured with CUDA events around every launch when switched on:
+ * out_ms2 / out_launches2 = {simulate+weight kernel, resample kernel(s)} summed over the call */
+int dpomp_pf_set_kernel_timing(dpomp_pf* pf, int32_t on);
+int dpomp_pf_last_kernel_timing(dpomp_pf* pf, float* out_ms2, int32_t* out_launches2);
+
 /* migration of whole filters between devices (multi-GPU SMC^2): pack / unpack the int32 SoA state of the
  * listed filters (1-based) to / from a caller-provided DEVICE buffer of n * C * n_particles int32 */
 int dpomp_pf_export_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, void* device_dst);

@@ -1,0 +1,56 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def dp():
+    import dpomp_b200
+
+    return dpomp_b200
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import oracle
+
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libdpomp.so built in-tree (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    import dpomp_b200
+
+    return dpomp_b200._capi.lib()
+
+
+def load_case(dp, name):
+    """(model, observations, private model, theta) of the named config."""
+    import numpy as np
+
+    cases = {
+        "sis_pooley": ("SIS", [100, 1], "pooley.csv", [0.003, 0.1]),
+        "sir_c2": ("SIR", [100, 1, 0], "sir_c2.csv", [0.003, 0.1]),
+        "sir_dense": ("SIR", [1000, 10, 0], "sir_dense.csv", [0.0003, 0.1]),
+        "seir_c3": ("SEIR", [100, 0, 1, 0], "seir_c3.csv", [0.005, 0.2, 0.1]),
+        "lotka_c4": ("LOTKA", [70, 70], "lotka_c4.csv", [0.5, 0.0025, 0.3]),
+    }
+    mname, ic, csv, theta = cases[name]
+    model = dp.generate_model(mname, ic)
+    y = dp.get_observations(os.path.join(GOLDEN, csv))
+    return model, y, dp.get_private_model(model, y), np.asarray(theta, dtype=np.float64)

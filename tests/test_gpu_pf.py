@@ -1,0 +1,221 @@
+"""GPU parity tests of the particle-filter hot path, through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * ancestors / populations / event counts: bit-exact on identical Philox draws (f64 event loop)
+  * per-trajectory log-likelihoods (log weights): <= 1e-6 relative (f64 loop: exact; f32 loop: on the trajectories that
+    did not flip an event)
+  * PF log-likelihood estimates: z-test against the oracle's Monte-Carlo distribution (f32 loop)
+"""
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _pf(dp, hmm, n, nb=1, rs=1, seed=1, f64=False, **kw):
+    return dp.ParticleFilter(dp.device_model(hmm), n, nb, rs, seed=seed,
+                             sim_precision=dp._capi.SIM_F64 if f64 else dp._capi.SIM_F32, **kw)
+
+
+@pytest.mark.parametrize("case", ["sis_pooley", "sir_c2", "seir_c3", "lotka_c4"])
+@pytest.mark.parametrize("rs_type", [1, 2, 3])
+def test_f64_loop_is_bit_exact_against_oracle(dp, orc, case, rs_type):
+    model, y, hmm, theta = load_case(dp, case)
+    ymax = min(len(y), 4)
+    for n in (200, 1024, 3000):  # 256-particle tile, exactly one 1024 tile, ragged multi-tile
+        if case == "lotka_c4" and n > 1024:
+            continue
+        pf = _pf(dp, hmm, n, rs=rs_type, f64=True)
+        pf.set_record_ancestors(True)
+        tile, items = pf.geometry()
+        key = 0xABCDEF00 + n + rs_type
+        pf.set_stream_key(key)
+        ll = pf.partial(theta, 1, ymax)[0]
+        o_ll, o_lw, o_anc, o_ev, o_ovf, o_pop = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, ymax, rs_type,
+                                                               key, 0, orc.MODE_DEVICE, tile, items)
+        assert pf.last_event_count() == o_ev
+        assert np.array_equal(pf.last_logw(), o_lw)
+        assert np.array_equal(pf.last_ancestors(), o_anc)
+        assert np.array_equal(pf.get_pop(1), o_pop)
+        assert abs(ll - o_ll) <= 1e-12 * max(1.0, abs(o_ll))
+
+
+def test_literal_reference_arithmetic_gives_same_ancestors(dp, orc):
+    # the oracle's LITERAL mode (running linear cumsum, sequential walk: the reference's own arithmetic) picks the same
+    # ancestors as the device tree at these sizes, and the log-likelihood agrees to rounding
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    n = 2000
+    pf = _pf(dp, hmm, n, f64=True)
+    key = 424242
+    pf.set_stream_key(key)
+    ll = pf.loglik(theta)[0]
+    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 5, 1, key, 0, orc.MODE_LITERAL)
+    assert np.array_equal(pf.get_pop(1), o[5]) and abs(ll - o[0]) < 1e-10
+
+
+def test_batched_filters_match_single_filters(dp, orc):
+    # filter b of a batch == a single filter with global id b (batch_offset), bit for bit: sharding invariance
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    n, nb = 1500, 5
+    rng = np.random.default_rng(1)
+    thetas = theta[:, None] * rng.uniform(0.8, 1.2, size=(2, nb))
+    pf = _pf(dp, hmm, n, nb, f64=True)
+    key = 777
+    pf.set_stream_key(key)
+    lls = pf.partial(thetas, 1, 10)
+    tile, items = pf.geometry()
+    for b in (0, 3, 4):
+        single = _pf(dp, hmm, n, 1, f64=True)
+        single.set_batch_offset(b)
+        single.set_stream_key(key)
+        assert single.partial(thetas[:, b], 1, 10)[0] == lls[b]
+        assert np.array_equal(single.get_pop(1), pf.get_pop(b + 1))
+        o = orc.pf_partial(pf.dmodel.compiled.desc, thetas[:, b], n, None, 1, 10, 1, key, b, orc.MODE_DEVICE, tile, items)
+        assert np.array_equal(pf.get_pop(b + 1), o[5]) and abs(lls[b] - o[0]) < 1e-11
+
+
+def test_partial_calls_compose_on_device(dp, orc):
+    # run_pibis' call pattern (src/hmm_ibis.jl:53-56): one observation per call on device-resident populations
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    n = 1024
+    pf = _pf(dp, hmm, n, f64=True)
+    desc = pf.dmodel.compiled.desc
+    tile, items = pf.geometry()
+    pop = np.zeros((n, 2), dtype=np.int64)
+    for i in range(1, 6):
+        key = 1000 + i
+        pf.set_stream_key(key)
+        g = pf.partial(theta, i, i)[0]
+        o = orc.pf_partial(desc, theta, n, pop, i, i, 1, key, 0, orc.MODE_DEVICE, tile, items)
+        assert abs(g - o[0]) < 1e-12 and np.array_equal(pf.get_pop(1), pop)
+    with pytest.raises(dp._capi.DpompError):
+        _pf(dp, hmm, n).partial(theta, 2, 3)  # ymin > 1 on a filter that was never started
+
+
+def test_f32_loop_trajectories_match_within_1e6(dp, orc):
+    # same Philox draws, f32 event loop: almost every trajectory is identical to the f64 oracle; on those the
+    # per-trajectory log-likelihood matches to <= 1e-6 relative (it is computed in f64 from identical integer states)
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    n = 4096
+    pf = _pf(dp, hmm, n)
+    key = 31337
+    pf.set_stream_key(key)
+    pf.partial(theta, 1, 1)
+    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 1, 1, key, 0, orc.MODE_LITERAL)
+    lw = pf.last_logw()
+    same = lw == o[1]
+    assert same.mean() > 0.999
+    assert np.all(np.abs(lw[same] - o[1][same]) <= 1e-6 * np.abs(o[1][same]))
+
+
+@pytest.mark.parametrize("case,n,reps", [("sis_pooley", 200, 512), ("sir_c2", 1024, 128), ("seir_c3", 1024, 128),
+                                         ("lotka_c4", 512, 64)])
+def test_f32_loglik_z_test_against_oracle(dp, orc, case, n, reps):
+    """z-test (|z| < 4.5) of the mean PF log-likelihood, f32 GPU path vs literal oracle, independent draws."""
+    model, y, hmm, theta = load_case(dp, case)
+    pf = _pf(dp, hmm, n, reps, seed=99)
+    gpu = pf.loglik(np.tile(theta[:, None], (1, reps)))
+    tile, items = pf.geometry()
+    ref, _ = orc.pf_partial_batch(pf.dmodel.compiled.desc, np.tile(theta[:, None], (1, reps)), n, 1, len(y), 1,
+                                  key=20261018, threads=orc.max_threads())
+    z = (gpu.mean() - ref.mean()) / np.sqrt(gpu.var(ddof=1) / reps + ref.var(ddof=1) / reps)
+    assert abs(z) < 4.5, (case, gpu.mean(), ref.mean(), z)
+    assert 0.5 < gpu.std() / ref.std() < 2.0
+
+
+def test_sis_pooley_anchor(dp):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    f = dp.get_particle_filter_lpdf(model, y, np=1 << 16, n_batch=8)
+    lls = f(np.tile(theta[:, None], (1, 8)))
+    assert abs(lls.mean() + 15.69) < 0.03  # SURVEY.md 8c anchor: -15.69 +- 0.01 as N -> inf
+    assert isinstance(f(theta), float)
+
+
+def test_determinism_and_seed_dependence(dp):
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    a = _pf(dp, hmm, 5000, seed=5).loglik(theta)[0]
+    b = _pf(dp, hmm, 5000, seed=5).loglik(theta)[0]
+    c = _pf(dp, hmm, 5000, seed=6).loglik(theta)[0]
+    assert a == b and a != c
+    pf = _pf(dp, hmm, 5000, seed=5)
+    assert pf.loglik(theta)[0] == a and pf.loglik(theta)[0] != a  # consecutive calls use fresh streams
+
+
+def test_event_cap_overflow_is_flagged(dp):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    pf = _pf(dp, hmm, 512, max_events=10)
+    ll = pf.partial(theta, 1, 1)[0]
+    assert pf.overflow_count() > 0 and np.isneginf(pf.last_logw()).sum() == pf.overflow_count()
+    assert np.isfinite(ll) or np.isneginf(ll)
+
+
+def test_zero_rate_absorption_and_all_zero_weights(dp, orc):
+    # theta = 0: no events ever; the state stays at the initial condition and the weights are the closed form
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    pf = _pf(dp, hmm, 300, f64=True)
+    ll = pf.loglik(np.zeros(2))[0]
+    assert pf.last_event_count() == 0 and np.all(pf.get_pop(1) == np.array([100, 1]))
+    want = sum(np.log(1 / (np.sqrt(2 * np.pi) * 2.0)) - (v - 1) ** 2 / 8.0 for v in (18, 65, 70, 66, 67))
+    assert abs(ll - want) < 1e-9
+    # an observation so far away that every weight underflows in the linear domain: the reference returns -Inf,
+    # the LSE path stays finite (documented divergence)
+    far = [dp.Observation(o.time, 1, 1.0, [0, 1000]) for o in y]
+    hmm2 = dp.get_private_model(model, far)
+    ll2 = _pf(dp, hmm2, 300).loglik(np.zeros(2))[0]
+    assert np.isfinite(ll2) and ll2 < -1e5
+
+
+def test_obs_id_zero_skips_likelihood_and_resampling(dp, orc):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    y2 = [dp.Observation(o.time, 0 if i == 1 else 1, 1.0, o.val) for i, o in enumerate(y)]
+    hmm2 = dp.get_private_model(model, y2)
+    pf = _pf(dp, hmm2, 1024, f64=True)
+    tile, items = pf.geometry()
+    pf.set_stream_key(55)
+    ll = pf.loglik(theta)[0]
+    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, 1024, None, 1, 5, 1, 55, 0, orc.MODE_DEVICE, tile, items)
+    assert abs(ll - o[0]) < 1e-12 and np.array_equal(pf.get_pop(1), o[5])
+
+
+def test_t0_index_parameter(dp, orc):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    def rf(out, p, x):
+        out[0] = p[0] * x[0] * x[1]; out[1] = p[1] * x[1]
+    m3 = dp.generate_custom_model("SIS", rf, [100, 1], [[-1, 1], [1, -1]], prior=dp.generate_weak_prior(3), t0_index=3)
+    hmm3 = dp.get_private_model(m3, y)
+    th = np.array([0.003, 0.1, 5.0])
+    pf = _pf(dp, hmm3, 1024, f64=True)
+    tile, items = pf.geometry()
+    pf.set_stream_key(91)
+    ll = pf.loglik(th)[0]
+    o = orc.pf_partial(pf.dmodel.compiled.desc, th, 1024, None, 1, 5, 1, 91, 0, orc.MODE_DEVICE, tile, items)
+    assert abs(ll - o[0]) < 1e-12 and np.array_equal(pf.get_pop(1), o[5])
+
+
+def test_full_size_c2_properties(dp):
+    """BASELINE config C2 at full size (2^20 particles x 100 observations): size-independent properties."""
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    n = 1 << 20
+    pf = _pf(dp, hmm, n, seed=2)
+    pf.set_record_ancestors(True)
+    ll = pf.loglik(theta)[0]
+    pop = pf.get_pop(1)
+    assert np.all(pop.sum(axis=1) == 101) and pop.min() >= 0  # SIR conserves the population
+    assert pf.overflow_count() == 0
+    # the last resampling step (observation 99): ancestors are sorted (systematic) and cover 1..N
+    pf.partial(theta, 1, 2)
+    anc = pf.last_ancestors()
+    pf2 = _pf(dp, hmm, n, seed=2)
+    assert np.all(np.diff(anc) >= 0) and anc.min() >= 1 and anc.max() <= n
+    # offspring counts follow the weights: |count_j - N w_j| < 1 for systematic resampling (first observation only)
+    pf2.set_record_ancestors(True)
+    pf2.partial(theta, 1, 1)
+    lw = pf2.last_logw(); anc1 = pf2.last_ancestors()
+    w = np.exp(lw - lw.max()); w /= w.sum()
+    counts = np.bincount(anc1 - 1, minlength=n)
+    assert np.max(np.abs(counts - n * w)) < 1.0 + 1e-6
+    # two independent 2^20-particle estimates agree to Monte-Carlo error (sd of one estimate ~ 0.01)
+    ll_b = _pf(dp, hmm, n, seed=3).loglik(theta)[0]
+    assert abs(ll - ll_b) < 0.1

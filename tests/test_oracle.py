@@ -1,0 +1,116 @@
+"""CPU tests of the oracle: known-answer vectors, the resampling searches on hand-built inputs, the reference anchors."""
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+
+def test_philox_known_answers(orc):
+    # Random123 kat_vectors for philox4x32-10
+    assert orc.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert orc.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert orc.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]).tolist() == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_rs_systematic_hand_cases(orc):
+    # rs_systematic (src/hmm_resample.jl:44-62): u_i = (r/N + (i-1)/N) * sum(w), first j with u_i <= cw_j
+    w = [1.0, 1.0, 1.0, 1.0]
+    assert orc.rs(1, w, [0.5]).tolist() == [1, 2, 3, 4]
+    assert orc.rs(1, w, [0.0]).tolist() == [1, 1, 2, 3]  # u on the bin edges: strict `>` keeps the lower index
+    assert orc.rs(1, [0.0, 0.0, 2.0, 0.0], [0.3]).tolist() == [3, 3, 3, 3]
+    assert orc.rs(1, [3.0, 0.0, 0.0, 1.0], [0.999]).tolist() == [1, 1, 1, 4]
+    assert orc.rs(1, [0.0, 0.0, 0.0], [0.7]).tolist() == [1, 1, 1]  # all-zero weights: everything maps to ancestor 1
+
+
+def test_rs_stratified_and_multinomial_hand_cases(orc):
+    w = [1.0, 2.0, 1.0]
+    # stratified (src/hmm_resample.jl:66-83): u_i = (r_i/N + (i-1)/N) * 4 -> 0.667, 2.0, 3.733 ; cw = 1,3,4
+    assert orc.rs(2, w, [0.5, 0.5, 0.8]).tolist() == [1, 2, 3]
+    # multinomial (src/hmm_resample.jl:4-20): chs = r*4, first p2 < N with chs < cw[p2] (strict), else N
+    assert orc.rs(3, w, [0.0, 0.25, 0.2499, 0.75, 0.99], n_out=5).tolist() == [1, 2, 1, 3, 3]
+    assert orc.rs(3, w, [0.1, 0.9], n_out=2).tolist() == [1, 3]
+
+
+def test_rsp_equals_rs_on_cumsum(orc):
+    rng = np.random.default_rng(5)
+    w = rng.random(257)
+    r = rng.random(257)
+    for rs_type in (1, 2, 3):
+        assert np.array_equal(orc.rs(rs_type, w, r), orc.rsp(rs_type, np.cumsum(w), r))
+
+
+def test_ess_and_weighted_moments(orc):
+    rng = np.random.default_rng(6)
+    w = rng.random(100)
+    assert np.isclose(orc.compute_ess(w), w.sum() ** 2 / (w * w).sum(), rtol=1e-14)
+    theta = rng.normal(size=(3, 100))
+    mu, cv = orc.compute_is_mu_covar(theta, w)
+    mu_np = (theta * w).sum(axis=1) / w.sum()
+    d = theta - mu_np[:, None]
+    cv_np = (d * w) @ d.T / w.sum()
+    assert np.allclose(mu, mu_np, rtol=1e-12) and np.allclose(cv, cv_np, rtol=1e-10)
+
+
+def test_obs_model_closed_form(dp, orc):
+    # one particle, one observation, no events possible (theta = 0): log g = log(1/(sqrt(2 pi) 2)) - (18 - 1)^2 / 8
+    model, y, hmm, _ = load_case(dp, "sis_pooley")
+    cm = dp.compile_model(model, y)
+    ll, lw, *_ = orc.pf_partial(cm.desc, [0.0, 0.0], 1, None, 1, 1)
+    want = np.log(1.0 / (np.sqrt(2 * np.pi) * 2.0)) - (18 - 1) ** 2 / 8.0
+    assert np.isclose(lw[0], want, rtol=1e-15) and np.isclose(ll, want, rtol=1e-15)
+
+
+def test_literal_and_device_mode_agree(dp, orc):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    cm = dp.compile_model(model, y)
+    for rs_type in (1, 2, 3):
+        for n, tile, items in ((200, 256, 1), (1500, 1024, 4)):
+            a = orc.pf_partial(cm.desc, theta, n, None, 1, 5, rs_type, 99, 0, orc.MODE_LITERAL, tile, items)
+            b = orc.pf_partial(cm.desc, theta, n, None, 1, 5, rs_type, 99, 0, orc.MODE_DEVICE, tile, items)
+            assert abs(a[0] - b[0]) < 1e-11
+            assert np.array_equal(a[5], b[5])  # identical final populations => identical ancestors at every step
+
+
+def test_partial_calls_compose(dp, orc):
+    # run_pibis calls partial_log_likelihood! one observation at a time on a persistent pop (src/hmm_ibis.jl:53-56)
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    cm = dp.compile_model(model, y)
+    n = 300
+    full = orc.pf_partial(cm.desc, theta, n, None, 1, 5, 1, 7)
+    pop = np.zeros((n, 2), dtype=np.int64)
+    total = 0.0
+    for i in range(1, 6):
+        total += orc.pf_partial(cm.desc, theta, n, pop, i, i, 1, 7)[0]
+    assert abs(total - full[0]) < 1e-12 and np.array_equal(pop, full[5])
+
+
+def test_reference_anchor_sis_pooley(dp, orc):
+    """PF log-lik at theta=(0.003,0.1) on data/pooley.csv -> -15.69 +- 0.01 as N grows (SURVEY.md 8c anchor)."""
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    cm = dp.compile_model(model, y)
+    lls = np.array([orc.pf_loglik(cm.desc, theta, 20000, key=4000 + i, threads=orc.max_threads())[0] for i in range(6)])
+    assert abs(lls.mean() + 15.69) < 0.04, lls
+    lls200 = np.array([orc.pf_loglik(cm.desc, theta, 200, key=5000 + i)[0] for i in range(200)])
+    # N=200: mean -15.709, sd 0.295 in the surveyor probe
+    assert abs(lls200.mean() + 15.71) < 0.08 and 0.2 < lls200.std() < 0.4, (lls200.mean(), lls200.std())
+
+
+def test_event_cap_flags_overflow(dp, orc):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    cm = dp.compile_model(model, y)
+    ll, lw, anc, ev, ovf, pop = orc.pf_partial(cm.desc, theta, 50, None, 1, 1, max_events=10)
+    assert ovf > 0 and np.isneginf(lw).sum() == ovf
+
+
+def test_t0_index_shifts_start(dp, orc):
+    # with t0_index = 3 the simulation starts at theta[3]; starting at the first observation time means no events
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    model.t0_index = 3
+    model.prior = dp.generate_weak_prior(3)
+    def rf(out, p, x):
+        out[0] = p[0] * x[0] * x[1]; out[1] = p[1] * x[1]
+    model.rate_function = rf
+    cm = dp.compile_model(model, y)
+    ll, lw, anc, ev, ovf, pop = orc.pf_partial(cm.desc, [0.003, 0.1, 20.0], 64, None, 1, 1)
+    assert ev == 0 and np.all(pop == np.array([100, 1]))
