@@ -40,6 +40,28 @@ __device__ __forceinline__ Philox4 stream_draw(uint64_t key, uint32_t particle, 
     return philox4x32_10(particle, filter, obs, (tag << 30) | block, (uint32_t)key, (uint32_t)(key >> 32));
 }
 
+// Philox2x32-10: 64-bit counter, 32-bit key.  One call = the two uniforms of one event attempt.
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += 0x9E3779B9u;
+    }
+    return make_uint2(c0, c1);
+}
+
+// Event-loop stream of one (call key, filter, observation): Philox2x32 key K and counter masks A, B, hashed once with
+// Philox4x32-10 (DESIGN.md "random streams").  Attempt k of particle n draws philox2x32_10(n ^ A, k ^ B, K).
+struct SimStream {
+    uint32_t k, a, b;
+};
+__device__ __forceinline__ SimStream sim_stream_init(uint64_t key, uint32_t filter, uint32_t obs) {
+    const Philox4 p = stream_draw(key, 0u, filter, obs, kTagSim, 0u);
+    return SimStream{p.w0, p.w1, p.w2};
+}
+
 // (0,1) with 32-bit resolution; f64 value is exact, f32 value is the rounding of it
 __device__ __forceinline__ double u32_open_f64(uint32_t w) { return ((double)w + 0.5) * 0x1.0p-32; }
 __device__ __forceinline__ float u32_open_f32(uint32_t w) { return fmaf(__uint2float_rn(w), 0x1.0p-32f, 0x1.0p-33f); }

@@ -21,7 +21,7 @@ struct DevModel {
     int has_den[E];
     int any_den;
     Real trans[E][C];
-    Real xmask[C];
+    int xmask_i[C];
     int ic[C];
     double obs_tmp1, obs_tmp2;  // log(1/(sqrt(2 pi) sigma)), 2 sigma^2 (src/hmm_examples.jl:61-62)
     int t0_index;

@@ -5,11 +5,13 @@
 // closures (src/hmm_examples.jl:103-168) and the Gaussian observation model (src/hmm_examples.jl:59-67) of the
 // reference, plus the `log(cum_weight[end]/N)` accumulation of partial_log_likelihood! (src/hmm_particle_filter.jl:60).
 //
-// Mapping: one CTA of 256 threads per (filter, tile of 256*ITEMS particles).  Each lane owns ITEMS particles and runs
-// them back to back in ONE flat event loop ("lane refill"): a lane that finishes a particle immediately starts its next
-// one, so a warp iterates max_lanes(sum of attempts) times instead of sum(max_lanes(attempts)).  Compartment counts live
-// in registers as Real during the loop; the tile's int32 states are staged in shared memory so the refill never waits
-// on HBM.  One Philox4x32-10 call feeds two event attempts (waiting time + event type each).
+// Mapping: one CTA of 256 threads per (filter, tile of 256*ITEMS particles).  The tile's int32 states are staged in
+// shared memory; each warp then drains its chunk of 32*ITEMS particles through a ballot-based work queue: one loop
+// iteration is ONE event attempt for every lane, and a lane whose particle reached the observation time parks it and
+// pulls the next unassigned particle of the chunk, so all lanes stay busy until the chunk is empty (no atomics: the
+// queue head is warp-uniform).  Compartment counts live in registers as Real during the loop.  One Philox2x32-10 call
+// per attempt yields the waiting-time and event-type uniforms.  The observation log-weight (one f64 divide per
+// particle) is computed afterwards in a convergent pass together with the coalesced write-back.
 #pragma once
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
@@ -32,14 +34,17 @@ template <typename Real, int C, int E, int ITEMS>
 __global__ void __launch_bounds__(kBlockThreads)
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
+    constexpr int CHUNK = 32 * ITEMS;  // particles owned by one warp
     constexpr bool kF32 = sizeof(Real) == 4;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lw_s = reinterpret_cast<double*>(smem_raw);   // [TILE] log weights of the tile
     int* st_s = reinterpret_cast<int*>(lw_s + TILE);      // [C][TILE] staged compartment counts
     __shared__ double warp_scratch[kBlockThreads / 32];
     __shared__ int is_last_s;
+    __shared__ uint32_t stream_s[3];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x % a.ntiles;
     const int b = blockIdx.x / a.ntiles;
     const long long base_n = (long long)tile * TILE;
@@ -55,7 +60,14 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     int32_t* pop_b = a.pop + (size_t)b * a.n_comp * a.n_pad;
     const uint32_t max_ev = (uint32_t)a.max_events;
 
-    if (!a.fresh) {  // stage this thread's particles (coalesced); each lane only ever touches its own slots
+    if (tid == 0) {
+        const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)a.t);
+        stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;
+    }
+    // stage the tile: coalesced loads, one slot per (thread, r); lw_s doubles as the overflow marker (0 = fine)
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) lw_s[r * kBlockThreads + tid] = 0.0;
+    if (!a.fresh) {
 #pragma unroll
         for (int c = 0; c < C; ++c)
             if (c < a.n_comp) {
@@ -64,129 +76,132 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     st_s[c * TILE + r * kBlockThreads + tid] = pop_b[(size_t)c * a.n_pad + base_n + r * kBlockThreads + tid];
             }
     }
+    __syncthreads();
+    const SimStream ss{stream_s[0], stream_s[1], stream_s[2]};
 
+    // ---- event loop: each warp drains its chunk of CHUNK particles through a ballot-based work queue ----------
+    const int chunk0 = warp * CHUNK;
+    const long long left = a.n - (base_n + chunk0);
+    const int chunk_valid = left < CHUNK ? (left > 0 ? (int)left : 0) : CHUNK;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int next = 32;  // warp-uniform: next unassigned slot of the chunk
+    int q = chunk0 + lane;
+    bool active = lane < chunk_valid;
     Real x[C];
-    Real tm = 0;          // f32: remaining time to the observation; f64: absolute time
-    uint32_t k = 0;       // events so far of the current particle
-    int r = -1, q = 0;
-    long long n_idx = 0;
-    bool active = false;
+    Real tm = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;  // f32: remaining time; f64: absolute time
+    const Real tm0 = tm;
+    uint32_t k = 0;
     unsigned long long ev_local = 0, ovf_local = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        x[c] = (active && c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
 
-    auto next_particle = [&]() {
-        active = false;
-        while (++r < ITEMS) {
-            q = r * kBlockThreads + tid;
-            n_idx = base_n + q;
-            if (n_idx < a.n) {
+    while (__any_sync(FULL, active)) {
+        bool fin = false, ovf = false;
+        if (active) {
+            // rate_function + cumsum! (src/hmm_particle_filter.jl:20-21)
+            Real cum[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                Real l1 = m.k1[e], l2 = m.k2[e];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    l1 += m.f1[e][c] * x[c];
+                    l2 += m.f2[e][c] * x[c];
+                }
+                Real rate = Arith<Real>::mul(Arith<Real>::mul(par[e], l1), l2);
+                if (m.any_den && m.has_den[e]) {
+                    Real dn = m.kd[e];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) dn += m.dn[e][c] * x[c];
+                    rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
+                }
+                cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+            }
+            const Real rtot = cum[E - 1];
+            fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
+            if (!fin) {
+                if (k >= max_ev) {  // event cap: documented divergence, the reference loop is unbounded
+                    fin = true;
+                    ovf = true;
+                } else {
+                    const uint2 w = philox2x32_10((uint32_t)(base_n + q) ^ ss.a, k ^ ss.b, ss.k);
+                    Real etc;
+                    if constexpr (kF32) {
+                        // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
+                        tm = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm);
+                        fin = tm < 0.0f;  // `time > tmax && break` (:24)
+                        etc = u32_open_f32(w.y) * rtot;
+                    } else {
+                        tm = tm - log(u32_open_f64(w.x)) / rtot;
+                        fin = tm > t_obs;
+                        etc = __dmul_rn(u32_open_f64(w.y), rtot);
+                    }
+                    if (!fin) {
+                        // choose_event (src/hmm_cmn.jl:4-10) + `ptemp .+= fn_transition(et)` (:26)
+                        Real dx[C];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
+#pragma unroll
+                        for (int i = E - 2; i >= 0; --i) {
+                            const bool hit = cum[i] > etc;
+#pragma unroll
+                            for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c) x[c] += dx[c];
+                        ++k;
+                    }
+                }
+            }
+        }
+        const unsigned fmask = __ballot_sync(FULL, fin);
+        if (fmask) {  // warp-uniform: finished lanes park their particle and pull the next slot of the chunk
+            if (fin) {
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    x[c] = (c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
-                tm = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;
-                k = 0;
-                active = true;
-                break;
-            }
-            lw_s[q] = -INFINITY;
-        }
-    };
-    next_particle();
-
-    while (active) {
-        const Philox4 w = stream_draw(a.key, (uint32_t)n_idx, gfilter, (uint32_t)a.t, kTagSim, k >> 1);
-        bool just_started = false;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (active && !just_started) {
-                // rate_function + cumsum! (src/hmm_particle_filter.jl:20-21)
-                Real cum[E];
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    Real l1 = m.k1[e], l2 = m.k2[e];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        l1 += m.f1[e][c] * x[c];
-                        l2 += m.f2[e][c] * x[c];
-                    }
-                    Real rate = Arith<Real>::mul(Arith<Real>::mul(par[e], l1), l2);
-                    if (m.any_den && m.has_den[e]) {
-                        Real dn = m.kd[e];
-#pragma unroll
-                        for (int c = 0; c < C; ++c) dn += m.dn[e][c] * x[c];
-                        rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
-                    }
-                    cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
-                }
-                const Real rtot = cum[E - 1];
-                bool fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
-                bool ovf = false;
-                if (!fin) {
-                    if (k >= max_ev) {  // event cap: documented divergence, the reference loop is unbounded
-                        fin = true;
-                        ovf = true;
-                    } else {
-                        const uint32_t wa = h ? w.w2 : w.w0, wb = h ? w.w3 : w.w1;
-                        Real etc;
-                        if constexpr (kF32) {
-                            // time -= log(rand()) / R  (:23) tracked as remaining time; lg2.approx + rcp.approx on the XU pipe
-                            tm = fmaf(__log2f(u32_open_f32(wa)), __fdividef(0.693147180559945f, rtot), tm);
-                            fin = tm < 0.0f;  // `time > tmax && break` (:24)
-                            etc = u32_open_f32(wb) * rtot;
-                        } else {
-                            tm = tm - log(u32_open_f64(wa)) / rtot;
-                            fin = tm > t_obs;
-                            etc = __dmul_rn(u32_open_f64(wb), rtot);
-                        }
-                        if (!fin) {
-                            // choose_event (src/hmm_cmn.jl:4-10) + `ptemp .+= fn_transition(et)` (:26)
-                            Real dx[C];
-#pragma unroll
-                            for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
-#pragma unroll
-                            for (int i = E - 2; i >= 0; --i) {
-                                const bool hit = cum[i] > etc;
-#pragma unroll
-                                for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
-                            }
-#pragma unroll
-                            for (int c = 0; c < C; ++c) x[c] += dx[c];
-                            ++k;
-                        }
-                    }
-                }
-                if (fin) {
-                    // exp(obs_model(...)) is deferred: store log g (src/hmm_examples.jl:63-65)
-                    Real xs = 0;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) xs += m.xmask[c] * x[c];
-                    const double d = ysum - (double)xs;
-                    lw_s[q] = ovf ? -INFINITY : m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
+                    if (c < a.n_comp) st_s[c * TILE + q] = (int)x[c];
+                if (ovf) lw_s[q] = -INFINITY;
+                ev_local += k;
+                ovf_local += ovf ? 1u : 0u;
+                const int slot = next + __popc(fmask & lt_mask);
+                active = slot < chunk_valid;
+                if (active) {
+                    q = chunk0 + slot;
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        if (c < a.n_comp) st_s[c * TILE + q] = (int)x[c];
-                    ev_local += k;
-                    ovf_local += ovf ? 1u : 0u;
-                    next_particle();
-                    just_started = true;
+                        x[c] = (c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
+                    tm = tm0;
+                    k = 0;
                 }
             }
+            next += __popc(fmask);
         }
     }
     __syncthreads();
 
-    // write back states and log weights (coalesced)
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-        if (c < a.n_comp) {
-#pragma unroll
-            for (int rr = 0; rr < ITEMS; ++rr) {
-                const int qq = rr * kBlockThreads + tid;
-                if (base_n + qq < a.n) pop_b[(size_t)c * a.n_pad + base_n + qq] = st_s[c * TILE + qq];
-            }
-        }
+    // ---- convergent pass: observation log-weight (src/hmm_examples.jl:63-65, exp deferred), write-back -----------
     double* lw_b = a.logw + (size_t)b * a.n_pad + base_n;
 #pragma unroll
-    for (int rr = 0; rr < ITEMS; ++rr) lw_b[rr * kBlockThreads + tid] = lw_s[rr * kBlockThreads + tid];
+    for (int r = 0; r < ITEMS; ++r) {
+        const int qq = r * kBlockThreads + tid;
+        double lw = -INFINITY;
+        if (base_n + qq < a.n) {
+            int xs = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (c < a.n_comp) {
+                    const int v = st_s[c * TILE + qq];
+                    xs += m.xmask_i[c] * v;
+                    pop_b[(size_t)c * a.n_pad + base_n + qq] = v;
+                }
+            const double d = ysum - (double)xs;
+            if (lw_s[qq] == 0.0) lw = m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
+        }
+        lw_s[qq] = lw;
+        lw_b[qq] = lw;
+    }
+    __syncthreads();
 
     // event statistics: one atomic per warp
 #pragma unroll
@@ -287,7 +302,7 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
     }
     for (int c = 0; c < C; ++c) {
         const bool cpad = c >= d.n_compartments;
-        m.xmask[c] = cpad ? (Real)0 : (Real)d.obs_xmask[c];
+        m.xmask_i[c] = cpad ? 0 : (int)d.obs_xmask[c];
         m.ic[c] = cpad ? 0 : (int)d.initial_condition[c];
     }
     m.obs_tmp1 = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * d.obs_sigma));

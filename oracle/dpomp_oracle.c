@@ -53,6 +53,19 @@ void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (same paper): 64-bit counter, 32-bit key, two output words */
+void orc_philox2x32_10(const uint32_t ctr_in[2], uint32_t key, uint32_t out[2]) {
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p;
+        c0 = n0;
+        key += 0x9E3779B9u;
+    }
+    out[0] = c0; out[1] = c1;
+}
+
 #define ORC_TAG_SIM 0u
 #define ORC_TAG_RESAMPLE 1u
 
@@ -61,6 +74,20 @@ static inline void stream_draw(uint64_t key, uint32_t particle, uint32_t filter,
     uint32_t ctr[4] = {particle, filter, obs, (tag << 30) | block};
     uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
     orc_philox4x32_10(ctr, k, out);
+}
+/* Event-loop draws (DESIGN.md "random streams"): the (call key, filter, observation) triple is hashed once with
+ * Philox4x32-10 into a 32-bit Philox2x32 key K and two counter masks A, B; attempt k of particle n then uses
+ * Philox2x32-10(ctr = (n ^ A, k ^ B), key = K): word 0 -> waiting time, word 1 -> event type. */
+typedef struct { uint32_t k, a, b; } sim_stream;
+static inline sim_stream sim_stream_init(uint64_t key, uint32_t filter, uint32_t obs) {
+    uint32_t w[4];
+    stream_draw(key, 0u, filter, obs, ORC_TAG_SIM, 0u, w);
+    sim_stream s = {w[0], w[1], w[2]};
+    return s;
+}
+static inline void sim_draw(const sim_stream* s, uint32_t particle, uint32_t attempt, uint32_t out[2]) {
+    uint32_t ctr[2] = {particle ^ s->a, attempt ^ s->b};
+    orc_philox2x32_10(ctr, s->k, out);
 }
 static inline double u32_open(uint32_t w) { return ((double)w + 0.5) * 0x1.0p-32; }               /* (0,1)  */
 static inline double u53(uint32_t hi, uint32_t lo) {                                                /* [0,1)  */
@@ -108,20 +135,19 @@ static double obs_model(const dpomp_model_desc* m, int t, const int64_t* x) {
 }
 
 /* the event loop of iterate_particles! (src/hmm_particle_filter.jl:19-27) for ONE particle over (t, tmax].
- * Event k uses Philox block k/2, words 2(k%2) (waiting time) and 2(k%2)+1 (event type). */
+ * Attempt k (k = number of events so far) draws Philox2x32 words (waiting time, event type). */
 static int64_t sim_interval(const dpomp_model_desc* m, const double* th, int64_t* x, double time, double tmax,
-                            uint64_t key, uint32_t particle, uint32_t filter, uint32_t obs, int64_t max_events,
-                            int* overflow) {
+                            const sim_stream* st, uint32_t particle, int64_t max_events, int* overflow) {
     double cum[DPOMP_MAX_EVENTS];
-    uint32_t w[4] = {0, 0, 0, 0};
     int64_t k = 0;
     *overflow = 0;
     for (;;) {
         cum_rates(m, th, x, cum);
         if (!(cum[m->n_events - 1] > 0.0)) break; /* `== 0.0 && break` (:22); rates are >= 0 here */
         if (k >= max_events) { *overflow = 1; break; } /* event cap: documented divergence (no cap in the reference) */
-        if ((k & 1) == 0) stream_draw(key, particle, filter, obs, ORC_TAG_SIM, (uint32_t)(k >> 1), w);
-        double u_wait = u32_open(w[2 * (k & 1)]), u_evt = u32_open(w[2 * (k & 1) + 1]);
+        uint32_t w[2];
+        sim_draw(st, particle, (uint32_t)k, w);
+        double u_wait = u32_open(w[0]), u_evt = u32_open(w[1]);
         time -= log(u_wait) / cum[m->n_events - 1]; /* :23 */
         if (time > tmax) break;                     /* :24 */
         int e = choose_event(cum, m->n_events, u_evt);
@@ -438,12 +464,13 @@ int orc_pf_partial(const dpomp_model_desc* m, const double* theta, int64_t n, in
         const int t = oi - 1;
         const double tmax = m->obs_time[t];
         /* iterate_particles! (:9-33) */
+        const sim_stream st = sim_stream_init(key, filter, (uint32_t)t);
 #pragma omp parallel for schedule(static) num_threads(threads) reduction(+ : ev_total, ovf_total) if (threads > 1)
         for (int64_t p = 0; p < n; ++p) {
             int64_t x[DPOMP_MAX_COMPARTMENTS];
             for (int c = 0; c < C; ++c) x[c] = pop[c * n + p];
             int ovf = 0;
-            ev_total += sim_interval(m, theta, x, t_prev, tmax, key, (uint32_t)p, filter, (uint32_t)t, max_events, &ovf);
+            ev_total += sim_interval(m, theta, x, t_prev, tmax, &st, (uint32_t)p, max_events, &ovf);
             ovf_total += ovf;
             lw[p] = ovf ? -INFINITY : obs_model(m, t, x);
             for (int c = 0; c < C; ++c) pop[c * n + p] = x[c];
@@ -541,7 +568,8 @@ int orc_gillespie_sim(const dpomp_model_desc* m, const double* theta, uint64_t k
     int64_t ev = 0;
     for (int i = 0; i < m->n_obs; ++i) {
         int ovf = 0;
-        ev += sim_interval(m, theta, x, t, m->obs_time[i], key, 0u, 0u, (uint32_t)i, max_events, &ovf);
+        const sim_stream st = sim_stream_init(key, 0u, (uint32_t)i);
+        ev += sim_interval(m, theta, x, t, m->obs_time[i], &st, 0u, max_events, &ovf);
         for (int c = 0; c < m->n_compartments; ++c) out_states[(size_t)i * m->n_compartments + c] = x[c];
         t = m->obs_time[i];
     }

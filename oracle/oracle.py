@@ -125,3 +125,9 @@ def gillespie_sim(desc, theta, key: int = 0, max_events: int = 1 << 24):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def philox2(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32); out = np.zeros(2, dtype=np.uint32)
+    lib().orc_philox2x32_10(_p(c), C.c_uint32(key), _p(out))
+    return out
