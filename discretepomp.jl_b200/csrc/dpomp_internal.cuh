@@ -23,6 +23,8 @@ struct DevModel {
     Real trans[E][C];
     int xmask_i[C];
     int ic[C];
+    double obs_inv_tmp2;
+    int obs_tmp2_pow2;
     double obs_tmp1, obs_tmp2;  // log(1/(sqrt(2 pi) sigma)), 2 sigma^2 (src/hmm_examples.jl:61-62)
     int t0_index;
     int n_params;

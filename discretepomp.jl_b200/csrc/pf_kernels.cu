@@ -25,14 +25,44 @@ int sim_kernel_supported(int n_comp, int n_events) {
 // Kernel 2: one CTA per (filter, ancestor tile).  The tile's cumulative weights never leave the SM:
 //   w_q = exp(logw_q - m_b);  cw_q = off_b + f_b * incl_q   (deterministic scan tree)
 //   e_q = E(cw_q) = number of offspring whose uniform is <= cw_q  (counting form of `while u[i] > cw[j]`)
-//   offspring (lo_b, hi_b] belong to this tile; offspring i takes the first q with e_q >= i; its state row is copied
-//   from the source buffer (coalesced writes over i, near-sorted reads over q).
+//   offspring (lo_b, hi_b] belong to this tile; offspring i takes the first q with e_q >= i, i.e. ancestor q owns
+//   (max_{q'<q} e_q', max_{q'<=q} e_q'].  The offspring -> ancestor map of a window of TILE offspring is built in
+//   shared memory by a scatter of the range starts followed by an inclusive max-scan (no per-offspring search);
+//   state rows are then copied with coalesced writes over i and near-sorted reads over q.
 // ------------------------------------------------------------------------------------------------------------
+// inclusive max-scan over the block in blocked order (thread owns ITEMS consecutive values); returns in `v`, and the
+// inclusive value of the previous thread's last item in `prev` (identity for thread 0).  Two __syncthreads().
+template <int ITEMS>
+__device__ __forceinline__ void block_max_scan(int (&v)[ITEMS], int& prev, int identity, int* warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 1; k < ITEMS; ++k) v[k] = max(v[k], v[k - 1]);
+    int inc = v[ITEMS - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = max(inc, y);
+    }
+    int pl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) pl = identity;
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int wp = identity;
+#pragma unroll
+    for (int w = 0; w < kBlockThreads / 32; ++w)
+        if (w < warp) wp = max(wp, warp_tot[w]);
+    prev = max(wp, pl);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) v[k] = max(v[k], prev);
+    __syncthreads();
+}
+
 template <int ITEMS>
 __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
-    __shared__ int e_s[TILE];
+    __shared__ int am_s[TILE];  // offspring window -> local ancestor index
     __shared__ double warp_scratch[kBlockThreads / 32];
+    __shared__ int warp_iscratch[kBlockThreads / 32];
     __shared__ long long lohi_s[2];
 
     const int tid = threadIdx.x;
@@ -77,27 +107,70 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
 
     if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, off_b);
     if (tid == 32) lohi_s[1] = (tile == a.ntiles - 1) ? a.n : resample_ecount(ctx, off_n);
+    long long er[ITEMS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k)
-        e_s[tid * ITEMS + k] = (int)resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
+    for (int k = 0; k < ITEMS; ++k) er[k] = resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
     __syncthreads();
 
     const long long lo = lohi_s[0], hi = lohi_s[1];
     const long long rem = a.n - base_n;
     const int nvalid = rem < TILE ? (int)rem : TILE;
+    // owned offspring as offsets from lo: item q owns (prev_q, emax_q]; the last valid item closes the tile's range
+    int emax[ITEMS], prev;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int qk = tid * ITEMS + k;
+        long long ev = er[k] < lo ? lo : (er[k] > hi ? hi : er[k]);
+        if (qk >= nvalid - 1) ev = hi;
+        emax[k] = (int)(ev - lo);
+    }
+    block_max_scan<ITEMS>(emax, prev, 0, warp_iscratch);
+
+    const int total = (int)(hi - lo);
     const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad;
     int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad;
-    for (long long i = lo + 1 + tid; i <= hi; i += kBlockThreads) {
-        int lq = 0, hq = nvalid - 1;  // e of the last valid item is forced to hi >= i
-        while (lq < hq) {
-            const int mid = (lq + hq) >> 1;
-            long long ev = e_s[mid];
-            ev = ev < lo ? lo : (ev > hi ? hi : ev);
-            if (ev >= i) hq = mid; else lq = mid + 1;
+    for (int wlo = 0; wlo < total; wlo += TILE) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_s[tid * ITEMS + k] = -1;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int first = (k == 0) ? prev : emax[k - 1];  // offspring offsets (first, emax[k]] belong to item k
+            if (emax[k] > first && first < wlo + TILE && emax[k] > wlo) am_s[max(first - wlo, 0)] = tid * ITEMS + k;
         }
-        const long long src = base_n + lq;
-        for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + (i - 1)] = src_b[(size_t)c * a.n_pad + src];
-        if (a.anc) a.anc[(size_t)b * a.n_pad + (i - 1)] = (int32_t)src;
+        __syncthreads();
+        int am[ITEMS], dummy;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am[k] = am_s[tid * ITEMS + k];
+        block_max_scan<ITEMS>(am, dummy, -1, warp_iscratch);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_s[tid * ITEMS + k] = am[k];
+        __syncthreads();
+        // gather: striped over the window; per compartment, the ITEMS loads of a thread are issued before its stores
+        int srcq[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int pidx = j * kBlockThreads + tid;
+            srcq[j] = (wlo + pidx < total) ? am_s[pidx] : -1;
+        }
+        const long long i_base = lo + wlo + tid;  // 0-based offspring index of j = 0
+        for (int c = 0; c < a.n_comp; ++c) {
+            const int32_t* sc = src_b + (size_t)c * a.n_pad + base_n;
+            int32_t* dc = dst_b + (size_t)c * a.n_pad + i_base;
+            int vals[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0) vals[j] = sc[srcq[j]];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0) dc[j * kBlockThreads] = vals[j];
+        }
+        if (a.anc) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0) a.anc[(size_t)b * a.n_pad + i_base + j * kBlockThreads] = (int32_t)(base_n + srcq[j]);
+        }
+        __syncthreads();
     }
 }
 

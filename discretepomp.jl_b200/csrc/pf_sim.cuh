@@ -30,16 +30,27 @@ template <> struct Arith<double> {  // round-to-nearest, never contracted: the r
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 
+// resident CTAs per SM the register allocation is tuned for (the f64 parity loop is not tuned)
+template <typename Real, int C, int E>
+// measured on B200 (SIR C2): 4 resident CTAs with 64 registers and no spills beat 5 / 6 CTAs with 48 / 40 registers
+#ifndef DPOMP_SIM_MINB
+#define DPOMP_SIM_MINB 4
+#endif
+constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; }
+
+template <int N>
+struct alignas(4 * N) IntVec { int v[N]; };
+
 template <typename Real, int C, int E, int ITEMS>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, sim_min_blocks<Real, C, E>())
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
     constexpr int CHUNK = 32 * ITEMS;  // particles owned by one warp
     constexpr bool kF32 = sizeof(Real) == 4;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* lw_s = reinterpret_cast<double*>(smem_raw);   // [TILE] log weights of the tile
-    int* st_s = reinterpret_cast<int*>(lw_s + TILE);      // [C][TILE] staged compartment counts
+    int* ovf_s = reinterpret_cast<int*>(smem_raw);        // [TILE] 1 = the particle hit the event cap
+    int* st_s = ovf_s + TILE;                             // [C][TILE] staged compartment counts
     __shared__ double warp_scratch[kBlockThreads / 32];
     __shared__ int is_last_s;
     __shared__ uint32_t stream_s[3];
@@ -64,17 +75,20 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)a.t);
         stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;
     }
-    // stage the tile: coalesced loads, one slot per (thread, r); lw_s doubles as the overflow marker (0 = fine)
+    // stage the tile: each thread moves ITEMS consecutive particles per compartment with one vector access
+    using Vec = IntVec<ITEMS>;
+    {
+        Vec z;
 #pragma unroll
-    for (int r = 0; r < ITEMS; ++r) lw_s[r * kBlockThreads + tid] = 0.0;
+        for (int kk = 0; kk < ITEMS; ++kk) z.v[kk] = 0;
+        *reinterpret_cast<Vec*>(ovf_s + tid * ITEMS) = z;
+    }
     if (!a.fresh) {
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (c < a.n_comp) {
-#pragma unroll
-                for (int r = 0; r < ITEMS; ++r)
-                    st_s[c * TILE + r * kBlockThreads + tid] = pop_b[(size_t)c * a.n_pad + base_n + r * kBlockThreads + tid];
-            }
+            if (c < a.n_comp)
+                *reinterpret_cast<Vec*>(st_s + c * TILE + tid * ITEMS) =
+                    *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
     }
     __syncthreads();
     const SimStream ss{stream_s[0], stream_s[1], stream_s[2]};
@@ -161,7 +175,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
                 for (int c = 0; c < C; ++c)
                     if (c < a.n_comp) st_s[c * TILE + q] = (int)x[c];
-                if (ovf) lw_s[q] = -INFINITY;
+                if (ovf) ovf_s[q] = 1;
                 ev_local += k;
                 ovf_local += ovf ? 1u : 0u;
                 const int slot = next + __popc(fmask & lt_mask);
@@ -180,28 +194,39 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
     __syncthreads();
 
-    // ---- convergent pass: observation log-weight (src/hmm_examples.jl:63-65, exp deferred), write-back -----------
-    double* lw_b = a.logw + (size_t)b * a.n_pad + base_n;
+    // ---- convergent pass (blocked: thread owns ITEMS consecutive particles): observation log-weight
+    // (src/hmm_examples.jl:63-65, exp deferred) and vectorised write-back of states and log weights
+    double it[ITEMS], av[ITEMS], incl[ITEMS], excl[ITEMS];
+    {
+        int xs[ITEMS];
 #pragma unroll
-    for (int r = 0; r < ITEMS; ++r) {
-        const int qq = r * kBlockThreads + tid;
-        double lw = -INFINITY;
-        if (base_n + qq < a.n) {
-            int xs = 0;
+        for (int kk = 0; kk < ITEMS; ++kk) xs[kk] = 0;
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                if (c < a.n_comp) {
-                    const int v = st_s[c * TILE + qq];
-                    xs += m.xmask_i[c] * v;
-                    pop_b[(size_t)c * a.n_pad + base_n + qq] = v;
-                }
-            const double d = ysum - (double)xs;
-            if (lw_s[qq] == 0.0) lw = m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
+        for (int c = 0; c < C; ++c)
+            if (c < a.n_comp) {
+                const Vec v = *reinterpret_cast<const Vec*>(st_s + c * TILE + tid * ITEMS);
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) xs[kk] += m.xmask_i[c] * v.v[kk];
+                *reinterpret_cast<Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS) = v;  // padding slots included
+            }
+        const Vec of = *reinterpret_cast<const Vec*>(ovf_s + tid * ITEMS);
+#pragma unroll
+        for (int kk = 0; kk < ITEMS; ++kk) {
+            const double d = ysum - (double)xs[kk];
+            const double dd = __dmul_rn(d, d);
+            const double quot = m.obs_tmp2_pow2 ? __dmul_rn(dd, m.obs_inv_tmp2) : __ddiv_rn(dd, m.obs_tmp2);
+            const bool valid = base_n + tid * ITEMS + kk < a.n;
+            it[kk] = (valid && of.v[kk] == 0) ? m.obs_tmp1 - quot : -INFINITY;
         }
-        lw_s[qq] = lw;
-        lw_b[qq] = lw;
+        double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+        if constexpr (ITEMS % 2 == 0) {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(lw_b + kk) = make_double2(it[kk], it[kk + 1]);
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) lw_b[kk] = it[kk];
+        }
     }
-    __syncthreads();
 
     // event statistics: one atomic per warp
 #pragma unroll
@@ -215,13 +240,9 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
 
     // tile partials (m_b, s_b) in the blocked item order of the scan tree
-    double it[ITEMS], av[ITEMS], incl[ITEMS], excl[ITEMS];
     double mloc = -INFINITY;
 #pragma unroll
-    for (int kk = 0; kk < ITEMS; ++kk) {
-        it[kk] = lw_s[tid * ITEMS + kk];
-        mloc = fmax(mloc, it[kk]);
-    }
+    for (int kk = 0; kk < ITEMS; ++kk) mloc = fmax(mloc, it[kk]);
     const double m_b = block_max(mloc, warp_scratch);
     const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
 #pragma unroll
@@ -307,6 +328,11 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
     }
     m.obs_tmp1 = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * d.obs_sigma));
     m.obs_tmp2 = 2.0 * d.obs_sigma * d.obs_sigma;
+    {
+        int ex = 0;
+        m.obs_tmp2_pow2 = frexp(m.obs_tmp2, &ex) == 0.5 ? 1 : 0;  // then x / tmp2 == x * (1 / tmp2) bit for bit
+        m.obs_inv_tmp2 = 1.0 / m.obs_tmp2;
+    }
     m.t0_index = d.t0_index;
     m.n_params = d.n_params;
     return m;
@@ -316,7 +342,7 @@ template <typename Real, int C, int E, int ITEMS>
 static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream) {
     constexpr int TILE = kBlockThreads * ITEMS;
     const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
-    const size_t smem = (size_t)TILE * (sizeof(double) + C * sizeof(int));
+    const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
     auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS>;
     static bool configured = false;
     if (!configured) {
