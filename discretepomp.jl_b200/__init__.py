@@ -21,4 +21,7 @@ from .particle_filter import (C_DF_ESS_CRIT, C_DF_PF_P, DeviceModel, ParticleFil
                               device_model, estimate_likelihood, get_log_pdf_fn, get_particle_filter_lpdf,
                               get_private_model)
 from .resample import rs_multinomial, rs_stratified, rs_systematic, rsp_indices
+from .distributed import Comm, migration_plan, partition_bounds, partition_owner
+from .ibis import (compute_is_mu_covar, get_mv_param, get_prop_density, run_ibis_analysis, run_pibis)
+from .mcmc import gelman_diagnostic_sre, handle_rej_samples, run_pmcmc, run_pmcmc_analysis
 from . import _capi

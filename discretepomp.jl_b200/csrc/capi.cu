@@ -54,6 +54,8 @@ struct dpomp_pf {
     unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
     double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
     int64_t* slots_dev = nullptr;            // 2 * n_batch
+    uint32_t* filter_ids_dev = nullptr;      // n_batch, valid when use_filter_ids
+    bool use_filter_ids = false;
     double* h_theta = nullptr;               // pinned staging
     double* h_ll = nullptr;
     int64_t* h_slots = nullptr;
@@ -141,7 +143,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->cw); cudaFree(pf->anc);
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
-    cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev);
+    cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev);
     cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
     for (cudaEvent_t e : pf->kev) cudaEventDestroy(e);
     if (pf->ev0) cudaEventDestroy(pf->ev0);
@@ -209,6 +211,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->obs_time_dev, (size_t)d.n_obs * sizeof(double));
     ALLOC(pf->obs_ysum_dev, (size_t)d.n_obs * sizeof(double));
     ALLOC(pf->slots_dev, 2 * B * sizeof(int64_t));
+    ALLOC(pf->filter_ids_dev, B * sizeof(uint32_t));
 #undef ALLOC
     bool ok = cudaMallocHost((void**)&pf->h_theta, B * pf->n_params * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void**)&pf->h_ll, B * sizeof(double)) == cudaSuccess &&
@@ -251,6 +254,21 @@ int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t m) {
 int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t off) {
     if (!pf || off < 0 || off + pf->n_batch > 0xffffffffll) return fail(DPOMP_ERR_ARG, "batch_offset out of range");
     pf->batch_offset = off;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    if (!ids) { pf->use_filter_ids = false; return DPOMP_OK; }
+    if (n < 1 || n > pf->n_batch) return fail(DPOMP_ERR_ARG, "n out of range");
+    CK(cudaSetDevice(pf->device));
+    std::vector<uint32_t> tmp((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] > 0xffffffffll) return fail(DPOMP_ERR_ARG, "filter id out of range");
+        tmp[(size_t)i] = (uint32_t)ids[i];
+    }
+    CK(cudaMemcpyAsync(pf->filter_ids_dev, tmp.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->use_filter_ids = true;
     return DPOMP_OK;
 }
 int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key) {
@@ -336,6 +354,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
         a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
+        a.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
         if (pf->kernel_timing) CK(kernel_event(pf, 0, st));
         CK(launch_sim_weight(mh, pf->sim_precision, pf->items, a, st));
         if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
@@ -348,6 +367,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;
             r.t = t; r.rs_type = pf->rs_type; r.key = key; r.filter0 = (uint32_t)pf->batch_offset;
+            r.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
             if (pf->kernel_timing) CK(kernel_event(pf, 1, st));
             CK(launch_resample(pf->items, r, st));
             if (pf->kernel_timing) CK(kernel_event(pf, -1, st));

@@ -57,6 +57,7 @@ struct SimLaunch {
     int has_lik;             // obs_id[t] > 0
     uint64_t key;
     uint32_t filter0;        // global id of local filter 0
+    const uint32_t* filter_ids;  // optional explicit global ids [n_filters] (overrides filter0 + b)
     long long max_events;
 };
 
@@ -75,6 +76,7 @@ struct ResampleLaunch {
     int t, rs_type;
     uint64_t key;
     uint32_t filter0;
+    const uint32_t* filter_ids;
 };
 
 struct ModelHost {

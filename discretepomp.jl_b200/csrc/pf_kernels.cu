@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
     const int tile = blockIdx.x % a.ntiles;
     const int b = blockIdx.x / a.ntiles;
     const long long base_n = (long long)tile * TILE;
-    const uint32_t gfilter = a.filter0 + (uint32_t)b;
+    const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
 
     const double big_s = a.filt_s[b];
     const double off_b = a.tile_off[(size_t)b * (a.ntiles + 1) + tile];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
     const int b = (int)(gi / a.n_pad);
     const long long i = gi % a.n_pad;
     if (b >= a.n_filters || i >= a.n) return;
-    const uint32_t gfilter = a.filter0 + (uint32_t)b;
+    const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double big_s = a.filt_s[b];
     const Philox4 p = stream_draw(a.key, (uint32_t)i, gfilter, (uint32_t)a.t, kTagResample, 1u);
     const double chs = __dmul_rn(u53(p.w0, p.w1), big_s);

@@ -59,7 +59,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const int tile = blockIdx.x % a.ntiles;
     const int b = blockIdx.x / a.ntiles;
     const long long base_n = (long long)tile * TILE;
-    const uint32_t gfilter = a.filter0 + (uint32_t)b;
+    const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double* th = a.theta + (size_t)b * m.n_params;
 
     Real par[E];

@@ -1,0 +1,150 @@
+"""Multi-GPU plumbing for the outer layers: one process per GPU, torch.distributed over NCCL / NVLink.
+
+theta-particles (SMC^2, MBP-IBIS) and chains (pMCMC) are partitioned contiguously over ranks.  The small per-particle
+scalars (gx, aw) are exchanged with an all-gather; resampled filters move between ranks with one all-to-all of packed
+int32 population blocks (dpomp_pf_export_filters / dpomp_pf_import_filters).  Every rank draws the same host random
+numbers (same seed), so all ranks take identical outer-layer decisions without further communication, and particle-filter
+streams are keyed by the GLOBAL filter index, which makes results independent of the number of ranks.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+class Comm:
+    """Thin wrapper over torch.distributed; `Comm(None)` is the single-process communicator (no torch needed)."""
+
+    def __init__(self, group="world"):
+        self.dist = None
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.dist = dist
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = None  # torch device of the exchange buffers (cuda:k under NCCL, cpu under gloo)
+        if self.dist is not None:
+            import torch
+
+            self.device = (torch.device("cuda", torch.cuda.current_device())
+                           if self.dist.get_backend() == "nccl" else torch.device("cpu"))
+
+    # -- partition -------------------------------------------------------------------------------------------
+    def bounds(self, n: int) -> Tuple[int, int]:
+        """Contiguous block [lo, hi) of `n` items owned by this rank (sizes differ by at most one)."""
+        return partition_bounds(n, self.world, self.rank)
+
+    def owner(self, n: int, idx: np.ndarray) -> np.ndarray:
+        return partition_owner(n, self.world, idx)
+
+    # -- collectives -----------------------------------------------------------------------------------------
+    def allgather_f64(self, local: np.ndarray, n_total: int) -> np.ndarray:
+        """Concatenate each rank's contiguous block of doubles (block sizes per `bounds`)."""
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        if self.dist is None:
+            return local
+        import torch
+
+        sizes = [partition_bounds(n_total, self.world, r) for r in range(self.world)]
+        width = local.shape[1] if local.ndim == 2 else 1
+        maxn = max(hi - lo for lo, hi in sizes)
+        buf = torch.zeros(maxn * width, dtype=torch.float64, device=self.device)
+        buf[: local.size] = torch.from_numpy(local.reshape(-1)).to(self.device)
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(out, buf)
+        parts = [o[: (hi - lo) * width].cpu().numpy() for o, (lo, hi) in zip(out, sizes)]
+        res = np.concatenate(parts)
+        return res.reshape(-1, width) if local.ndim == 2 else res
+
+    def all_to_all_blocks(self, send, send_counts: Sequence[int], recv_counts: Sequence[int], block_words: int):
+        """Exchange packed int32 filter blocks.  `send` is a torch int32 tensor of sum(send_counts) * block_words words,
+        ordered by destination rank; returns the received tensor ordered by source rank."""
+        import torch
+
+        recv = torch.empty(int(sum(recv_counts)) * block_words, dtype=torch.int32, device=send.device)
+        if self.dist is None:
+            recv.copy_(send)
+            return recv
+        rs = [int(c) * block_words for c in recv_counts]
+        ss = [int(c) * block_words for c in send_counts]
+        if send.device != self.device:  # gloo with CUDA-resident filters (tests): stage through the host
+            tmp = torch.empty(recv.numel(), dtype=torch.int32, device=self.device)
+            self._all_to_all(tmp, send.to(self.device), rs, ss)
+            recv.copy_(tmp)
+        else:
+            self._all_to_all(recv, send, rs, ss)
+        return recv
+
+    def _all_to_all(self, recv, send, rs, ss):
+        import torch
+
+        if self.dist.get_backend() == "gloo":  # gloo has no all_to_all_single on every build: pairwise send/recv
+            ro = np.concatenate(([0], np.cumsum(rs))); so = np.concatenate(([0], np.cumsum(ss)))
+            reqs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    recv[ro[r]:ro[r + 1]] = send[so[r]:so[r + 1]]
+                    continue
+                if ss[r]:
+                    reqs.append(self.dist.isend(send[so[r]:so[r + 1]].contiguous(), r))
+            for r in range(self.world):
+                if r != self.rank and rs[r]:
+                    buf = torch.empty(rs[r], dtype=torch.int32)
+                    self.dist.recv(buf, r)
+                    recv[ro[r]:ro[r + 1]] = buf
+            for q in reqs:
+                q.wait()
+        else:
+            self.dist.all_to_all_single(recv, send, rs, ss)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+def partition_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def partition_owner(n: int, world: int, idx: np.ndarray) -> np.ndarray:
+    idx = np.asarray(idx, dtype=np.int64)
+    base, extra = divmod(n, world)
+    cut = extra * (base + 1)
+    return np.where(idx < cut, idx // (base + 1), extra + (idx - cut) // max(base, 1)).astype(np.int64)
+
+
+def migration_plan(nidx0: np.ndarray, n: int, world: int, rank: int):
+    """Who sends what after the outer resample `new[p] <- old[nidx0[p]]` (0-based global indices).
+
+    Returns (local_src, send_slots, send_counts, recv_slots, recv_counts):
+      local_src[k]   local source slot for local destination k, or k itself when the ancestor is remote (placeholder)
+      send_slots     local slots to pack, ordered by destination rank then by destination index
+      recv_slots     local destination slots of the received blocks, ordered by source rank then by destination index
+    """
+    nidx0 = np.asarray(nidx0, dtype=np.int64)
+    dst_owner = partition_owner(n, world, np.arange(n))
+    src_owner = partition_owner(n, world, nidx0)
+    lo, hi = partition_bounds(n, world, rank)
+    local_src = np.arange(hi - lo, dtype=np.int64)
+    mine = np.arange(lo, hi)
+    same = src_owner[mine] == rank
+    local_src[same] = nidx0[mine][same] - lo
+    send_slots: List[int] = []
+    send_counts = [0] * world
+    recv_slots: List[int] = []
+    recv_counts = [0] * world
+    for r in range(world):
+        if r == rank:
+            continue
+        out = np.nonzero((dst_owner == r) & (src_owner == rank))[0]  # destinations on r fed by my filters
+        send_slots.extend((nidx0[out] - lo).tolist())
+        send_counts[r] = len(out)
+        inc = np.nonzero((dst_owner == rank) & (src_owner == r))[0]  # my destinations fed by r
+        recv_slots.extend((inc - lo).tolist())
+        recv_counts[r] = len(inc)
+    return local_src, np.asarray(send_slots, dtype=np.int64), send_counts, np.asarray(recv_slots, dtype=np.int64), recv_counts

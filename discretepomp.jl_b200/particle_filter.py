@@ -113,6 +113,14 @@ class ParticleFilter:
     def set_batch_offset(self, off: int) -> None:
         _capi.check(_capi.lib().dpomp_pf_set_batch_offset(self._h, int(off)))
 
+    def set_filter_ids(self, ids) -> None:
+        """Explicit 0-based GLOBAL ids of the first len(ids) filters (random-stream keying); None resets."""
+        if ids is None:
+            _capi.check(_capi.lib().dpomp_pf_set_filter_ids(self._h, None, 0))
+        else:
+            a = _capi.as_i64(ids)
+            _capi.check(_capi.lib().dpomp_pf_set_filter_ids(self._h, _capi.ptr(a), len(a)))
+
     def set_stream_key(self, key: int) -> None:
         _capi.check(_capi.lib().dpomp_pf_set_stream_key(self._h, C.c_uint64(key)))
 
@@ -210,6 +218,27 @@ class ParticleFilter:
     def loglik_device(self, theta_dev_ptr: int, n_batch_used: int, out_dev_ptr: int) -> None:
         _capi.check(_capi.lib().dpomp_pf_loglik_device(self._h, C.c_void_p(theta_dev_ptr), int(n_batch_used),
                                                        C.c_void_p(out_dev_ptr)))
+
+    @property
+    def filter_words(self) -> int:
+        """int32 words of one packed filter: n_compartments * padded particle count."""
+        tile, _ = self.geometry()
+        return self.n_comp * (-(-self.n_particles // tile) * tile)
+
+    def export_tensor(self, slots):
+        """Pack the listed filters (1-based) into a new torch int32 CUDA tensor (migration send buffer)."""
+        import torch
+
+        s = _capi.as_i64(slots)
+        buf = torch.empty(len(s) * self.filter_words, dtype=torch.int32, device="cuda")
+        if len(s):
+            self.export_filters(s, buf.data_ptr())
+        return buf
+
+    def import_tensor(self, slots, buf) -> None:
+        s = _capi.as_i64(slots)
+        if len(s):
+            self.import_filters(s, buf.data_ptr())
 
     def export_filters(self, slots, device_dst_ptr: int) -> None:
         s = _capi.as_i64(slots)

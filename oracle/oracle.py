@@ -131,3 +131,31 @@ def philox2(ctr, key) -> np.ndarray:
     c = np.asarray(ctr, dtype=np.uint32); out = np.zeros(2, dtype=np.uint32)
     lib().orc_philox2x32_10(_p(c), C.c_uint32(key), _p(out))
     return out
+
+
+def run_pibis(desc, theta_init, prior_lo, prior_hi, ess_rs_crit=0.3, ind_prop=True, alpha=1.002, npf=200, n_props=1,
+              seed=1, threads=1, max_events=1 << 20):
+    """run_pibis (src/hmm_ibis.jl:12-135).  theta_init: (n_theta, outer_p).  Returns dict(mu, cv, theta, w, bme, k_log, pf_steps)."""
+    th = np.ascontiguousarray(np.asarray(theta_init, dtype=np.float64).T).copy()  # (outer_p, n_theta) == Julia col-major
+    outer_p, d = th.shape
+    lo = np.ascontiguousarray(prior_lo, dtype=np.float64); hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+    mu = np.zeros(d); cv = np.zeros((d, d)); w = np.zeros(outer_p); bme = np.zeros(2)
+    k_log = np.zeros(2, dtype=np.int64); steps = C.c_int64()
+    rc = lib().orc_run_pibis(C.byref(desc), _p(th), C.c_int64(outer_p), _p(lo), _p(hi), C.c_double(ess_rs_crit),
+                             int(bool(ind_prop)), C.c_double(alpha), C.c_int64(npf), int(n_props), C.c_uint64(seed),
+                             int(threads), C.c_int64(max_events), _p(mu), _p(cv), _p(w), _p(bme), _p(k_log), C.byref(steps))
+    assert rc == 0
+    return dict(mu=mu, cv=cv, theta=th.T.copy(), w=w, bme=bme, k_log=k_log, pf_steps=steps.value)
+
+
+def run_pmcmc(desc, theta_init, steps, adapt_period, npf, prior_lo, prior_hi, c_initial=0.1, seed=1, threads=1,
+              max_events=1 << 20):
+    """pMCMC per src/hmm_mcmc.jl:349-365,166-211.  theta_init: (n_theta, chains).  Returns samples (n_theta, steps, chains)."""
+    th0 = np.ascontiguousarray(np.asarray(theta_init, dtype=np.float64).T)
+    n_chains, d = th0.shape
+    lo = np.ascontiguousarray(prior_lo, dtype=np.float64); hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+    samples = np.zeros((n_chains, steps, d)); acc = np.zeros(n_chains, dtype=np.int64)
+    rc = lib().orc_run_pmcmc(C.byref(desc), _p(th0), n_chains, int(steps), int(adapt_period), C.c_int64(npf), _p(lo), _p(hi),
+                             C.c_double(c_initial), C.c_uint64(seed), int(threads), C.c_int64(max_events), _p(samples), _p(acc))
+    assert rc == 0
+    return np.ascontiguousarray(samples.transpose(2, 1, 0)), acc

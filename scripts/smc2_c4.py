@@ -1,0 +1,25 @@
+"""SMC^2 on BASELINE config C4 (LOTKA [70,70], 8192 theta x 4096 state particles, prior U(0,(1,0.01,1))); single or
+multi rank (torchrun).  Prints one line of timing + evidence."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import dpomp_b200 as dp
+outer_p = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+npf = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+comm = None
+if world > 1:
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    comm = dp.Comm()
+model = dp.generate_model("LOTKA", [70, 70])
+model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
+y = dp.get_observations("tests/golden/lotka_c4.csv")
+t0 = time.time()
+res = dp.run_ibis_analysis(model, y, np=outer_p, npf=npf, seed=1, comm=comm, verbose=False)
+dt = time.time() - t0
+if rank == 0:
+    print(f"SMC2 C4 outer_p={outer_p} npf={npf} world={world}: {dt:.2f} s  theta-particle-obs/s={outer_p*len(y)/dt:.1f} "
+          f"bme={res.bme} mu={res.mu} k_log={res.k_log}")
+if world > 1:
+    torch.distributed.destroy_process_group()

@@ -1,0 +1,125 @@
+"""GPU tests of the outer layers that call the particle filter: SMC^2 (run_pibis), pMCMC, the whole-filter gathers and
+the migration path.  Statistical bars: z-tests / tolerances against the oracle's literal restatement and the reference's
+anchors (-ln p(y) = 19.98 in the reference's single seeded run, 20.18 +- 0.1 prior importance sampling)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _sis(dp):
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    return model, y, dp.get_private_model(model, y), theta
+
+
+def test_filter_gathers_are_exact(dp):
+    model, y, hmm, theta = _sis(dp)
+    dm = dp.device_model(hmm)
+    nb, n = 7, 1500
+    a = dp.ParticleFilter(dm, n, nb, seed=3)
+    thetas = theta[:, None] * np.linspace(0.7, 1.3, nb)[None, :]
+    a.partial(thetas, 1, 2)
+    before = [a.get_pop(b + 1) for b in range(nb)]
+    nidx = np.array([3, 3, 1, 7, 7, 7, 2])
+    a.permute(nidx)
+    for p in range(nb):
+        assert np.array_equal(a.get_pop(p + 1), before[nidx[p] - 1])
+    b = dp.ParticleFilter(dm, n, nb, seed=4)
+    b.partial(thetas, 1, 1)
+    keep = b.get_pop(2)
+    b.copy_from(a, [1, 5], [4, 6])
+    assert np.array_equal(b.get_pop(1), a.get_pop(4)) and np.array_equal(b.get_pop(5), a.get_pop(6))
+    assert np.array_equal(b.get_pop(2), keep)
+    buf = a.export_tensor([2, 6])
+    assert buf.numel() == 2 * a.filter_words and buf.is_cuda
+    b.import_tensor([3, 4], buf)
+    assert np.array_equal(b.get_pop(3), a.get_pop(2)) and np.array_equal(b.get_pop(4), a.get_pop(6))
+    pop = np.arange(n * 2).reshape(n, 2) % 97
+    b.set_pop(7, pop)
+    assert np.array_equal(b.get_pop(7), pop)
+
+
+def test_smc2_default_config_against_oracle_and_anchor(dp, orc):
+    """run_ibis_analysis defaults (4000 theta-particles x 200 state particles) on SIS/pooley."""
+    model, y, hmm, theta = _sis(dp)
+    cm = dp.compile_model(model, y)
+    reps = 5
+    ours, ref, mus, rmus = [], [], [], []
+    for s in range(reps):
+        r = dp.run_ibis_analysis(model, y, seed=40 + s, verbose=False)
+        ours.append(r.bme.copy()); mus.append(r.mu.copy())
+        assert r.theta.shape == (2, 4000) and r.weight.shape == (4000,)
+        th0 = model.prior.rand(4000, np.random.default_rng(70 + s))
+        o = orc.run_pibis(cm.desc, th0, model.prior.lower, model.prior.upper, npf=200, seed=90 + s, threads=orc.max_threads())
+        ref.append(o["bme"].copy()); rmus.append(o["mu"].copy())
+    ours, ref, mus, rmus = map(np.array, (ours, ref, mus, rmus))
+    for k in range(2):  # both evidence estimators
+        z = (ours[:, k].mean() - ref[:, k].mean()) / np.sqrt(ours[:, k].var(ddof=1) / reps + ref[:, k].var(ddof=1) / reps)
+        assert abs(z) < 4.5, (k, ours[:, k], ref[:, k])
+    assert 19.7 < ours[:, 0].mean() < 20.4  # reference single run 19.98; prior-IS anchor 20.18 +- 0.1
+    assert np.all(np.abs(mus.mean(axis=0) - rmus.mean(axis=0)) < 0.08 * np.abs(rmus.mean(axis=0)))
+
+
+def test_smc2_stratified_outer_and_dependent_proposals(dp):
+    model, y, hmm, theta = _sis(dp)
+    th0 = model.prior.rand(1000, np.random.default_rng(1))
+    r = dp.run_pibis(hmm, th0, 0.5, False, 1.002, 200, n_props=2, seed=8, outer_rs=dp.rs_stratified, verbose=False)
+    assert 19.5 < r.bme[0] < 20.6 and r.k_log[0] > 0 and np.all(np.isfinite(r.mu))
+
+
+def test_pmcmc_posterior_against_oracle(dp, orc):
+    model, y, hmm, theta = _sis(dp)
+    cm = dp.compile_model(model, y)
+    chains, steps, adapt = 8, 1500, 500
+    th0 = np.tile(np.array([[0.003], [0.1]]), (1, chains)) * np.random.default_rng(2).uniform(0.8, 1.2, (2, chains))
+    res = dp.run_pmcmc(hmm, th0, steps=steps, adapt_period=adapt, p=256, seed=11, verbose=False)
+    assert res.samples.theta.shape == (2, steps, chains) and res.adapt_period == adapt
+    ref, acc = orc.run_pmcmc(cm.desc, th0, steps, adapt, 256, model.prior.lower, model.prior.upper, seed=12, threads=orc.max_threads())
+    ref_mu = ref[:, adapt:, :].reshape(2, -1).mean(axis=1)
+    # posterior mean theta ~ (0.0032, 0.107); chains are short, so compare to 12 %
+    assert np.all(np.abs(res.samples.mu - ref_mu) < 0.12 * ref_mu), (res.samples.mu, ref_mu)
+    assert 0.002 < res.samples.mu[0] < 0.0045 and 0.06 < res.samples.mu[1] < 0.16
+    assert np.all(res.accepted > 20)
+
+
+def _smc2_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    import dpomp_b200 as dp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    comm = None
+    if world > 1:
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+        comm = dp.Comm()
+    torch.cuda.set_device(0)
+    model = dp.generate_model("SIS", [100, 1])
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "pooley.csv"))
+    hmm = dp.get_private_model(model, y)
+    th0 = model.prior.rand(301, np.random.default_rng(5))  # odd count: ragged partition
+    res = dp.run_pibis(hmm, th0, 0.5, True, 1.002, 300, rng=np.random.default_rng(6), seed=7, comm=comm, verbose=False)
+    if rank == 0:
+        np.savez(out_path, bme=res.bme, mu=res.mu, theta=res.theta, w=res.weight)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def test_smc2_two_ranks_equal_one_rank_bitwise(tmp_path):
+    """Two ranks (gloo collectives, both on cuda:0) run the real kernels, export/import migration included, and must
+    reproduce the single-process run bit for bit: random streams are keyed by global theta-particle ids."""
+    one, two = str(tmp_path / "one.npz"), str(tmp_path / "two.npz")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_smc2_worker, args=(1, port, one), nprocs=1, join=True)
+    mp.spawn(_smc2_worker, args=(2, port, two), nprocs=2, join=True)
+    a, b = np.load(one), np.load(two)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k

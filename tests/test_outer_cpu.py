@@ -1,0 +1,127 @@
+"""CPU tests of the host-side outer layers (SMC^2, pMCMC) and their multi-rank sharding.  The CUDA particle filter is
+replaced by an oracle-backed stand-in (tests/fake_pf.py) so that the bookkeeping, the migration plan and the
+world_size-2 gloo path can be exercised without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_case
+
+
+def test_partition_and_migration_plan(dp):
+    n, world = 11, 3
+    bounds = [dp.partition_bounds(n, world, r) for r in range(world)]
+    assert bounds == [(0, 4), (4, 8), (8, 11)]
+    assert dp.partition_owner(n, world, np.arange(n)).tolist() == [0] * 4 + [1] * 4 + [2] * 3
+    rng = np.random.default_rng(0)
+    nidx0 = np.sort(rng.integers(0, n, n))
+    # replay the plan on plain arrays: every destination must end up with its ancestor's payload
+    payload = [np.arange(lo, hi) * 10 for lo, hi in bounds]
+    plans = [dp.migration_plan(nidx0, n, world, r) for r in range(world)]
+    sent = {}
+    for r, (local_src, send_slots, send_counts, recv_slots, recv_counts) in enumerate(plans):
+        pos = 0
+        for dst in range(world):
+            sent[(r, dst)] = payload[r][send_slots[pos:pos + send_counts[dst]]]
+            pos += send_counts[dst]
+    for r, (local_src, send_slots, send_counts, recv_slots, recv_counts) in enumerate(plans):
+        new = payload[r][local_src].copy()
+        pos = 0
+        for src in range(world):
+            got = sent[(src, r)]
+            assert len(got) == recv_counts[src]
+            new[recv_slots[pos:pos + len(got)]] = got
+            pos += len(got)
+        lo, hi = bounds[r]
+        assert np.array_equal(new, nidx0[lo:hi] * 10)
+
+
+def _pibis_worker(rank, world, port, out_path, kind):
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dpomp_b200 as dp
+    from fake_pf import OraclePF
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    comm = None
+    if world > 1:
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+        comm = dp.Comm()
+    model = dp.generate_model("SIS", [100, 1])
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "pooley.csv"))
+    hmm = dp.get_private_model(model, y)
+    desc = dp.compile_model(model, y)
+    factory = lambda nb, sd: OraclePF(desc.desc, 40, nb, 1, sd)
+    if kind == "pibis":
+        theta0 = model.prior.rand(24, np.random.default_rng(3))
+        res = dp.run_pibis(hmm, theta0, 0.5, True, 1.002, 40, rng=np.random.default_rng(9), seed=5, comm=comm,
+                           pf_factory=factory, outer_rs=lambda w, rng: _host_rs_systematic(w, rng), verbose=False)
+        out = dict(bme=res.bme, mu=res.mu, theta=res.theta, w=res.weight, k=res.k_log)
+    else:
+        theta0 = model.prior.rand(5, np.random.default_rng(4)) * 0.5 + np.array([[0.002], [0.05]])
+        res = dp.run_pmcmc(hmm, theta0, steps=40, adapt_period=20, p=40, seed=6, comm=comm, pf_factory=factory, verbose=False)
+        out = dict(theta=res.samples.theta, mu=res.samples.mu, acc=res.accepted)
+    if rank == 0:
+        np.savez(out_path, **out)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def _host_rs_systematic(w, rng):
+    # CPU stand-in for the GPU search hook (tests only): the oracle's literal rs_systematic
+    from oracle import oracle as orc
+    return orc.rs(1, w, [rng.random()])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("kind", ["pibis", "pmcmc"])
+def test_world_size_2_gloo_matches_single_process(tmp_path, kind):
+    """Sharding theta-particles / chains over 2 ranks (gloo) gives bit-identical results to one process: the streams are
+    keyed by global filter ids and call counters, the host RNG is replicated."""
+    one = str(tmp_path / "one.npz"); two = str(tmp_path / "two.npz")
+    _pibis_worker(0, 1, 0, one, kind)
+    mp.spawn(_pibis_worker, args=(2, _free_port(), two, kind), nprocs=2, join=True)
+    a, b = np.load(one), np.load(two)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_run_pibis_bookkeeping_against_oracle(dp, orc):
+    """Host driver (batched sweep) vs the oracle's literal run_pibis on the same tiny problem: same law.  With so few
+    particles only coarse agreement is expected; the GPU suite does the real z-tests."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_pf import OraclePF
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    hmm = dp.get_private_model(model, y)
+    cm = dp.compile_model(model, y)
+    ours, ref = [], []
+    for s in range(6):
+        th0 = model.prior.rand(200, np.random.default_rng(s))
+        r = dp.run_pibis(hmm, th0, 0.3, True, 1.002, 50, rng=np.random.default_rng(100 + s), seed=s,
+                         pf_factory=lambda nb, sd: OraclePF(cm.desc, 50, nb, 1, sd), outer_rs=_host_rs_systematic, verbose=False)
+        ours.append(r.bme[0])
+        ref.append(orc.run_pibis(cm.desc, th0, model.prior.lower, model.prior.upper, npf=50, seed=200 + s, threads=orc.max_threads())["bme"][0])
+    assert abs(np.mean(ours) - np.mean(ref)) < 0.5, (ours, ref)
+    assert 19.0 < np.mean(ours) < 21.5
+
+
+def test_prop_density_guard(dp):
+    old = dp.ibis.ProposalDensity.identity(2) if hasattr(dp, "ibis") else None
+    from dpomp_b200.ibis import ProposalDensity
+    old = ProposalDensity.identity(2)
+    assert dp.get_prop_density(np.array([[1.0, 2.0], [2.0, 1.0]]), old) is old  # not positive definite -> keep old
+    new = dp.get_prop_density(np.array([[2.0, 0.5], [0.5, 1.0]]), old)
+    assert np.allclose(new.chol @ new.chol.T, [[2.0, 0.5], [0.5, 1.0]])
+    mu, cv = dp.compute_is_mu_covar(np.array([[1.0, 3.0], [2.0, 2.0]]), np.array([1.0, 3.0]))
+    assert np.allclose(mu, [2.5, 2.0]) and np.allclose(cv, [[0.75, 0.0], [0.0, 0.0]])
