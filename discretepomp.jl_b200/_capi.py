@@ -93,6 +93,16 @@ _SIGS = {
     "dpomp_pf_export_filters": (C.c_int, [_P, _P, C.c_int32, _P]),
     "dpomp_pf_import_filters": (C.c_int, [_P, _P, C.c_int32, _P]),
     "dpomp_pf_loglik_device": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "dpomp_mbp_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(_P)]),
+    "dpomp_mbp_destroy": (C.c_int, [_P]),
+    "dpomp_mbp_set_batch_offset": (C.c_int, [_P, C.c_int64]),
+    "dpomp_mbp_set_stream_key": (C.c_int, [_P, C.c_uint64]),
+    "dpomp_mbp_reset": (C.c_int, [_P]),
+    "dpomp_mbp_iterate": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "dpomp_mbp_propose": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "dpomp_mbp_accept": (C.c_int, [_P, _P, C.c_int32]),
+    "dpomp_mbp_permute": (C.c_int, [_P, _P, C.c_int32]),
+    "dpomp_mbp_get_particle": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
     "dpomp_resample_indices": (
         C.c_int,
         [C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, C.c_int32],

@@ -18,6 +18,7 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+int dpomp_set_error(int code, const std::string& msg) { return fail(code, msg); }  // for the other C-ABI TUs
 #define CK(expr)                                                                                     \
     do {                                                                                             \
         cudaError_t _e = (expr);                                                                     \

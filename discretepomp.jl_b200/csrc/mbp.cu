@@ -1,0 +1,504 @@
+// mbp.cu -- MBP-IBIS layer on the device: one trajectory with its full event list per theta-particle.
+//
+// Replaces, for ALL theta-particles of a rank in one launch each:
+//   iterate_particle!             src/hmm_sim.jl:6-25      -> mbp_iterate_kernel
+//   partial_model_based_proposal  src/hmm_mbp.jl:83-108    -> mbp_propose_kernel  (iterate_mbp! :7-44,
+//                                                             initialise_trajectory! :47-80 inlined)
+//   ptcls2[p] = deepcopy(ptcls[nidx[p]]) (src/hmm_ibis.jl:196-199), ptcls[p] = xf (:214) -> mbp_copy_kernel
+//
+// Trajectory store in HBM: per particle `cap` events as f64 time + u8 type (1-based), int32 length, int32 final state,
+// f64 log_like[2].  One thread per trajectory (the Gillespie / MBP walks are sequential per trajectory; the work is
+// ~300 events per trajectory, tiny next to the particle filter), f64 arithmetic with the reference's expressions, never
+// contracted, so the walks are draw-for-draw comparable with the oracle.  `cap` plays the role of MAX_TRAJ
+// (src/DiscretePOMP.jl:40): a trajectory that would exceed it gets log_like = -Inf.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dpomp_dev.cuh"
+#include "dpomp_internal.cuh"
+
+namespace dpomp {
+
+constexpr uint32_t kTagMbp = 2u;
+
+struct MbpModel {  // integer rate table + f64 observation constants, runtime C / E
+    int n_comp, n_events, n_params, t0_index;
+    int par[DPOMP_MAX_EVENTS];
+    int f1[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS], k1[DPOMP_MAX_EVENTS];
+    int f2[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS], k2[DPOMP_MAX_EVENTS];
+    int dn[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS], kd[DPOMP_MAX_EVENTS], has_den[DPOMP_MAX_EVENTS];
+    int trans[DPOMP_MAX_EVENTS][DPOMP_MAX_COMPARTMENTS];
+    int xmask[DPOMP_MAX_COMPARTMENTS], ic[DPOMP_MAX_COMPARTMENTS];
+    double obs_tmp1, obs_tmp2;
+};
+
+struct MbpStore {
+    double* ev_time;      // [n][cap]
+    unsigned char* ev_type;  // [n][cap]
+    int* len;             // [n]
+    int* fc;              // [n][C]
+    double* ll;           // [n][2]
+};
+
+struct MbpStream {
+    uint32_t k, a, b, id, j;
+};
+__device__ __forceinline__ MbpStream mbp_stream_init(uint64_t key, uint32_t id, uint32_t obs, uint32_t which) {
+    const Philox4 p = stream_draw(key, 0u, id, obs, kTagMbp, which);
+    return MbpStream{p.w0, p.w1, p.w2, id, 0u};
+}
+__device__ __forceinline__ uint2 mbp_draw(MbpStream& s) {
+    const uint2 w = philox2x32_10(s.id ^ s.a, s.j ^ s.b, s.k);
+    s.j += 1;
+    return w;
+}
+
+__device__ __forceinline__ void mbp_rates(const MbpModel& m, const double* th, const int* x, double* out) {
+    for (int e = 0; e < m.n_events; ++e) {
+        long long l1 = m.k1[e], l2 = m.k2[e], dn = m.kd[e];
+        for (int c = 0; c < m.n_comp; ++c) {
+            l1 += (long long)m.f1[e][c] * x[c];
+            l2 += (long long)m.f2[e][c] * x[c];
+            dn += (long long)m.dn[e][c] * x[c];
+        }
+        const double p = m.par[e] >= 0 ? th[m.par[e]] : 1.0;
+        double r = __dmul_rn(__dmul_rn(p, (double)l1), (double)l2);
+        if (m.has_den[e]) r = (dn == 0) ? 0.0 : __ddiv_rn(r, (double)dn);
+        out[e] = r;
+    }
+}
+__device__ __forceinline__ void mbp_cumsum(double* v, int n) {
+    for (int i = 1; i < n; ++i) v[i] = __dadd_rn(v[i - 1], v[i]);
+}
+__device__ __forceinline__ int mbp_choose(const double* cum, int n, double u) {
+    const double etc = __dmul_rn(u, cum[n - 1]);
+    for (int i = 0; i < n - 1; ++i)
+        if (cum[i] > etc) return i;
+    return n - 1;
+}
+__device__ __forceinline__ double mbp_obs_ll(const MbpModel& m, double ysum, const int* x) {
+    long long xs = 0;
+    for (int c = 0; c < m.n_comp; ++c) xs += (long long)m.xmask[c] * x[c];
+    const double d = ysum - (double)xs;
+    return m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
+}
+
+// iterate_particle! (src/hmm_sim.jl:6-25) for every particle
+__global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant__ MbpModel m, MbpStore st, const double* theta,
+                                                           const double* obs_time, const double* obs_ysum, int n, int cap, int t,
+                                                           int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double* th = theta + (size_t)p * m.n_params;
+    int x[DPOMP_MAX_COMPARTMENTS];
+    for (int c = 0; c < m.n_comp; ++c) x[c] = st.fc[(size_t)p * m.n_comp + c];
+    int len = st.len[p];
+    double* et = st.ev_time + (size_t)p * cap;
+    unsigned char* ey = st.ev_type + (size_t)p * cap;
+    double time = fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : obs_time[t - 1];
+    const double t_obs = obs_time[t];
+    MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, (uint32_t)t, 0u);
+    double cum[DPOMP_MAX_EVENTS];
+    bool overflow = false;
+    for (;;) {
+        mbp_rates(m, th, x, cum);
+        mbp_cumsum(cum, m.n_events);
+        const double tot = cum[m.n_events - 1];
+        if (!(tot > 0.0)) break;
+        const uint2 w = mbp_draw(rs);
+        time = time - log(u32_open_f64(w.x)) / tot;
+        if (time > t_obs) break;
+        const int e = mbp_choose(cum, m.n_events, u32_open_f64(w.y));
+        for (int c = 0; c < m.n_comp; ++c) x[c] += m.trans[e][c];
+        if (len >= cap) { overflow = true; break; }
+        et[len] = time;
+        ey[len] = (unsigned char)(e + 1);
+        ++len;
+    }
+    for (int c = 0; c < m.n_comp; ++c) st.fc[(size_t)p * m.n_comp + c] = x[c];
+    st.len[p] = len;
+    double out;
+    if (overflow) {
+        st.ll[2 * (size_t)p] = -INFINITY;
+        out = -INFINITY;
+    } else {
+        out = mbp_obs_ll(m, obs_ysum[t], x);
+        if (has_lik) st.ll[2 * (size_t)p] += out;
+    }
+    out_logg[p] = out;
+}
+
+// partial_model_based_proposal (src/hmm_mbp.jl:83-108): xi = current store, xf = proposal store
+__global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant__ MbpModel m, MbpStore xi, MbpStore xf,
+                                                           const double* theta_i, const double* theta_f, const unsigned char* valid,
+                                                           const double* obs_time, const double* obs_ysum, const int* obs_haslik,
+                                                           int n, int cap, int ymax, uint64_t key, uint32_t id0, double* out_ll) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double ll0 = 0.0, ll1 = 0.0;
+    int flen = 0;
+    int xfc[DPOMP_MAX_COMPARTMENTS], pop_i[DPOMP_MAX_COMPARTMENTS];
+    for (int c = 0; c < m.n_comp; ++c) xfc[c] = pop_i[c] = m.ic[c];
+    if (!valid[p]) {
+        ll0 = ll1 = -INFINITY;
+    } else {
+        const double* thi = theta_i + (size_t)p * m.n_params;
+        const double* thf = theta_f + (size_t)p * m.n_params;
+        const double* it = xi.ev_time + (size_t)p * cap;
+        const unsigned char* iy = xi.ev_type + (size_t)p * cap;
+        const int ilen = xi.len[p];
+        double* ft = xf.ev_time + (size_t)p * cap;
+        unsigned char* fy = xf.ev_type + (size_t)p * cap;
+        MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, 0u, 1u);
+        double lf[DPOMP_MAX_EVENTS], li[DPOMP_MAX_EVENTS], ld[DPOMP_MAX_EVENTS];
+        const int E = m.n_events;
+        int evt = 0;
+        double time = 0.0;
+        bool overflow = false;
+        if (m.t0_index > 0) {  // initialise_trajectory! (:47-80)
+            const double t0f = thf[m.t0_index - 1], t0i = thi[m.t0_index - 1];
+            if (t0f < t0i) {
+                double t = t0f;
+                for (;;) {
+                    mbp_rates(m, thf, xfc, lf);
+                    mbp_cumsum(lf, E);
+                    if (!(lf[E - 1] > 0.0)) break;
+                    const uint2 w = mbp_draw(rs);
+                    t = t - log(u32_open_f64(w.x)) / lf[E - 1];
+                    if (t > t0i) break;
+                    const int e = mbp_choose(lf, E, u32_open_f64(w.y));
+                    if (flen >= cap) { overflow = true; break; }
+                    ft[flen] = t; fy[flen] = (unsigned char)(e + 1); ++flen;
+                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                }
+            } else {
+                while (evt < ilen && !(it[evt] > t0f)) {
+                    const int e = iy[evt] - 1;
+                    for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
+                    ++evt;
+                }
+            }
+            time = t0f > t0i ? t0f : t0i;
+        }
+        for (int oi = 0; oi < ymax && !overflow; ++oi) {
+            const double t_obs = obs_time[oi];
+            for (;;) {  // iterate_mbp! (:14-42)
+                const double tmax = (evt >= ilen) ? t_obs : (t_obs < it[evt] ? t_obs : it[evt]);
+                mbp_rates(m, thi, pop_i, li);
+                for (;;) {
+                    mbp_rates(m, thf, xfc, lf);
+                    for (int e = 0; e < E; ++e) {
+                        const double dlt = __dsub_rn(lf[e], li[e]);
+                        ld[e] = dlt > 0.0 ? dlt : 0.0;
+                    }
+                    mbp_cumsum(ld, E);
+                    if (!(ld[E - 1] > 0.0)) break;
+                    const uint2 w = mbp_draw(rs);
+                    time = time - log(u32_open_f64(w.x)) / ld[E - 1];
+                    if (time > tmax) break;
+                    const int e = mbp_choose(ld, E, u32_open_f64(w.y));
+                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                    if (flen >= cap) { overflow = true; break; }
+                    ft[flen] = time; fy[flen] = (unsigned char)(e + 1); ++flen;
+                }
+                if (overflow) break;
+                if (evt >= ilen) break;
+                if (it[evt] > t_obs) break;
+                const int e = iy[evt] - 1;
+                time = it[evt];
+                const double prob_keep = __ddiv_rn(lf[e], li[e]);
+                bool keep = prob_keep > 1.0;
+                if (!keep) {
+                    const uint2 w = mbp_draw(rs);
+                    keep = prob_keep > u53(w.x, w.y);
+                }
+                if (keep) {
+                    if (flen >= cap) { overflow = true; break; }
+                    ft[flen] = time; fy[flen] = (unsigned char)(e + 1); ++flen;
+                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                }
+                for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
+                ++evt;
+            }
+            if (overflow) break;
+            time = t_obs;
+            ll1 = mbp_obs_ll(m, obs_ysum[oi], xfc);
+            if (obs_haslik[oi]) ll0 += ll1;
+        }
+        if (overflow) ll0 = -INFINITY;
+    }
+    for (int c = 0; c < m.n_comp; ++c) xf.fc[(size_t)p * m.n_comp + c] = xfc[c];
+    xf.len[p] = flen;
+    xf.ll[2 * (size_t)p] = ll0;
+    xf.ll[2 * (size_t)p + 1] = ll1;
+    out_ll[2 * (size_t)p] = ll0;
+    out_ll[2 * (size_t)p + 1] = ll1;
+}
+
+// dst[dst_slot[k]] <- src[src_slot[k]] : one CTA per particle, only the live part of the trajectory moves
+__global__ void __launch_bounds__(128) mbp_copy_kernel(MbpStore dst, MbpStore src, const int64_t* dst_slots, const int64_t* src_slots,
+                                                        int cap, int n_comp) {
+    const int k = blockIdx.x;
+    const long long d = dst_slots ? dst_slots[k] - 1 : k, s = src_slots ? src_slots[k] - 1 : k;
+    const int len = src.len[s];
+    const double* st = src.ev_time + (size_t)s * cap;
+    double* dt = dst.ev_time + (size_t)d * cap;
+    const unsigned char* sy = src.ev_type + (size_t)s * cap;
+    unsigned char* dy = dst.ev_type + (size_t)d * cap;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        dt[i] = st[i];
+        dy[i] = sy[i];
+    }
+    if (threadIdx.x < n_comp) dst.fc[(size_t)d * n_comp + threadIdx.x] = src.fc[(size_t)s * n_comp + threadIdx.x];
+    if (threadIdx.x == 32) dst.len[d] = len;
+    if (threadIdx.x == 64) { dst.ll[2 * d] = src.ll[2 * s]; dst.ll[2 * d + 1] = src.ll[2 * s + 1]; }
+}
+
+__global__ void mbp_reset_kernel(const __grid_constant__ MbpModel m, MbpStore st, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    for (int c = 0; c < m.n_comp; ++c) st.fc[(size_t)p * m.n_comp + c] = m.ic[c];
+    st.len[p] = 0;
+    st.ll[2 * (size_t)p] = st.ll[2 * (size_t)p + 1] = 0.0;
+}
+
+}  // namespace dpomp
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+using namespace dpomp;
+
+struct dpomp_model {  // same layout as in capi.cu
+    ModelHost h;
+};
+extern "C" const char* dpomp_last_error(void);
+int dpomp_set_error(int code, const std::string& msg);  // defined in capi.cu
+
+#define MCK(expr)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) return dpomp_set_error(DPOMP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct dpomp_mbp {
+    const dpomp_model* model = nullptr;
+    int device = 0, n = 0, cap = 0;
+    cudaStream_t stream = nullptr;
+    MbpModel dm{};
+    MbpStore store[3]{};   // [cur], [cur ^ 1] (resample workspace), [2] proposal
+    int cur = 0;
+    uint64_t seed = 0, call_index = 0, forced_key = 0;
+    bool key_forced = false;
+    long long batch_offset = 0;
+    double *theta_i = nullptr, *theta_f = nullptr, *out = nullptr, *obs_time = nullptr, *obs_ysum = nullptr;
+    int* obs_haslik = nullptr;
+    unsigned char* valid = nullptr;
+    int64_t* slots = nullptr;  // 2 * n
+};
+
+static uint64_t mbp_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t mbp_next_key(dpomp_mbp* h) {
+    const uint64_t k = h->key_forced ? h->forced_key : mbp_splitmix64(h->seed ^ mbp_splitmix64(0x4D4250ull + h->call_index));
+    h->key_forced = false;
+    h->call_index += 1;
+    return k;
+}
+static void mbp_free(dpomp_mbp* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int s = 0; s < 3; ++s) {
+        cudaFree(h->store[s].ev_time); cudaFree(h->store[s].ev_type); cudaFree(h->store[s].len);
+        cudaFree(h->store[s].fc); cudaFree(h->store[s].ll);
+    }
+    cudaFree(h->theta_i); cudaFree(h->theta_f); cudaFree(h->out); cudaFree(h->obs_time); cudaFree(h->obs_ysum);
+    cudaFree(h->obs_haslik); cudaFree(h->valid); cudaFree(h->slots);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" {
+
+int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_traj, uint64_t seed, int32_t device,
+                     dpomp_mbp** out) {
+    if (!model || !out) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n_particles < 1 || max_traj < 1) return dpomp_set_error(DPOMP_ERR_ARG, "n_particles and max_traj must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return dpomp_set_error(DPOMP_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0) MCK(cudaGetDevice(&device));
+    if (device >= ndev) return dpomp_set_error(DPOMP_ERR_ARG, "device index out of range");
+    MCK(cudaSetDevice(device));
+    dpomp_mbp* h = new (std::nothrow) dpomp_mbp();
+    if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "out of host memory");
+    const dpomp_model_desc& d = model->h.desc;
+    h->model = model; h->device = device; h->n = n_particles; h->cap = max_traj; h->seed = seed;
+    MbpModel& m = h->dm;
+    m.n_comp = d.n_compartments; m.n_events = d.n_events; m.n_params = d.n_params; m.t0_index = d.t0_index;
+    for (int ev = 0; ev < DPOMP_MAX_EVENTS; ++ev) {
+        m.par[ev] = d.rate_par[ev]; m.k1[ev] = d.rate_k1[ev]; m.k2[ev] = d.rate_k2[ev]; m.kd[ev] = d.rate_kd[ev];
+        m.has_den[ev] = d.rate_has_den[ev];
+        for (int c = 0; c < DPOMP_MAX_COMPARTMENTS; ++c) {
+            m.f1[ev][c] = d.rate_f1[ev][c]; m.f2[ev][c] = d.rate_f2[ev][c]; m.dn[ev][c] = d.rate_dn[ev][c];
+            m.trans[ev][c] = d.trans[ev][c];
+        }
+    }
+    for (int c = 0; c < DPOMP_MAX_COMPARTMENTS; ++c) { m.xmask[c] = d.obs_xmask[c]; m.ic[c] = (int)d.initial_condition[c]; }
+    m.obs_tmp1 = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * d.obs_sigma));
+    m.obs_tmp2 = 2.0 * d.obs_sigma * d.obs_sigma;
+    const size_t N = (size_t)n_particles, CAP = (size_t)max_traj;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int s = 0; s < 3 && ok; ++s) {
+        ok = cudaMalloc((void**)&h->store[s].ev_time, N * CAP * sizeof(double)) == cudaSuccess &&
+             cudaMalloc((void**)&h->store[s].ev_type, N * CAP) == cudaSuccess &&
+             cudaMalloc((void**)&h->store[s].len, N * sizeof(int)) == cudaSuccess &&
+             cudaMalloc((void**)&h->store[s].fc, N * m.n_comp * sizeof(int)) == cudaSuccess &&
+             cudaMalloc((void**)&h->store[s].ll, N * 2 * sizeof(double)) == cudaSuccess;
+    }
+    std::vector<int> haslik(d.n_obs);
+    for (int t = 0; t < d.n_obs; ++t) haslik[t] = model->h.obs_id[t] > 0;
+    ok = ok && cudaMalloc((void**)&h->theta_i, N * m.n_params * sizeof(double)) == cudaSuccess &&
+         cudaMalloc((void**)&h->theta_f, N * m.n_params * sizeof(double)) == cudaSuccess &&
+         cudaMalloc((void**)&h->out, N * 2 * sizeof(double)) == cudaSuccess &&
+         cudaMalloc((void**)&h->obs_time, d.n_obs * sizeof(double)) == cudaSuccess &&
+         cudaMalloc((void**)&h->obs_ysum, d.n_obs * sizeof(double)) == cudaSuccess &&
+         cudaMalloc((void**)&h->obs_haslik, d.n_obs * sizeof(int)) == cudaSuccess &&
+         cudaMalloc((void**)&h->valid, N) == cudaSuccess && cudaMalloc((void**)&h->slots, 2 * N * sizeof(int64_t)) == cudaSuccess &&
+         cudaMemcpy(h->obs_time, model->h.obs_time.data(), d.n_obs * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->obs_ysum, model->h.obs_ysum.data(), d.n_obs * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->obs_haslik, haslik.data(), d.n_obs * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        std::string msg = std::string("dpomp_mbp_create: ") + cudaGetErrorString(cudaGetLastError());
+        mbp_free(h);
+        return dpomp_set_error(DPOMP_ERR_CUDA, msg);
+    }
+    mbp_reset_kernel<<<(n_particles + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[0], n_particles);
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_destroy(dpomp_mbp* h) { mbp_free(h); return DPOMP_OK; }
+
+int dpomp_mbp_set_batch_offset(dpomp_mbp* h, int64_t off) {
+    if (!h || off < 0 || off + h->n > 0xffffffffll) return dpomp_set_error(DPOMP_ERR_ARG, "batch_offset out of range");
+    h->batch_offset = off;
+    return DPOMP_OK;
+}
+int dpomp_mbp_set_stream_key(dpomp_mbp* h, uint64_t key) {
+    if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "null handle");
+    h->forced_key = key; h->key_forced = true;
+    return DPOMP_OK;
+}
+int dpomp_mbp_reset(dpomp_mbp* h) {
+    if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "null handle");
+    MCK(cudaSetDevice(h->device));
+    mbp_reset_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->n);
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(h->stream));
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_i, int32_t fresh, double* out_logg) {
+    if (!h || !theta || !out_logg) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const dpomp_model_desc& d = h->model->h.desc;
+    if (n < 1 || n > h->n || obs_i < 1 || obs_i > d.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "argument out of range");
+    MCK(cudaSetDevice(h->device));
+    const uint64_t key = mbp_next_key(h);
+    MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    mbp_iterate_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap,
+                                                               obs_i - 1, fresh ? 1 : 0, h->model->h.obs_id[obs_i - 1] > 0, key,
+                                                               (uint32_t)h->batch_offset, h->out);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCK(cudaStreamSynchronize(h->stream));
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_propose(dpomp_mbp* h, const double* theta_i, const double* theta_f, const uint8_t* valid, int32_t n, int32_t ymax,
+                      double* out_loglike) {
+    if (!h || !theta_i || !theta_f || !valid || !out_loglike) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const dpomp_model_desc& d = h->model->h.desc;
+    if (n < 1 || n > h->n || ymax < 1 || ymax > d.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "argument out of range");
+    MCK(cudaSetDevice(h->device));
+    const uint64_t key = mbp_next_key(h);
+    const size_t tb = (size_t)n * d.n_params * sizeof(double);
+    MCK(cudaMemcpyAsync(h->theta_i, theta_i, tb, cudaMemcpyHostToDevice, h->stream));
+    MCK(cudaMemcpyAsync(h->theta_f, theta_f, tb, cudaMemcpyHostToDevice, h->stream));
+    MCK(cudaMemcpyAsync(h->valid, valid, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    mbp_propose_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid,
+                                                               h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap, ymax, key,
+                                                               (uint32_t)h->batch_offset, h->out);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCK(cudaStreamSynchronize(h->stream));
+    return DPOMP_OK;
+}
+
+static int mbp_copy(dpomp_mbp* h, int dst_store, int src_store, const int64_t* dst_slots, const int64_t* src_slots, int n) {
+    if (n == 0) return DPOMP_OK;
+    for (int i = 0; i < n; ++i) {
+        if (dst_slots && (dst_slots[i] < 1 || dst_slots[i] > h->n)) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
+        if (src_slots && (src_slots[i] < 1 || src_slots[i] > h->n)) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
+    }
+    if (dst_slots) MCK(cudaMemcpyAsync(h->slots, dst_slots, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (src_slots) MCK(cudaMemcpyAsync(h->slots + h->n, src_slots, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    mbp_copy_kernel<<<n, 128, 0, h->stream>>>(h->store[dst_store], h->store[src_store], dst_slots ? h->slots : nullptr,
+                                              src_slots ? h->slots + h->n : nullptr, h->cap, h->dm.n_comp);
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(h->stream));
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_accept(dpomp_mbp* h, const int64_t* slots, int32_t n) {
+    if (!h || (!slots && n > 0)) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n < 0 || n > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "n out of range");
+    MCK(cudaSetDevice(h->device));
+    return mbp_copy(h, h->cur, 2, slots, slots, n);
+}
+
+int dpomp_mbp_permute(dpomp_mbp* h, const int64_t* nidx, int32_t n) {
+    if (!h || !nidx) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n != h->n) return dpomp_set_error(DPOMP_ERR_ARG, "permute needs one index per particle");
+    MCK(cudaSetDevice(h->device));
+    int rc = mbp_copy(h, h->cur ^ 1, h->cur, nullptr, nidx, n);
+    if (rc) return rc;
+    h->cur ^= 1;
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_get_particle(dpomp_mbp* h, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times, int32_t* types,
+                           int64_t cap_out, double* loglike2) {
+    if (!h || !fc || !len || !loglike2) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (p < 1 || p > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
+    MCK(cudaSetDevice(h->device));
+    const MbpStore& s = h->store[which ? 2 : h->cur];
+    int l = 0;
+    int fci[DPOMP_MAX_COMPARTMENTS];
+    MCK(cudaMemcpy(&l, s.len + (p - 1), sizeof(int), cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(fci, s.fc + (size_t)(p - 1) * h->dm.n_comp, h->dm.n_comp * sizeof(int), cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(loglike2, s.ll + 2 * (size_t)(p - 1), 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < h->dm.n_comp; ++c) fc[c] = fci[c];
+    *len = l;
+    const int ncopy = l < cap_out ? l : (int)cap_out;
+    if (times && types && ncopy > 0) {
+        std::vector<unsigned char> ty((size_t)ncopy);
+        MCK(cudaMemcpy(times, s.ev_time + (size_t)(p - 1) * h->cap, (size_t)ncopy * sizeof(double), cudaMemcpyDeviceToHost));
+        MCK(cudaMemcpy(ty.data(), s.ev_type + (size_t)(p - 1) * h->cap, (size_t)ncopy, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ncopy; ++i) types[i] = ty[(size_t)i];
+    }
+    return DPOMP_OK;
+}
+
+}  // extern "C"

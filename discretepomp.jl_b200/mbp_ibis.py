@@ -1,0 +1,175 @@
+"""MBP-IBIS -- host-side mirror of run_mbp_ibis (src/hmm_ibis.jl:140-244).
+
+Each theta-particle is ONE trajectory with its event list (struct Particle, src/hmm_structs.jl:51-58), kept in HBM by
+the dpomp_mbp handle.  The per-particle loops of the reference become one C-ABI call each:
+    iterate_particle! over all particles        (:176-179)  -> dpomp_mbp_iterate
+    ptcls2[p] = deepcopy(ptcls[nidx[p]])        (:196-199)  -> dpomp_mbp_permute
+    partial_model_based_proposal over particles (:207)      -> dpomp_mbp_propose
+    ptcls[p] = xf for accepted proposals        (:214)      -> dpomp_mbp_accept
+Priors, MvNormal proposals, accept/reject and the evidence bookkeeping stay host code, as in the reference.
+
+Stated departures: (1) a mutation sweep proposes for all particles at once, so the random-walk scale `tj`
+(ind_prop = false, the MBP-IBIS default) is frozen within a sweep and updated afterwards with the same factors
+(SURVEY.md 7); (2) `outer_rs` may be rs_stratified (BASELINE config C5) where the reference hard-codes rs_systematic
+(:194); (3) the trajectory capacity `max_traj` defaults to 8192 events instead of MAX_TRAJ = 196000.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _capi
+from .distributed import Comm
+from .ibis import (_M64, ProposalDensity, compute_is_mu_covar, get_mv_param, get_prop_density, splitmix64)
+from .particle_filter import compute_ess, device_model
+from .resample import rs_systematic
+from .structs import HiddenMarkovModel, ImportanceSample
+
+
+class MbpParticles:
+    """dpomp_mbp handle: the trajectories of this process's theta-particles."""
+
+    def __init__(self, dmodel, n_particles: int, max_traj: int = 8192, seed: int = 1, device: int = -1):
+        self.dmodel, self.n, self.cap = dmodel, int(n_particles), int(max_traj)
+        self.n_params = int(dmodel.compiled.desc.n_params)
+        self.n_comp = int(dmodel.compiled.desc.n_compartments)
+        self._h = C.c_void_p()
+        _capi.check(_capi.lib().dpomp_mbp_create(dmodel.handle, self.n, self.cap, C.c_uint64(seed & _M64), device,
+                                                 C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                _capi.lib().dpomp_mbp_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def set_stream_key(self, key: int) -> None:
+        _capi.check(_capi.lib().dpomp_mbp_set_stream_key(self._h, C.c_uint64(key)))
+
+    def set_batch_offset(self, off: int) -> None:
+        _capi.check(_capi.lib().dpomp_mbp_set_batch_offset(self._h, int(off)))
+
+    def reset(self) -> None:
+        _capi.check(_capi.lib().dpomp_mbp_reset(self._h))
+
+    def _cols(self, theta) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(theta, dtype=np.float64).T)  # (n, n_theta) == Julia column-major
+
+    def iterate(self, theta, obs_i: int, fresh: bool) -> np.ndarray:
+        th = self._cols(theta)
+        out = np.empty(th.shape[0])
+        _capi.check(_capi.lib().dpomp_mbp_iterate(self._h, _capi.ptr(th), th.shape[0], int(obs_i), 1 if fresh else 0,
+                                                  _capi.ptr(out)))
+        return out
+
+    def propose(self, theta_i, theta_f, valid, ymax: int) -> np.ndarray:
+        ti, tf = self._cols(theta_i), self._cols(theta_f)
+        v = np.ascontiguousarray(valid, dtype=np.uint8)
+        out = np.empty((ti.shape[0], 2))
+        _capi.check(_capi.lib().dpomp_mbp_propose(self._h, _capi.ptr(ti), _capi.ptr(tf), _capi.ptr(v), ti.shape[0], int(ymax),
+                                                  _capi.ptr(out)))
+        return out
+
+    def accept(self, slots) -> None:
+        s = _capi.as_i64(slots)
+        if len(s):
+            _capi.check(_capi.lib().dpomp_mbp_accept(self._h, _capi.ptr(s), len(s)))
+
+    def permute(self, nidx) -> None:
+        s = _capi.as_i64(nidx)
+        _capi.check(_capi.lib().dpomp_mbp_permute(self._h, _capi.ptr(s), len(s)))
+
+    def get_particle(self, p: int, proposal: bool = False):
+        """(final_condition, times, types(1-based), log_like[2]) of particle p (1-based)."""
+        fc = np.zeros(self.n_comp, dtype=np.int64); ln = C.c_int64()
+        times = np.zeros(self.cap); types = np.zeros(self.cap, dtype=np.int32); ll = np.zeros(2)
+        _capi.check(_capi.lib().dpomp_mbp_get_particle(self._h, int(p), 1 if proposal else 0, _capi.ptr(fc), C.byref(ln),
+                                                       _capi.ptr(times), _capi.ptr(types), self.cap, _capi.ptr(ll)))
+        return fc, times[: ln.value].copy(), types[: ln.value].copy(), ll
+
+
+def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, n_props: int, ind_prop: bool,
+                 alpha: float, msgs: bool = True, rng: Optional[np.random.Generator] = None, seed: int = 1,
+                 comm: Optional[Comm] = None, max_traj: int = 8192, outer_rs: Callable = rs_systematic,
+                 particles_factory: Optional[Callable] = None, verbose: bool = True) -> ImportanceSample:
+    """run_mbp_ibis(model, theta, ess_rs_crit, n_props, ind_prop, alpha, msgs = true) (src/hmm_ibis.jl:140-244).
+    `theta` is (n_theta, outer_p).  Single process (MBP-IBIS trajectories do not migrate between ranks in this round)."""
+    if comm is not None and comm.world > 1:
+        raise NotImplementedError("run_mbp_ibis: multi-rank sharding of trajectories is not implemented in this round")
+    rng = rng or np.random.default_rng(seed)
+    theta = np.array(theta, dtype=np.float64, order="C")
+    d, outer_p = theta.shape
+    if verbose:
+        print(f"Running: {outer_p}-particle MBP-IBIS analysis (model: {model.model_name})")
+    start_time = time.time_ns()
+    ess_crit = ess_rs_crit * outer_p
+    make = particles_factory or (lambda n, sd: MbpParticles(device_model(model), n, max_traj, sd))
+    ptcls = make(outer_p, seed)
+    prior = np.array([model.prior.logpdf(theta[:, p]) for p in range(outer_p)])  # Particle.prior (:153)
+    log_like = np.zeros(outer_p)  # Particle.log_like[1], mirrored on the host for the acceptance ratio
+    propd = ProposalDensity.identity(d)
+    tj = 0.2
+    w = np.ones(outer_p)
+    k_log = np.zeros(2, dtype=np.int64)
+    bme = np.zeros(2)
+    call = 0
+
+    def next_key() -> int:
+        nonlocal call
+        call += 1
+        return splitmix64((seed & _M64) ^ splitmix64(0x4D42 + call))
+
+    mu, cv = compute_is_mu_covar(theta, w)
+    for obs_i in range(1, len(model.obs_data) + 1):
+        ptcls.set_stream_key(next_key())
+        lg = ptcls.iterate(theta, obs_i, fresh=(obs_i == 1))  # :176-179
+        if model.obs_data[obs_i - 1].obs_id > 0:
+            log_like = log_like + lg  # -Inf propagates for overflowed trajectories (src/hmm_sim.jl:17-20)
+            gx = np.exp(lg)
+            lml = np.log(np.sum(w * gx) / np.sum(w))
+            bme[0] += lml
+            w = w * gx
+            mu, cv = compute_is_mu_covar(theta, w)
+            if compute_ess(w) < ess_crit:
+                propd = get_prop_density(cv, propd)
+                nidx = outer_rs(w.copy(), rng)
+                mtd_gx = gx[nidx - 1].copy()
+                ptcls.permute(nidx)
+                theta, prior, log_like = theta[:, nidx - 1], prior[nidx - 1], log_like[nidx - 1]
+                mlr = np.mean(gx[nidx - 1]) * np.exp(lml)
+                k_log[0] += outer_p * n_props
+                for _ in range(n_props):  # :203-219, one sweep over all particles
+                    theta_f = (mu[:, None] + propd.rand(rng, outer_p)) if ind_prop else get_mv_param(propd, tj, theta, rng)
+                    prior_f = np.array([model.prior.logpdf(theta_f[:, p]) for p in range(outer_p)])
+                    valid = prior_f != -np.inf
+                    ptcls.set_stream_key(next_key())
+                    ll_f = ptcls.propose(theta, theta_f, valid, obs_i)  # (outer_p, 2)
+                    u = rng.random(outer_p)
+                    with np.errstate(over="ignore", invalid="ignore"):
+                        ratio = np.exp(prior_f - prior) * np.exp(ll_f[:, 0] - log_like)  # :212
+                    accepted = ratio > u  # NaN compares false, as in the reference
+                    ptcls.accept(np.nonzero(accepted)[0] + 1)
+                    mtd_gx[accepted] = np.exp(ll_f[accepted, 1])
+                    theta[:, accepted] = theta_f[:, accepted]
+                    prior[accepted] = prior_f[accepted]
+                    log_like[accepted] = ll_f[accepted, 0]
+                    n_acc = int(accepted.sum())
+                    k_log[1] += n_acc
+                    tj *= alpha ** n_acc * 0.999 ** (outer_p - n_acc)
+                bme[1] += np.log(mlr / np.mean(mtd_gx))
+                w = np.ones(outer_p)
+            else:
+                bme[1] += np.log(np.sum(w * gx) / np.sum(w))
+    mu, cv = compute_is_mu_covar(theta, w)
+    output = ImportanceSample(mu, cv, theta, w, time.time_ns() - start_time, -bme)
+    if verbose:
+        ar = 100.0 * k_log[1] / k_log[0] if k_log[0] else float("nan")
+        print(f"- finished in {output.run_time / 1e9:.1f} seconds (AR := {ar:.3g}%)")
+    output.k_log = k_log
+    output.particles = ptcls
+    return output

@@ -175,6 +175,32 @@ int dpomp_pf_import_filters(dpomp_pf* pf, const int64_t* slots, int32_t n, const
 int dpomp_pf_loglik_device(dpomp_pf* pf, const double* theta_dev, int32_t n_batch_used, double* out_ll_dev);
 
 /*
+ * MBP-IBIS layer (run_mbp_ibis src/hmm_ibis.jl:140-244): n_particles theta-particles, each ONE trajectory with its event
+ * list (struct Particle src/hmm_structs.jl:51-58) resident in HBM; max_traj plays MAX_TRAJ (src/DiscretePOMP.jl:40).
+ */
+typedef struct dpomp_mbp dpomp_mbp;
+int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_traj, uint64_t seed, int32_t device,
+                     dpomp_mbp** out_mbp);
+int dpomp_mbp_destroy(dpomp_mbp* mbp);
+int dpomp_mbp_set_batch_offset(dpomp_mbp* mbp, int64_t batch_offset);  /* global id of local particle 0 */
+int dpomp_mbp_set_stream_key(dpomp_mbp* mbp, uint64_t key);            /* Philox key of the NEXT call */
+int dpomp_mbp_reset(dpomp_mbp* mbp);  /* every particle back to the initial condition, empty trajectory, log_like = 0 */
+/* iterate_particle! (src/hmm_sim.jl:6-25) for particles 1..n up to observation obs_i (1-based); theta is n_params x n
+ * column-major; fresh != 0 starts at t = 0 / theta[t0_index], else at the previous observation time.
+ * out_logg[n] = observation log-likelihood (-Inf after a trajectory overflow). */
+int dpomp_mbp_iterate(dpomp_mbp* mbp, const double* theta, int32_t n, int32_t obs_i, int32_t fresh, double* out_logg);
+/* partial_model_based_proposal (src/hmm_mbp.jl:83-108) for particles 1..n: proposal trajectories under theta_f conditional
+ * on the current ones (theta_i); valid[p] == 0 marks a proposal outside the prior (log_like = -Inf, nothing simulated).
+ * out_loglike[n][2] = Particle.log_like of the proposals.  The proposals stay in the handle until dpomp_mbp_accept. */
+int dpomp_mbp_propose(dpomp_mbp* mbp, const double* theta_i, const double* theta_f, const uint8_t* valid, int32_t n,
+                      int32_t ymax, double* out_loglike);
+int dpomp_mbp_accept(dpomp_mbp* mbp, const int64_t* slots, int32_t n);    /* ptcls[p] = xf (src/hmm_ibis.jl:214), 1-based */
+int dpomp_mbp_permute(dpomp_mbp* mbp, const int64_t* nidx, int32_t n);    /* ptcls2[p] = deepcopy(ptcls[nidx[p]]) (:196-199) */
+/* read back one particle (which: 0 current, 1 proposal): final state, event list (types 1-based), log_like[2] */
+int dpomp_mbp_get_particle(dpomp_mbp* mbp, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times,
+                           int32_t* types, int64_t cap_out, double* loglike2);
+
+/*
  * Bit-exactness hook for the resampling searches (host buffers).
  *   on_cumulative = 1: `w` is already cumulative  -> rsp_* semantics (src/hmm_pf_resample.jl:24-42, and the
  *                      intended semantics of the broken rsp_stratified/rsp_multinomial :46-63, :5-20)

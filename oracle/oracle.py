@@ -16,7 +16,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("dpomp_oracle.c", "dpomp_oracle_ibis.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("dpomp_oracle.c", "dpomp_oracle_ibis.c", "dpomp_oracle_mbp.c", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return LIB_PATH
@@ -159,3 +159,39 @@ def run_pmcmc(desc, theta_init, steps, adapt_period, npf, prior_lo, prior_hi, c_
                              C.c_double(c_initial), C.c_uint64(seed), int(threads), C.c_int64(max_events), _p(samples), _p(acc))
     assert rc == 0
     return np.ascontiguousarray(samples.transpose(2, 1, 0)), acc
+
+
+def mbp_iterate(desc, theta, fc, ev_time, ev_type, length, log_like, t_start, obs_i, key, pid):
+    """iterate_particle! (src/hmm_sim.jl:6-25) on flat arrays (updated in place).  Returns (log g, new length)."""
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    ln = C.c_int64(int(length))
+    f = lib().orc_mbp_iterate
+    f.restype = C.c_double
+    g = f(C.byref(desc), _p(th), _p(fc), _p(ev_time), _p(ev_type), C.byref(ln), C.c_int64(len(ev_time)), _p(log_like),
+          C.c_double(t_start), int(obs_i), C.c_uint64(key), C.c_uint32(pid))
+    return g, ln.value
+
+
+def mbp_propose(desc, theta_i, theta_f, xi_time, xi_type, xi_len, cap, ymax, key, pid):
+    """partial_model_based_proposal (src/hmm_mbp.jl:83-108).  Returns (times, types(1-based), fc, log_like[2], overflow)."""
+    ti = np.ascontiguousarray(theta_i, dtype=np.float64); tf = np.ascontiguousarray(theta_f, dtype=np.float64)
+    xt = np.ascontiguousarray(xi_time, dtype=np.float64); xy = np.ascontiguousarray(xi_type, dtype=np.int32)
+    ot = np.zeros(cap); oy = np.zeros(cap, dtype=np.int32); ln = C.c_int64(0)
+    fc = np.zeros(desc.n_compartments, dtype=np.int64); ll = np.zeros(2)
+    rc = lib().orc_mbp_propose(C.byref(desc), _p(ti), _p(tf), _p(xt), _p(xy), C.c_int64(int(xi_len)), _p(ot), _p(oy), C.byref(ln),
+                               C.c_int64(cap), _p(fc), _p(ll), int(ymax), C.c_uint64(key), C.c_uint32(pid))
+    return ot[: ln.value].copy(), oy[: ln.value].copy(), fc, ll, rc
+
+
+def run_mbp_ibis(desc, theta_init, prior_lo, prior_hi, ess_rs_crit=0.5, n_props=3, ind_prop=False, alpha=1.002, rs_type=1,
+                 cap=4096, seed=1, threads=1):
+    """run_mbp_ibis (src/hmm_ibis.jl:140-244).  Returns dict(mu, cv, theta, w, bme, k_log)."""
+    th = np.ascontiguousarray(np.asarray(theta_init, dtype=np.float64).T).copy()
+    outer_p, d = th.shape
+    lo = np.ascontiguousarray(prior_lo, dtype=np.float64); hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+    mu = np.zeros(d); cv = np.zeros((d, d)); w = np.zeros(outer_p); bme = np.zeros(2); k_log = np.zeros(2, dtype=np.int64)
+    rc = lib().orc_run_mbp_ibis(C.byref(desc), _p(th), C.c_int64(outer_p), _p(lo), _p(hi), C.c_double(ess_rs_crit), int(n_props),
+                                int(bool(ind_prop)), C.c_double(alpha), int(rs_type), C.c_int64(cap), C.c_uint64(seed), int(threads),
+                                _p(mu), _p(cv), _p(w), _p(bme), _p(k_log))
+    assert rc == 0
+    return dict(mu=mu, cv=cv, theta=th.T.copy(), w=w, bme=bme, k_log=k_log)

@@ -1,0 +1,117 @@
+"""GPU tests of the MBP-IBIS layer (row a12): iterate_particle!, partial_model_based_proposal and run_mbp_ibis through
+the C ABI, against the oracle's literal restatement on identical Philox draws."""
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dp, case="sis_pooley", t0=False):
+    model, y, hmm, theta = load_case(dp, case)
+    if t0:
+        def rf(out, p, x):
+            out[0] = p[0] * x[0] * x[1]; out[1] = p[1] * x[1]
+        model = dp.generate_custom_model("SIS", rf, [100, 1], [[-1, 1], [1, -1]], prior=dp.generate_weak_prior(3), t0_index=3)
+        theta = np.array([0.003, 0.1, 4.0])
+    hmm = dp.get_private_model(model, y)
+    return model, y, hmm, theta
+
+
+@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False)])
+def test_iterate_and_propose_match_oracle(dp, orc, case, t0):
+    model, y, hmm, theta = _setup(dp, case, t0)
+    dm = dp.device_model(hmm)
+    desc = dm.compiled.desc
+    n, cap = 64, 4096
+    rng = np.random.default_rng(3)
+    thetas = theta[:, None] * rng.uniform(0.8, 1.25, size=(len(theta), n))
+    if t0:
+        thetas[2] = rng.uniform(1.0, 8.0, n)
+    pt = dp.MbpParticles(dm, n, cap, seed=5)
+    n_obs = min(len(y), 4)
+    # oracle state per particle
+    o_fc = np.tile(np.asarray(model.initial_condition, dtype=np.int64), (n, 1))
+    o_t = np.zeros((n, cap)); o_y = np.zeros((n, cap), dtype=np.int32); o_len = np.zeros(n, dtype=np.int64); o_ll = np.zeros((n, 2))
+    for obs_i in range(1, n_obs + 1):
+        key = 9000 + obs_i
+        pt.set_stream_key(key)
+        lg = pt.iterate(thetas, obs_i, fresh=(obs_i == 1))
+        for p in range(n):
+            t_start = (thetas[2, p] if t0 else 0.0) if obs_i == 1 else y[obs_i - 2].time
+            g, o_len[p] = orc.mbp_iterate(desc, thetas[:, p], o_fc[p], o_t[p], o_y[p], o_len[p], o_ll[p], t_start, obs_i, key, p)
+            assert np.isclose(lg[p], g, rtol=1e-12, atol=0)
+    for p in (0, 7, n - 1):
+        fc, times, types, ll = pt.get_particle(p + 1)
+        assert np.array_equal(fc, o_fc[p]) and len(times) == o_len[p]
+        assert np.array_equal(types, o_y[p, : o_len[p]]) and np.allclose(times, o_t[p, : o_len[p]], rtol=1e-12, atol=0)
+        assert np.isclose(ll[0], o_ll[p, 0], rtol=1e-12)
+    # model-based proposals conditional on those trajectories
+    theta_f = thetas * rng.uniform(0.85, 1.2, size=thetas.shape)
+    valid = np.ones(n, dtype=bool); valid[3] = False
+    key = 777
+    pt.set_stream_key(key)
+    ll_f = pt.propose(thetas, theta_f, valid, n_obs)
+    assert np.all(np.isneginf(ll_f[3]))
+    for p in (0, 1, 7, 20, n - 1):
+        times, types, fc, ll, rc = orc.mbp_propose(desc, thetas[:, p], theta_f[:, p], o_t[p], o_y[p], o_len[p], cap, n_obs, key, p)
+        g_fc, g_times, g_types, g_ll = pt.get_particle(p + 1, proposal=True)
+        assert rc == 0 and np.array_equal(g_fc, fc) and np.array_equal(g_types, types)
+        assert np.allclose(g_times, times, rtol=1e-12, atol=0) and np.allclose(g_ll, ll, rtol=1e-12) and np.allclose(ll_f[p], ll, rtol=1e-12)
+    # accept / permute move whole particles
+    pt.accept([2, 8])
+    a = pt.get_particle(2); b = pt.get_particle(2, proposal=True)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    before = [pt.get_particle(p + 1) for p in range(n)]
+    nidx = np.sort(rng.integers(1, n + 1, n))
+    pt.permute(nidx)
+    for p in (0, 5, n - 1):
+        got = pt.get_particle(p + 1)
+        assert all(np.array_equal(u, v) for u, v in zip(got, before[nidx[p] - 1]))
+
+
+def test_trajectory_overflow_gives_minus_inf(dp):
+    model, y, hmm, theta = _setup(dp)
+    pt = dp.MbpParticles(dp.device_model(hmm), 32, 16, seed=1)  # 16 events is far too few for 20 time units
+    lg = pt.iterate(np.tile(theta[:, None], (1, 32)), 1, fresh=True)
+    dead = np.isneginf(lg)
+    assert dead.mean() > 0.4  # the rest are early extinctions (the single infective recovers) with <= 16 events
+    for p in range(32):
+        fc, times, types, ll = pt.get_particle(p + 1)
+        assert len(times) <= 16 and np.isneginf(ll[0]) == dead[p]
+        if not dead[p]:
+            assert fc[1] == 0  # extinct
+
+
+def test_run_mbp_ibis_against_oracle_and_anchor(dp, orc):
+    """run_ibis_analysis(model, y; algorithm = "MBPI") defaults (10000 particles, 3 mutations, ess 0.5) on SIS/pooley."""
+    model, y, hmm, theta = _setup(dp)
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    cm = dp.compile_model(model, y)
+    reps = 4
+    ours, ref, mus, rmus = [], [], [], []
+    for s in range(reps):
+        r = dp.run_ibis_analysis(model, y, algorithm="MBPI", seed=300 + s, verbose=False)
+        ours.append(r.bme.copy()); mus.append(r.mu.copy())
+        th0 = model.prior.rand(10000, np.random.default_rng(400 + s))
+        o = orc.run_mbp_ibis(cm.desc, th0, model.prior.lower, model.prior.upper, seed=500 + s, threads=orc.max_threads(), cap=8192)
+        ref.append(o["bme"].copy()); rmus.append(o["mu"].copy())
+    ours, ref, mus, rmus = map(np.array, (ours, ref, mus, rmus))
+    z = (ours[:, 0].mean() - ref[:, 0].mean()) / np.sqrt(ours[:, 0].var(ddof=1) / reps + ref[:, 0].var(ddof=1) / reps)
+    assert abs(z) < 4.5, (ours, ref)
+    assert 19.8 < ours[:, 0].mean() < 20.6  # prior-IS anchor 20.18 +- 0.1, SMC^2 reference run 19.98
+    assert np.all(np.abs(mus.mean(axis=0) - rmus.mean(axis=0)) < 0.12 * np.abs(rmus.mean(axis=0)))
+    # posterior mean: theta ~ (0.00327, 0.109)
+    assert abs(mus[:, 0].mean() - 0.00327) < 0.0005 and abs(mus[:, 1].mean() - 0.109) < 0.02
+
+
+def test_mbp_ibis_seir_stratified(dp):
+    """Shape of BASELINE config C5 at reduced size: SEIR, stratified outer resampling, n_props = 3, ind_prop = false."""
+    model, y, hmm, theta = load_case(dp, "seir_c3")
+    model.prior = dp.UniformProduct([0, 0, 0], [0.02, 1.0, 0.5])
+    hmm = dp.get_private_model(model, y[:30])
+    th0 = model.prior.rand(2048, np.random.default_rng(1))
+    r = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=3, outer_rs=dp.rs_stratified, verbose=False)
+    assert np.all(np.isfinite(r.bme)) and r.k_log[1] > 0
+    assert np.all(r.mu > 0) and np.all(r.mu < [0.02, 1.0, 0.5])
