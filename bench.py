@@ -99,6 +99,53 @@ def cpu_baseline(dp, model, y, theta, n_particles: int, threads: int):
     return n_particles * len(y) / dt, dt, ll, ev
 
 
+SMC2_OUTER, SMC2_NPF = 8192, 4096
+
+
+def run_smc2(dp, world, rank, barrier):
+    """BASELINE config C4: LOTKA [70,70], SMC^2 with 8192 theta-particles x 4096 state particles, T = 30 observations
+    (tests/golden/lotka_c4.csv), prior U(0,(1,0.01,1)), ess_rs_crit 0.3, independent proposals.  theta-particles are
+    sharded over the ranks (NCCL all-gather of weights, all-to-all of migrating filters).  One full run_ibis_analysis."""
+    import torch
+
+    model = dp.generate_model("LOTKA", [70, 70])
+    model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "lotka_c4.csv"))
+    comm = dp.Comm() if world > 1 else None
+    dp.run_ibis_analysis(model, y[:3], np=256 * world, npf=SMC2_NPF, seed=3, comm=comm, verbose=False)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    res = dp.run_ibis_analysis(model, y, np=SMC2_OUTER, npf=SMC2_NPF, seed=1, comm=comm, verbose=False)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    n_rs = int(res.k_log[0] // SMC2_OUTER)
+    out = {"metric": "SMC^2 theta-particle-observation updates/s", "value": SMC2_OUTER * len(y) / dt, "unit": "theta-particle-obs/s",
+           "wall_s": dt, "n_gpus": world, "scaling": "strong",
+           "config": {"workload": f"C4: LOTKA [70,70], {SMC2_OUTER} theta x {SMC2_NPF} state particles, T={len(y)}, prior U(0,(1,0.01,1)), "
+                                  "ess_rs_crit 0.3, ind_prop, n_props 1", "resample_mutate_steps": n_rs},
+           "minus_log_evidence": [float(v) for v in res.bme], "posterior_mean": [float(v) for v in res.mu],
+           "acceptance_rate": float(res.k_log[1] / max(res.k_log[0], 1))}
+    if world == 1 and rank == 0:
+        from oracle import oracle as orc
+
+        cm = dp.compile_model(model, y)
+        n_o, n_p = 128, 512
+        th0 = model.prior.rand(n_o, np.random.default_rng(5))
+        t0 = time.perf_counter()
+        o = orc.run_pibis(cm.desc, th0, model.prior.lower, model.prior.upper, npf=n_p, seed=7, threads=orc.max_threads())
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_o * len(y) / dtc, "unit": "theta-particle-obs/s", "cores": orc.max_threads(), "kind": "port",
+                               "sample": f"{n_o} theta x {n_p} state particles (1/64 of the theta-particles, 1/8 of the state particles), {dtc:.1f} s",
+                               "inner_pf_steps_per_s": o["pf_steps"] / dtc}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same config and metric."""
     rank = int(os.environ.get("RANK", "0"))
@@ -128,16 +175,28 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_json(line)
+
+
+def _json_only_stdout():
+    """Everything except the final JSON line goes to stderr (NCCL and the analysis drivers print to fd 1)."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
+    global print_json
+    out = _json_only_stdout()
+    print_json = lambda obj: (out.write(json.dumps(obj) + "\n"), out.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-smc2", action="store_true", help="skip the SMC^2 (config C4) secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -228,6 +287,11 @@ def main():
         k_n += (n0, n1)
     pf.set_kernel_timing(False)
 
+    # ---- secondary metric of BASELINE.json: SMC^2 theta-particles/s on config C4, sharded over the ranks ------------
+    smc2 = None
+    if not args.no_smc2:
+        smc2 = run_smc2(dp, world, rank, barrier)
+
     # max over ranks
     t = torch.tensor([wall, dev_ms, wall_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -279,6 +343,8 @@ def main():
             "roofline_pipeline": {"alg_bytes_per_step": 16 * C + 48, "achieved_gbs": (16 * C + 48) * value / world / 1e9,
                                   "frac_of_hbm_peak": (16 * C + 48) * value / world / 1e9 / hbm_peak},
         }
+        if smc2 is not None:
+            line["smc2"] = smc2
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
 
@@ -289,7 +355,7 @@ def main():
                                     "sample": f"the full workload once (2^20 particles x {T} obs, {dt_all:.1f} s), OpenMP over particles",
                                     "single_thread_value": v_one, "single_thread_sample": f"2^16 particles x {T} obs ({dt_one:.1f} s)",
                                     "loglik": ll_cpu}
-        print(json.dumps(line))
+        print_json(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -250,7 +250,7 @@ def run_ibis_analysis(model: DPOMPModel, obs_data, algorithm: str = C_ALG_NM_SMC
     rng = _np.random.default_rng(seed)
     theta_init = mdl.prior.rand(n_outer, rng)
     if smc2:
-        if comm is None or comm.rank == 0:
+        if kw.get("verbose", True) and (comm is None or comm.rank == 0):
             print(f"Running: {n_outer}-particle SMC^2 analysis (model: {model.model_name})")
         return run_pibis(mdl, theta_init, ess_rs_crit, ind_prop, alpha, npf, rng=rng, seed=seed, comm=comm, **kw)
     from .mbp_ibis import run_mbp_ibis
