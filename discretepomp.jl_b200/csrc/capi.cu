@@ -46,6 +46,7 @@ struct dpomp_pf {
     int32_t* pop[2] = {nullptr, nullptr};
     int cur = 0;
     double* logw = nullptr;
+    double* wtile = nullptr;
     double* cw = nullptr;
     int32_t* anc = nullptr;
     bool record_anc = false, initialised = false, last_resampled = false;
@@ -141,7 +142,7 @@ int dpomp_model_destroy(dpomp_model* model) {
 static void pf_free(dpomp_pf* pf) {
     if (!pf) return;
     cudaSetDevice(pf->device);
-    cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->cw); cudaFree(pf->anc);
+    cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->wtile); cudaFree(pf->cw); cudaFree(pf->anc);
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev);
@@ -198,6 +199,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->pop[0], B * pf->n_comp * NP * sizeof(int32_t));
     ALLOC(pf->pop[1], B * pf->n_comp * NP * sizeof(int32_t));
     ALLOC(pf->logw, B * NP * sizeof(double));
+    ALLOC(pf->wtile, B * NP * sizeof(double));
     if (rs_type == DPOMP_RS_MULTINOMIAL) ALLOC(pf->cw, B * NP * sizeof(double));
     ALLOC(pf->theta_dev, B * pf->n_params * sizeof(double));
     ALLOC(pf->tile_m, B * NT * sizeof(double));
@@ -345,6 +347,8 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         SimLaunch a{};
         a.pop = pf->pop[pf->cur];
         a.logw = pf->logw;
+        a.wtile = pf->wtile;
+        a.record_logw = pf->record_anc ? 1 : 0;
         a.theta = pf->theta_dev;
         a.obs_time = pf->obs_time_dev;
         a.obs_ysum = pf->obs_ysum_dev;
@@ -363,7 +367,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         if (do_rs) {
             ResampleLaunch r{};
             r.pop_src = pf->pop[pf->cur]; r.pop_dst = pf->pop[pf->cur ^ 1];
-            r.logw = pf->logw; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;
+            r.wtile = pf->wtile; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;
             r.anc = pf->record_anc ? pf->anc : nullptr;
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;
@@ -487,6 +491,7 @@ int dpomp_pf_set_pop(dpomp_pf* pf, int32_t b, const int64_t* in) {
 int dpomp_pf_get_last_logw(dpomp_pf* pf, int32_t b, double* out) {
     if (!pf || !out) return fail(DPOMP_ERR_ARG, "null argument");
     if (b < 1 || b > pf->n_batch) return fail(DPOMP_ERR_ARG, "filter index out of range");
+    if (!pf->record_anc) return fail(DPOMP_ERR_STATE, "diagnostics recording is off (dpomp_pf_set_record_ancestors)");
     CK(cudaSetDevice(pf->device));
     CK(cudaMemcpyAsync(out, pf->logw + (size_t)(b - 1) * pf->n_pad, (size_t)pf->n * sizeof(double), cudaMemcpyDeviceToHost, pf->stream));
     CK(cudaStreamSynchronize(pf->stream));

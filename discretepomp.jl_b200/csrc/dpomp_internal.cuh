@@ -33,7 +33,9 @@ struct DevModel {
 // Everything one launch of the simulate+weight kernel needs besides the model.
 struct SimLaunch {
     int32_t* pop;            // [B][C][n_pad] current populations (read unless fresh, written)
-    double* logw;            // [B][n_pad]
+    double* logw;            // [B][n_pad] log weights (diagnostics; written only when record_logw)
+    double* wtile;           // [B][n_pad] exp(logw - tile max): what the resample kernel scans
+    int record_logw;
     const double* theta;     // [B][n_params] device
     const double* obs_time;  // [T]
     const double* obs_ysum;  // [T]  sum_v ymask[v] * y.val[v]
@@ -64,7 +66,7 @@ struct SimLaunch {
 struct ResampleLaunch {
     const int32_t* pop_src;  // [B][C][n_pad]
     int32_t* pop_dst;
-    const double* logw;
+    const double* wtile;     // [B][n_pad] tile-scaled weights written by the simulate kernel
     const double* tile_m;
     const double* tile_f;
     const double* tile_off;
@@ -89,6 +91,7 @@ struct ModelHost {
 
 // launchers implemented in the kernel TUs; all asynchronous on `stream`; return cudaGetLastError()
 cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, const SimLaunch& a, cudaStream_t stream);
+int builtin_model_id(const dpomp_model_desc& d);  // 0 = generic rate table, > 0 = hand-specialised predefined model
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream);
 cudaError_t launch_gather_filters(int32_t* dst, const int32_t* src, const int64_t* dst_slots_dev,
                                   const int64_t* src_slots_dev, int n, long long filter_stride_words, cudaStream_t stream);

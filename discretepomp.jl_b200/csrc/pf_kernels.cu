@@ -17,6 +17,33 @@ cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, 
     return sim_precision == DPOMP_SIM_F64 ? launch_sim_f64(m, items, a, stream) : launch_sim_f32(m, items, a, stream);
 }
 
+// does the rate table equal one of the hand-specialised predefined models (pf_sim.cuh Builtin<>)?
+namespace {
+struct BuiltinSpec { int id, C, E; int A[3], B[3]; int T[3][4]; };
+const BuiltinSpec kSpecs[] = {
+    {1, 2, 1, {0}, {1}, {{-1, 1}}},
+    {2, 3, 2, {0, 1}, {1, -1}, {{-1, 1, 0}, {0, -1, 1}}},
+    {3, 2, 2, {0, 1}, {1, -1}, {{-1, 1}, {1, -1}}},
+    {4, 3, 2, {0, 1}, {2, -1}, {{-1, 1, 0}, {0, -1, 1}}},
+    {5, 4, 3, {0, 1, 2}, {2, -1, -1}, {{-1, 1, 0, 0}, {0, -1, 1, 0}, {0, 0, -1, 1}}},
+    {6, 3, 3, {0, 1, 2}, {2, -1, -1}, {{-1, 1, 0}, {0, -1, 1}, {1, 0, -1}}},
+    {7, 2, 3, {1, 0, 0}, {-1, 1, -1}, {{0, 1}, {1, -1}, {-1, 0}}},
+};
+}  // namespace
+int builtin_model_id(const dpomp_model_desc& d) {
+    for (const BuiltinSpec& s : kSpecs) {
+        if (d.n_compartments != s.C || d.n_events != s.E) continue;
+        bool ok = true;
+        for (int e = 0; e < s.E && ok; ++e) {
+            ok = d.rate_par[e] == e && d.rate_has_den[e] == 0 && d.rate_k1[e] == 0 && d.rate_k2[e] == (s.B[e] >= 0 ? 0 : 1);
+            for (int c = 0; c < s.C && ok; ++c)
+                ok = d.rate_f1[e][c] == (c == s.A[e] ? 1 : 0) && d.rate_f2[e][c] == (c == s.B[e] ? 1 : 0) && d.trans[e][c] == s.T[e][c];
+        }
+        if (ok) return s.id;
+    }
+    return 0;
+}
+
 int sim_kernel_supported(int n_comp, int n_events) {
     return n_comp >= 1 && n_comp <= 8 && n_events >= 1 && n_events <= 8;
 }
@@ -75,24 +102,20 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
     const double off_b = a.tile_off[(size_t)b * (a.ntiles + 1) + tile];
     const double off_n = a.tile_off[(size_t)b * (a.ntiles + 1) + tile + 1];
     const double f_b = a.tile_f[(size_t)b * a.ntiles + tile];
-    const double m_b = a.tile_m[(size_t)b * a.ntiles + tile];
-    const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
 
     double av[ITEMS], incl[ITEMS], excl[ITEMS];
-    const double* lw = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+    const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;  // exp(logw - m_b) from kernel 1
     if constexpr (ITEMS % 2 == 0) {  // 128-bit loads
 #pragma unroll
         for (int k = 0; k < ITEMS; k += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(lw + k);
+            const double2 v = *reinterpret_cast<const double2*>(wt + k);
             av[k] = v.x;
             av[k + 1] = v.y;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) av[k] = lw[k];
+        for (int k = 0; k < ITEMS; ++k) av[k] = wt[k];
     }
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) av[k] = (av[k] == -INFINITY) ? 0.0 : exp(av[k] - ref);
     tile_scan<ITEMS>(av, incl, excl, warp_scratch);
 
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel
@@ -107,9 +130,9 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
 
     if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, off_b);
     if (tid == 32) lohi_s[1] = (tile == a.ntiles - 1) ? a.n : resample_ecount(ctx, off_n);
-    long long er[ITEMS];
+    int er[ITEMS];  // n_particles < 2^31
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) er[k] = resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
+    for (int k = 0; k < ITEMS; ++k) er[k] = (int)resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
     __syncthreads();
 
     const long long lo = lohi_s[0], hi = lohi_s[1];
@@ -120,7 +143,7 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int qk = tid * ITEMS + k;
-        long long ev = er[k] < lo ? lo : (er[k] > hi ? hi : er[k]);
+        long long ev = er[k] < lo ? lo : (er[k] > hi ? hi : (long long)er[k]);
         if (qk >= nvalid - 1) ev = hi;
         emax[k] = (int)(ev - lo);
     }

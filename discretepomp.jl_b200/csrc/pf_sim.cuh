@@ -13,6 +13,8 @@
 // per attempt yields the waiting-time and event-type uniforms.  The observation log-weight (one f64 divide per
 // particle) is computed afterwards in a convergent pass together with the coalesced write-back.
 #pragma once
+#include <type_traits>
+
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
 
@@ -30,6 +32,29 @@ template <> struct Arith<double> {  // round-to-nearest, never contracted: the r
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 
+// ---- predefined models with compile-time rate structure (src/hmm_examples.jl:103-208, density dependent) ----------
+// rate[e] = theta[e] * x[A[e]] * (B[e] >= 0 ? x[B[e]] : 1), evaluated as (theta * x_a) * x_b like the reference; the
+// compiler folds the zero coefficients away (12 FFMA + 4 FMUL of the generic table become 3 FMUL + 1 FADD for SIR).
+enum : int { kModelGeneric = 0, kModelSI, kModelSIR, kModelSIS, kModelSEI, kModelSEIR, kModelSEIS, kModelLOTKA, kNumModels };
+template <int MODEL> struct Builtin;
+#define DPOMP_BUILTIN(ID, CC, EE, AL, BL, TL)                                                                        \
+    template <> struct Builtin<ID> {                                                                                 \
+        static constexpr int C = CC, E = EE;                                                                         \
+        __host__ __device__ static constexpr int A(int e) { constexpr int v[EE] = AL; return v[e]; }                 \
+        __host__ __device__ static constexpr int B(int e) { constexpr int v[EE] = BL; return v[e]; }                 \
+        __host__ __device__ static constexpr int T(int e, int c) { constexpr int v[EE][CC] = TL; return v[e][c]; }   \
+    };
+#define DPOMP_L(...) {__VA_ARGS__}
+DPOMP_BUILTIN(kModelSI, 2, 1, DPOMP_L(0), DPOMP_L(1), DPOMP_L({-1, 1}))
+DPOMP_BUILTIN(kModelSIR, 3, 2, DPOMP_L(0, 1), DPOMP_L(1, -1), DPOMP_L({-1, 1, 0}, {0, -1, 1}))
+DPOMP_BUILTIN(kModelSIS, 2, 2, DPOMP_L(0, 1), DPOMP_L(1, -1), DPOMP_L({-1, 1}, {1, -1}))
+DPOMP_BUILTIN(kModelSEI, 3, 2, DPOMP_L(0, 1), DPOMP_L(2, -1), DPOMP_L({-1, 1, 0}, {0, -1, 1}))
+DPOMP_BUILTIN(kModelSEIR, 4, 3, DPOMP_L(0, 1, 2), DPOMP_L(2, -1, -1), DPOMP_L({-1, 1, 0, 0}, {0, -1, 1, 0}, {0, 0, -1, 1}))
+DPOMP_BUILTIN(kModelSEIS, 3, 3, DPOMP_L(0, 1, 2), DPOMP_L(2, -1, -1), DPOMP_L({-1, 1, 0}, {0, -1, 1}, {1, 0, -1}))
+DPOMP_BUILTIN(kModelLOTKA, 2, 3, DPOMP_L(1, 0, 0), DPOMP_L(-1, 1, -1), DPOMP_L({0, 1}, {1, -1}, {-1, 0}))
+#undef DPOMP_L
+#undef DPOMP_BUILTIN
+
 // resident CTAs per SM the register allocation is tuned for (the f64 parity loop is not tuned)
 template <typename Real, int C, int E>
 // measured on B200 (SIR C2): 4 resident CTAs with 64 registers and no spills beat 5 / 6 CTAs with 48 / 40 registers
@@ -41,7 +66,7 @@ constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; 
 template <int N>
 struct alignas(4 * N) IntVec { int v[N]; };
 
-template <typename Real, int C, int E, int ITEMS>
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
 __global__ void __launch_bounds__(kBlockThreads, sim_min_blocks<Real, C, E>())
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -49,8 +74,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     constexpr bool kF32 = sizeof(Real) == 4;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // staged compartment counts: f32 loop keeps them as floats (no conversions in the divergent refill path; exact
+    // below 2^24), the f64 parity loop as int32
+    using SState = typename std::conditional<kF32, float, int>::type;
     int* ovf_s = reinterpret_cast<int*>(smem_raw);        // [TILE] 1 = the particle hit the event cap
-    int* st_s = ovf_s + TILE;                             // [C][TILE] staged compartment counts
+    SState* st_s = reinterpret_cast<SState*>(ovf_s + TILE);  // [C][TILE]
     __shared__ double warp_scratch[kBlockThreads / 32];
     __shared__ int is_last_s;
     __shared__ uint32_t stream_s[3];
@@ -87,8 +115,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
         for (int c = 0; c < C; ++c)
             if (c < a.n_comp)
-                *reinterpret_cast<Vec*>(st_s + c * TILE + tid * ITEMS) =
-                    *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
+            {
+                const Vec v = *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) st_s[c * TILE + tid * ITEMS + kk] = (SState)v.v[kk];
+            }
     }
     __syncthreads();
     const SimStream ss{stream_s[0], stream_s[1], stream_s[2]};
@@ -115,6 +146,15 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         if (active) {
             // rate_function + cumsum! (src/hmm_particle_filter.jl:20-21)
             Real cum[E];
+            if constexpr (MODEL != kModelGeneric) {
+                using BM = Builtin<MODEL>;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    Real rate = Arith<Real>::mul(par[e], x[BM::A(e)]);
+                    if (BM::B(e) >= 0) rate = Arith<Real>::mul(rate, x[BM::B(e) >= 0 ? BM::B(e) : 0]);
+                    cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+                }
+            } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 Real l1 = m.k1[e], l2 = m.k2[e];
@@ -131,6 +171,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
                 }
                 cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+            }
             }
             const Real rtot = cum[E - 1];
             fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
@@ -154,13 +195,25 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     if (!fin) {
                         // choose_event (src/hmm_cmn.jl:4-10) + `ptemp .+= fn_transition(et)` (:26)
                         Real dx[C];
+                        if constexpr (MODEL != kModelGeneric) {
+                            using BM = Builtin<MODEL>;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
+                            for (int c = 0; c < C; ++c) dx[c] = (Real)BM::T(E - 1, c);
 #pragma unroll
-                        for (int i = E - 2; i >= 0; --i) {
-                            const bool hit = cum[i] > etc;
+                            for (int i = E - 2; i >= 0; --i) {
+                                const bool hit = cum[i] > etc;
 #pragma unroll
-                            for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
+                                for (int c = 0; c < C; ++c) dx[c] = hit ? (Real)BM::T(i, c) : dx[c];
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
+#pragma unroll
+                            for (int i = E - 2; i >= 0; --i) {
+                                const bool hit = cum[i] > etc;
+#pragma unroll
+                                for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
+                            }
                         }
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[c] += dx[c];
@@ -174,7 +227,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             if (fin) {
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    if (c < a.n_comp) st_s[c * TILE + q] = (int)x[c];
+                    if (c < a.n_comp) st_s[c * TILE + q] = (SState)x[c];
                 if (ovf) ovf_s[q] = 1;
                 ev_local += k;
                 ovf_local += ovf ? 1u : 0u;
@@ -204,7 +257,9 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
         for (int c = 0; c < C; ++c)
             if (c < a.n_comp) {
-                const Vec v = *reinterpret_cast<const Vec*>(st_s + c * TILE + tid * ITEMS);
+                Vec v;
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) v.v[kk] = (int)st_s[c * TILE + tid * ITEMS + kk];
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) xs[kk] += m.xmask_i[c] * v.v[kk];
                 *reinterpret_cast<Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS) = v;  // padding slots included
@@ -218,11 +273,8 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             const bool valid = base_n + tid * ITEMS + kk < a.n;
             it[kk] = (valid && of.v[kk] == 0) ? m.obs_tmp1 - quot : -INFINITY;
         }
-        double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
-        if constexpr (ITEMS % 2 == 0) {
-#pragma unroll
-            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(lw_b + kk) = make_double2(it[kk], it[kk + 1]);
-        } else {
+        if (a.record_logw) {
+            double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
 #pragma unroll
             for (int kk = 0; kk < ITEMS; ++kk) lw_b[kk] = it[kk];
         }
@@ -247,6 +299,16 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
 #pragma unroll
     for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
+    {   // the tile-scaled weights are what the resample kernel scans: store them instead of recomputing the exps there
+        double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+        if constexpr (ITEMS % 2 == 0) {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(wt_b + kk) = make_double2(av[kk], av[kk + 1]);
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) wt_b[kk] = av[kk];
+        }
+    }
     const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
 
     if (tid == 0) {
@@ -338,12 +400,12 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
     return m;
 }
 
-template <typename Real, int C, int E, int ITEMS>
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
 static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream) {
     constexpr int TILE = kBlockThreads * ITEMS;
     const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
     const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
-    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS>;
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -354,12 +416,21 @@ static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cuda
     return cudaGetLastError();
 }
 
-// the instantiated (C, E) shapes; a model runs on the smallest shape that covers it
+// the instantiated generic (C, E) shapes; a model runs on the smallest shape that covers it
 #define DPOMP_SIM_SHAPES(X) X(2, 1) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(4, 3) X(4, 6) X(8, 8)
+#define DPOMP_SIM_BUILTINS(X) X(kModelSI) X(kModelSIR) X(kModelSIS) X(kModelSEI) X(kModelSEIR) X(kModelSEIS) X(kModelLOTKA)
 
 template <typename Real>
 static cudaError_t launch_sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStream_t stream) {
     const int c = mh.desc.n_compartments, e = mh.desc.n_events;
+    const int model_id = builtin_model_id(mh.desc);
+#define X(ID)                                                                                                    \
+    if (model_id == ID) {                                                                                        \
+        return items == 1 ? launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, 1, ID>(mh, a, stream)          \
+                          : launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, 4, ID>(mh, a, stream);         \
+    }
+    DPOMP_SIM_BUILTINS(X)
+#undef X
 #define X(CC, EE)                                                                             \
     if (c <= CC && e <= EE) {                                                                 \
         return items == 1 ? launch_sim_inst<Real, CC, EE, 1>(mh, a, stream)                   \

@@ -152,7 +152,7 @@ int dpomp_pf_set_pop(dpomp_pf* pf, int32_t b /*1-based*/, const int64_t* in);
  * observation processed, for filter b; out_anc may be NULL.  Ancestors are valid only if that observation resampled. */
 int dpomp_pf_get_last_logw(dpomp_pf* pf, int32_t b, double* out_logw);
 int dpomp_pf_get_last_ancestors(dpomp_pf* pf, int32_t b, int64_t* out_anc);
-int dpomp_pf_set_record_ancestors(dpomp_pf* pf, int32_t on);
+int dpomp_pf_set_record_ancestors(dpomp_pf* pf, int32_t on);  /* switches the diagnostics (log weights AND ancestors) on/off */
 /* number of (filter, particle, interval) simulations that hit the event cap since creation (sticky) */
 int dpomp_pf_overflow_count(dpomp_pf* pf, int64_t* out_count);
 /* total Gillespie events simulated by the last call (all filters) -- for events/s reporting */

@@ -15,8 +15,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _pf(dp, hmm, n, nb=1, rs=1, seed=1, f64=False, **kw):
-    return dp.ParticleFilter(dp.device_model(hmm), n, nb, rs, seed=seed,
-                             sim_precision=dp._capi.SIM_F64 if f64 else dp._capi.SIM_F32, **kw)
+    pf = dp.ParticleFilter(dp.device_model(hmm), n, nb, rs, seed=seed,
+                           sim_precision=dp._capi.SIM_F64 if f64 else dp._capi.SIM_F32, **kw)
+    pf.set_record_ancestors(True)  # diagnostics: log weights and ancestors of the last observation
+    return pf
 
 
 @pytest.mark.parametrize("case", ["sis_pooley", "sir_c2", "seir_c3", "lotka_c4"])
