@@ -12,6 +12,29 @@
 namespace dpomp {
 
 constexpr int kBlockThreads = 256;
+
+// Programmatic dependent launch: consecutive kernels of one filter pass are launched with the
+// programmatic-stream-serialization attribute, so the launch latency and block scheduling of kernel k+1 overlap the
+// tail of kernel k; every kernel calls pdl_wait() before it touches memory written by its predecessor.
+__device__ __forceinline__ void pdl_wait() {
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 constexpr uint32_t kTagSim = 0u;
 constexpr uint32_t kTagResample = 1u;
 

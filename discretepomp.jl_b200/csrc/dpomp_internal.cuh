@@ -34,7 +34,7 @@ struct DevModel {
 struct SimLaunch {
     int32_t* pop;            // [B][C][n_pad] current populations (read unless fresh, written)
     double* logw;            // [B][n_pad] log weights (diagnostics; written only when record_logw)
-    double* wtile;           // [B][n_pad] exp(logw - tile max): what the resample kernel scans
+    double* wtile;           // [B][n_pad] tile-local inclusive scan of exp(logw - tile max) (deterministic tree)
     int record_logw;
     const double* theta;     // [B][n_params] device
     const double* obs_time;  // [T]
@@ -66,7 +66,7 @@ struct SimLaunch {
 struct ResampleLaunch {
     const int32_t* pop_src;  // [B][C][n_pad]
     int32_t* pop_dst;
-    const double* wtile;     // [B][n_pad] tile-scaled weights written by the simulate kernel
+    const double* wtile;     // [B][n_pad] tile-local inclusive scans written by the simulate kernel
     const double* tile_m;
     const double* tile_f;
     const double* tile_off;

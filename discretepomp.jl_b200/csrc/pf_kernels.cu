@@ -49,74 +49,54 @@ int sim_kernel_supported(int n_comp, int n_events) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Kernel 2: one CTA per (filter, ancestor tile).  The tile's cumulative weights never leave the SM:
-//   w_q = exp(logw_q - m_b);  cw_q = off_b + f_b * incl_q   (deterministic scan tree)
-//   e_q = E(cw_q) = number of offspring whose uniform is <= cw_q  (counting form of `while u[i] > cw[j]`)
+// Kernel 2: one CTA per (filter, ancestor tile), one block barrier in total.
+//   cw_q = off_b + f_b * incl_q                 (incl_q: tile-local scan stored by kernel 1, deterministic tree)
+//   e_q  = E(cw_q) = #{ i : u_i <= cw_q }       (counting form of `while u[i] > cw[j]`, src/hmm_pf_resample.jl:34-40)
 //   offspring (lo_b, hi_b] belong to this tile; offspring i takes the first q with e_q >= i, i.e. ancestor q owns
-//   (max_{q'<q} e_q', max_{q'<=q} e_q'].  The offspring -> ancestor map of a window of TILE offspring is built in
-//   shared memory by a scatter of the range starts followed by an inclusive max-scan (no per-offspring search);
-//   state rows are then copied with coalesced writes over i and near-sorted reads over q.
+//   (max_{q'<q} e_q', max_{q'<=q} e_q'].
+// After the barrier that publishes (lo_b, hi_b) and the per-warp maxima, every warp works alone on the 32*ITEMS
+// ancestors it owns: the offspring -> ancestor map of a window of 32*ITEMS offspring is built in the warp's slice of
+// shared memory by a scatter of the range starts followed by an inclusive max-scan (no per-offspring search); state
+// rows are then copied with coalesced 128-byte writes over i and near-sorted reads over q.
 // ------------------------------------------------------------------------------------------------------------
-// inclusive max-scan over the block in blocked order (thread owns ITEMS consecutive values); returns in `v`, and the
-// inclusive value of the previous thread's last item in `prev` (identity for thread 0).  Two __syncthreads().
+#ifndef DPOMP_RS_MINB
+#define DPOMP_RS_MINB 4
+#endif
 template <int ITEMS>
-__device__ __forceinline__ void block_max_scan(int (&v)[ITEMS], int& prev, int identity, int* warp_tot) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 1; k < ITEMS; ++k) v[k] = max(v[k], v[k - 1]);
-    int inc = v[ITEMS - 1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc = max(inc, y);
-    }
-    int pl = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) pl = identity;
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    int wp = identity;
-#pragma unroll
-    for (int w = 0; w < kBlockThreads / 32; ++w)
-        if (w < warp) wp = max(wp, warp_tot[w]);
-    prev = max(wp, pl);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) v[k] = max(v[k], prev);
-    __syncthreads();
-}
-
-template <int ITEMS>
-__global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
+__global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
-    __shared__ int am_s[TILE];  // offspring window -> local ancestor index
-    __shared__ double warp_scratch[kBlockThreads / 32];
-    __shared__ int warp_iscratch[kBlockThreads / 32];
+    constexpr int CHUNK = 32 * ITEMS;
+    constexpr int NW = kBlockThreads / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ int am_s[NW][CHUNK];  // per warp: offspring window -> ancestor index within the warp's chunk
+    __shared__ int warp_max_s[NW];
     __shared__ long long lohi_s[2];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x % a.ntiles;
     const int b = blockIdx.x / a.ntiles;
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
 
+    pdl_wait();
     const double big_s = a.filt_s[b];
     const double off_b = a.tile_off[(size_t)b * (a.ntiles + 1) + tile];
     const double off_n = a.tile_off[(size_t)b * (a.ntiles + 1) + tile + 1];
     const double f_b = a.tile_f[(size_t)b * a.ntiles + tile];
 
-    double av[ITEMS], incl[ITEMS], excl[ITEMS];
-    const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;  // exp(logw - m_b) from kernel 1
+    double incl[ITEMS];
+    const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
     if constexpr (ITEMS % 2 == 0) {  // 128-bit loads
 #pragma unroll
         for (int k = 0; k < ITEMS; k += 2) {
             const double2 v = *reinterpret_cast<const double2*>(wt + k);
-            av[k] = v.x;
-            av[k + 1] = v.y;
+            incl[k] = v.x;
+            incl[k + 1] = v.y;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) av[k] = wt[k];
+        for (int k = 0; k < ITEMS; ++k) incl[k] = wt[k];
     }
-    tile_scan<ITEMS>(av, incl, excl, warp_scratch);
 
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel
         double* cw = a.cw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
@@ -130,75 +110,107 @@ __global__ void __launch_bounds__(kBlockThreads) pf_resample_kernel(const __grid
 
     if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, off_b);
     if (tid == 32) lohi_s[1] = (tile == a.ntiles - 1) ? a.n : resample_ecount(ctx, off_n);
-    int er[ITEMS];  // n_particles < 2^31
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) er[k] = (int)resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
-    __syncthreads();
-
-    const long long lo = lohi_s[0], hi = lohi_s[1];
     const long long rem = a.n - base_n;
     const int nvalid = rem < TILE ? (int)rem : TILE;
-    // owned offspring as offsets from lo: item q owns (prev_q, emax_q]; the last valid item closes the tile's range
-    int emax[ITEMS], prev;
+    // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
+    int er[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const int qk = tid * ITEMS + k;
-        long long ev = er[k] < lo ? lo : (er[k] > hi ? hi : (long long)er[k]);
-        if (qk >= nvalid - 1) ev = hi;
-        emax[k] = (int)(ev - lo);
+        er[k] = (int)resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
+        if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
     }
-    block_max_scan<ITEMS>(emax, prev, 0, warp_iscratch);
-
-    const int total = (int)(hi - lo);
-    const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad;
-    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad;
-    for (int wlo = 0; wlo < total; wlo += TILE) {
+    // running maximum in item order: lane-serial, then Kogge-Stone over the lanes; the warp maximum goes to shared memory
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am_s[tid * ITEMS + k] = -1;
-        __syncthreads();
+    for (int k = 1; k < ITEMS; ++k) er[k] = max(er[k], er[k - 1]);
+    int inc = er[ITEMS - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc = max(inc, y);
+    }
+    int prev_raw = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) prev_raw = -1;
+    if (lane == 31) warp_max_s[warp] = inc;
+    __syncthreads();  // the only block barrier
+
+    const long long lo = lohi_s[0], hi = lohi_s[1];
+    int wprev_raw = -1;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (w < warp) wprev_raw = max(wprev_raw, warp_max_s[w]);
+    prev_raw = max(prev_raw, wprev_raw);
+    // clamp is monotone, so clamp(running max) == running max of the clamped counts; offsets are relative to lo
+    auto clamp_off = [&](int v) -> int {
+        const long long c = v < lo ? lo : (v > hi ? hi : (long long)v);
+        return (int)(c - lo);
+    };
+    int emax[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) emax[k] = clamp_off(max(er[k], prev_raw));
+    const int prev = clamp_off(prev_raw);                       // owned range of item 0: (prev, emax[0]]
+    const int wfirst = clamp_off(wprev_raw);                    // the warp owns offspring offsets (wfirst, wlast]
+    const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
+
+    const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad + base_n + warp * CHUNK;
+    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
+    int* am_w = am_s[warp];
+    for (int wlo = wfirst; wlo < wlast; wlo += CHUNK) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = -1;
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
-            const int first = (k == 0) ? prev : emax[k - 1];  // offspring offsets (first, emax[k]] belong to item k
-            if (emax[k] > first && first < wlo + TILE && emax[k] > wlo) am_s[max(first - wlo, 0)] = tid * ITEMS + k;
+            const int first = (k == 0) ? prev : emax[k - 1];
+            if (emax[k] > first && first < wlo + CHUNK && emax[k] > wlo) am_w[max(first - wlo, 0)] = lane * ITEMS + k;
         }
-        __syncthreads();
-        int am[ITEMS], dummy;
+        __syncwarp();
+        int am[ITEMS];
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am[k] = am_s[tid * ITEMS + k];
-        block_max_scan<ITEMS>(am, dummy, -1, warp_iscratch);
+        for (int k = 0; k < ITEMS; ++k) am[k] = am_w[lane * ITEMS + k];
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am_s[tid * ITEMS + k] = am[k];
-        __syncthreads();
-        // gather: striped over the window; per compartment, the ITEMS loads of a thread are issued before its stores
+        for (int k = 1; k < ITEMS; ++k) am[k] = max(am[k], am[k - 1]);
+        int ainc = am[ITEMS - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, ainc, d);
+            if (lane >= d) ainc = max(ainc, y);
+        }
+        int aprev = __shfl_up_sync(FULL, ainc, 1);
+        if (lane == 0) aprev = -1;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
+        __syncwarp();
+        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
         int srcq[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const int pidx = j * kBlockThreads + tid;
-            srcq[j] = (wlo + pidx < total) ? am_s[pidx] : -1;
+            const int pidx = j * 32 + lane;
+            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
         }
-        const long long i_base = lo + wlo + tid;  // 0-based offspring index of j = 0
         for (int c = 0; c < a.n_comp; ++c) {
-            const int32_t* sc = src_b + (size_t)c * a.n_pad + base_n;
-            int32_t* dc = dst_b + (size_t)c * a.n_pad + i_base;
+            const int32_t* sc = src_b + (size_t)c * a.n_pad;
+            int32_t* dc = dst_b + (size_t)c * a.n_pad + wlo + lane;
             int vals[ITEMS];
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
                 if (srcq[j] >= 0) vals[j] = sc[srcq[j]];
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) dc[j * kBlockThreads] = vals[j];
+                if (srcq[j] >= 0) dc[j * 32] = vals[j];
         }
         if (a.anc) {
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) a.anc[(size_t)b * a.n_pad + i_base + j * kBlockThreads] = (int32_t)(base_n + srcq[j]);
+                if (srcq[j] >= 0)
+                    a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 // multinomial: offspring i draws chs = r_i * S; ancestor = first p2 < N with chs < cw[p2], else N (src/hmm_resample.jl:9-16)
 __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(const __grid_constant__ ResampleLaunch a, int tile_size) {
+    pdl_wait();
     const long long gi = (long long)blockIdx.x * kBlockThreads + threadIdx.x;
     const int b = (int)(gi / a.n_pad);
     const long long i = gi % a.n_pad;
@@ -235,9 +247,8 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
 
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
-    if (items == 1) pf_resample_kernel<1><<<grid, kBlockThreads, 0, stream>>>(a);
-    else pf_resample_kernel<4><<<grid, kBlockThreads, 0, stream>>>(a);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = items == 1 ? launch_pdl(pf_resample_kernel<1>, grid, kBlockThreads, 0, stream, a)
+                                 : launch_pdl(pf_resample_kernel<4>, grid, kBlockThreads, 0, stream, a);
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {
         const long long total = (long long)a.n_filters * a.n_pad;

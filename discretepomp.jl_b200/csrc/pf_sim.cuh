@@ -99,10 +99,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     int32_t* pop_b = a.pop + (size_t)b * a.n_comp * a.n_pad;
     const uint32_t max_ev = (uint32_t)a.max_events;
 
-    if (tid == 0) {
+    if (tid == 0) {  // independent of the predecessor kernel: overlaps its tail
         const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)a.t);
         stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;
     }
+    pdl_wait();  // everything below reads or writes buffers shared with the predecessor kernel
     // stage the tile: each thread moves ITEMS consecutive particles per compartment with one vector access
     using Vec = IntVec<ITEMS>;
     {
@@ -299,17 +300,17 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
 #pragma unroll
     for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
-    {   // the tile-scaled weights are what the resample kernel scans: store them instead of recomputing the exps there
+    const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
+    {   // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs: cw = off_b + f_b * incl
         double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
         if constexpr (ITEMS % 2 == 0) {
 #pragma unroll
-            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(wt_b + kk) = make_double2(av[kk], av[kk + 1]);
+            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(wt_b + kk) = make_double2(incl[kk], incl[kk + 1]);
         } else {
 #pragma unroll
-            for (int kk = 0; kk < ITEMS; ++kk) wt_b[kk] = av[kk];
+            for (int kk = 0; kk < ITEMS; ++kk) wt_b[kk] = incl[kk];
         }
     }
-    const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
 
     if (tid == 0) {
         a.tile_m[(size_t)b * a.ntiles + tile] = m_b;
@@ -412,8 +413,7 @@ static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cuda
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    kern<<<(unsigned)(a.n_filters * a.ntiles), kBlockThreads, smem, stream>>>(m, a);
-    return cudaGetLastError();
+    return launch_pdl(kern, (unsigned)(a.n_filters * a.ntiles), kBlockThreads, smem, stream, m, a);
 }
 
 // the instantiated generic (C, E) shapes; a model runs on the smallest shape that covers it
