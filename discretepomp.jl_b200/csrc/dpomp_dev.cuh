@@ -21,6 +21,11 @@ __device__ __forceinline__ void pdl_wait() {
     cudaGridDependencySynchronize();
 #endif
 }
+__device__ __forceinline__ void pdl_trigger() {
+#if __CUDA_ARCH__ >= 900 && defined(DPOMP_PDL_TRIGGER)
+    cudaTriggerProgrammaticLaunchCompletion();
+#endif
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg{};

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     if (lane == 0) prev_raw = -1;
     if (lane == 31) warp_max_s[warp] = inc;
     __syncthreads();  // the only block barrier
+    pdl_trigger();
 
     const long long lo = lohi_s[0], hi = lohi_s[1];
     int wprev_raw = -1;

@@ -248,6 +248,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
     __syncthreads();
 
+    pdl_trigger();
     // ---- convergent pass (blocked: thread owns ITEMS consecutive particles): observation log-weight
     // (src/hmm_examples.jl:63-65, exp deferred) and vectorised write-back of states and log weights
     double it[ITEMS], av[ITEMS], incl[ITEMS], excl[ITEMS];

@@ -221,3 +221,29 @@ def test_full_size_c2_properties(dp):
     # two independent 2^20-particle estimates agree to Monte-Carlo error (sd of one estimate ~ 0.01)
     ll_b = _pf(dp, hmm, n, seed=3).loglik(theta)[0]
     assert abs(ll - ll_b) < 0.1
+
+
+@pytest.mark.parametrize("name,ic,theta,fd", [("ROSSMAC", [50, 5, 60, 5], [0.02, 0.05, 0.05, 0.1, 0.5, 0.5], False),
+                                              ("SIR", [100, 2, 0], [0.3, 0.1], True), ("SEIS", [60, 0, 3], [0.01, 0.3, 0.2], False),
+                                              ("SI", [50, 1], [0.004], False), ("SEI", [80, 0, 2], [0.01, 0.4], True)])
+def test_generic_rate_table_models_bit_exact(dp, orc, name, ic, theta, fd):
+    """Models that run on the generic rate-table kernel (denominators, six events) or on other built-in structures."""
+    model = dp.generate_model(name, ic, freq_dep=fd)
+    c = len(ic)
+    val = [0] * c
+    val[(2 if name in ("SEI", "SEIS") else 1)] = 4
+    y = [dp.Observation(float(t), 1, 1.0, val) for t in (1.0, 2.5, 4.0)]
+    hmm = dp.get_private_model(model, y)
+    th = np.asarray(theta)
+    for n in (700, 2500):
+        pf = _pf(dp, hmm, n, f64=True)
+        tile, items = pf.geometry()
+        pf.set_stream_key(4242 + n)
+        ll = pf.loglik(th)[0]
+        o = orc.pf_partial(pf.dmodel.compiled.desc, th, n, None, 1, 3, 1, 4242 + n, 0, orc.MODE_DEVICE, tile, items)
+        assert pf.last_event_count() == o[3] and np.array_equal(pf.get_pop(1), o[5]) and abs(ll - o[0]) <= 1e-11 * max(1, abs(o[0]))
+    # f32 loop: same law (mean log-lik of 64 filters within 5 sd of the oracle's)
+    pf = _pf(dp, hmm, 1024, 64, seed=8)
+    g = pf.loglik(np.tile(th[:, None], (1, 64)))
+    r, _ = orc.pf_partial_batch(pf.dmodel.compiled.desc, np.tile(th[:, None], (1, 64)), 1024, 1, 3, 1, key=99, threads=orc.max_threads())
+    assert abs(g.mean() - r.mean()) < 5 * np.sqrt(g.var(ddof=1) / 64 + r.var(ddof=1) / 64) + 1e-9
