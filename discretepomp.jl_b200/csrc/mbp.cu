@@ -258,6 +258,31 @@ __global__ void __launch_bounds__(128) mbp_copy_kernel(MbpStore dst, MbpStore sr
     if (threadIdx.x == 64) { dst.ll[2 * d] = src.ll[2 * s]; dst.ll[2 * d + 1] = src.ll[2 * s + 1]; }
 }
 
+// migration: pack / unpack whole particles.  fixed record = 16 int32 words: [0] length, [1..8] final state, [10..13] log_like[2]
+constexpr int kMbpFixedWords = 16;
+__global__ void __launch_bounds__(128) mbp_pack_kernel(MbpStore st, const int64_t* slots, const int64_t* offsets, int* fixed,
+                                                        double* times, unsigned char* types, int cap, int n_comp, int unpack) {
+    const int k = blockIdx.x;
+    const long long p = slots[k] - 1;
+    int* fx = fixed + (size_t)k * kMbpFixedWords;
+    double* et = st.ev_time + (size_t)p * cap;
+    unsigned char* ey = st.ev_type + (size_t)p * cap;
+    const long long off = offsets[k];
+    if (!unpack) {
+        const int len = st.len[p];
+        for (int i = threadIdx.x; i < len; i += blockDim.x) { times[off + i] = et[i]; types[off + i] = ey[i]; }
+        if (threadIdx.x == 0) fx[0] = len;
+        if (threadIdx.x < n_comp) fx[1 + threadIdx.x] = st.fc[(size_t)p * n_comp + threadIdx.x];
+        if (threadIdx.x == 32) { double* l = reinterpret_cast<double*>(fx + 10); l[0] = st.ll[2 * p]; l[1] = st.ll[2 * p + 1]; }
+    } else {
+        const int len = fx[0];
+        for (int i = threadIdx.x; i < len; i += blockDim.x) { et[i] = times[off + i]; ey[i] = types[off + i]; }
+        if (threadIdx.x == 0) st.len[p] = len;
+        if (threadIdx.x < n_comp) st.fc[(size_t)p * n_comp + threadIdx.x] = fx[1 + threadIdx.x];
+        if (threadIdx.x == 32) { const double* l = reinterpret_cast<const double*>(fx + 10); st.ll[2 * p] = l[0]; st.ll[2 * p + 1] = l[1]; }
+    }
+}
+
 __global__ void mbp_reset_kernel(const __grid_constant__ MbpModel m, MbpStore st, int n) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -471,11 +496,50 @@ int dpomp_mbp_accept(dpomp_mbp* h, const int64_t* slots, int32_t n) {
 int dpomp_mbp_permute(dpomp_mbp* h, const int64_t* nidx, int32_t n) {
     if (!h || !nidx) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
     if (n != h->n) return dpomp_set_error(DPOMP_ERR_ARG, "permute needs one index per particle");
+    for (int i = 0; i < n; ++i)
+        if (nidx[i] < 1 || nidx[i] > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
     MCK(cudaSetDevice(h->device));
     int rc = mbp_copy(h, h->cur ^ 1, h->cur, nullptr, nidx, n);
     if (rc) return rc;
     h->cur ^= 1;
     return DPOMP_OK;
+}
+
+int dpomp_mbp_get_lengths(dpomp_mbp* h, const int64_t* slots, int32_t n, int32_t* out_len) {
+    if (!h || !slots || !out_len) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n < 0 || n > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "n out of range");
+    MCK(cudaSetDevice(h->device));
+    std::vector<int> all((size_t)h->n);
+    MCK(cudaMemcpy(all.data(), h->store[h->cur].len, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 1 || slots[i] > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
+        out_len[i] = all[(size_t)slots[i] - 1];
+    }
+    return DPOMP_OK;
+}
+
+static int mbp_pack(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets, int n, void* fixed, void* times, void* types, int unpack) {
+    if (!h || (n > 0 && (!slots || !offsets || !fixed))) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n == 0) return DPOMP_OK;
+    if (n < 0 || n > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "n out of range");
+    for (int i = 0; i < n; ++i)
+        if (slots[i] < 1 || slots[i] > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "particle index out of range");
+    MCK(cudaSetDevice(h->device));
+    MCK(cudaMemcpyAsync(h->slots, slots, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    MCK(cudaMemcpyAsync(h->slots + h->n, offsets, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    mbp_pack_kernel<<<n, 128, 0, h->stream>>>(h->store[h->cur], h->slots, h->slots + h->n, (int*)fixed, (double*)times,
+                                              (unsigned char*)types, h->cap, h->dm.n_comp, unpack);
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(h->stream));
+    return DPOMP_OK;
+}
+int dpomp_mbp_export(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets, int32_t n, void* dev_fixed, void* dev_times,
+                     void* dev_types) {
+    return mbp_pack(h, slots, offsets, n, dev_fixed, dev_times, dev_types, 0);
+}
+int dpomp_mbp_import(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
+                     const void* dev_times, const void* dev_types) {
+    return mbp_pack(h, slots, offsets, n, const_cast<void*>(dev_fixed), const_cast<void*>(dev_times), const_cast<void*>(dev_types), 1);
 }
 
 int dpomp_mbp_get_particle(dpomp_mbp* h, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times, int32_t* types,

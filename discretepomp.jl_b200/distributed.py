@@ -100,6 +100,37 @@ class Comm:
         else:
             self.dist.all_to_all_single(recv, send, rs, ss)
 
+    def all_to_all_v(self, send, send_counts: Sequence[int], recv_counts: Sequence[int]):
+        """Variable-size all-to-all of a 1-d torch tensor of any dtype; counts are element counts per rank."""
+        import torch
+
+        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+        if self.dist is None:
+            recv.copy_(send)
+            return recv
+        rs, ss = [int(c) for c in recv_counts], [int(c) for c in send_counts]
+        if self.dist.get_backend() == "gloo":
+            host_send = send.cpu()
+            host_recv = torch.empty(recv.numel(), dtype=send.dtype)
+            ro = np.concatenate(([0], np.cumsum(rs))); so = np.concatenate(([0], np.cumsum(ss)))
+            reqs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    host_recv[ro[r]:ro[r + 1]] = host_send[so[r]:so[r + 1]]
+                elif ss[r]:
+                    reqs.append(self.dist.isend(host_send[so[r]:so[r + 1]].contiguous(), r))
+            for r in range(self.world):
+                if r != self.rank and rs[r]:
+                    buf = torch.empty(rs[r], dtype=send.dtype)
+                    self.dist.recv(buf, r)
+                    host_recv[ro[r]:ro[r + 1]] = buf
+            for q in reqs:
+                q.wait()
+            recv.copy_(host_recv)
+        else:
+            self.dist.all_to_all_single(recv, send, rs, ss)
+        return recv
+
     def barrier(self):
         if self.dist is not None:
             self.dist.barrier()

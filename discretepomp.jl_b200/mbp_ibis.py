@@ -84,6 +84,38 @@ class MbpParticles:
         s = _capi.as_i64(nidx)
         _capi.check(_capi.lib().dpomp_mbp_permute(self._h, _capi.ptr(s), len(s)))
 
+    # -- migration between ranks (lengths first, then one packed payload) -------------------------------------
+    FIXED_WORDS = 16
+
+    def lengths(self, slots) -> np.ndarray:
+        s = _capi.as_i64(slots)
+        out = np.zeros(len(s), dtype=np.int32)
+        if len(s):
+            _capi.check(_capi.lib().dpomp_mbp_get_lengths(self._h, _capi.ptr(s), len(s), _capi.ptr(out)))
+        return out
+
+    def export_particles(self, slots, lens):
+        """Pack the listed particles (1-based) into CUDA tensors (fixed int32 records, f64 times, u8 types)."""
+        import torch
+
+        s = _capi.as_i64(slots)
+        off = np.concatenate(([0], np.cumsum(lens, dtype=np.int64)))
+        fixed = torch.zeros(len(s) * self.FIXED_WORDS, dtype=torch.int32, device="cuda")
+        times = torch.empty(int(off[-1]), dtype=torch.float64, device="cuda")
+        types = torch.empty(int(off[-1]), dtype=torch.uint8, device="cuda")
+        if len(s):
+            o = _capi.as_i64(off[:-1])
+            _capi.check(_capi.lib().dpomp_mbp_export(self._h, _capi.ptr(s), _capi.ptr(o), len(s), C.c_void_p(fixed.data_ptr()),
+                                                     C.c_void_p(times.data_ptr()), C.c_void_p(types.data_ptr())))
+        return fixed, times, types
+
+    def import_particles(self, slots, lens, fixed, times, types) -> None:
+        s = _capi.as_i64(slots)
+        if len(s):
+            o = _capi.as_i64(np.concatenate(([0], np.cumsum(lens, dtype=np.int64)))[:-1])
+            _capi.check(_capi.lib().dpomp_mbp_import(self._h, _capi.ptr(s), _capi.ptr(o), len(s), C.c_void_p(fixed.data_ptr()),
+                                                     C.c_void_p(times.data_ptr()), C.c_void_p(types.data_ptr())))
+
     def get_particle(self, p: int, proposal: bool = False):
         """(final_condition, times, types(1-based), log_like[2]) of particle p (1-based)."""
         fc = np.zeros(self.n_comp, dtype=np.int64); ln = C.c_int64()
@@ -98,18 +130,48 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                  comm: Optional[Comm] = None, max_traj: int = 8192, outer_rs: Callable = rs_systematic,
                  particles_factory: Optional[Callable] = None, verbose: bool = True) -> ImportanceSample:
     """run_mbp_ibis(model, theta, ess_rs_crit, n_props, ind_prop, alpha, msgs = true) (src/hmm_ibis.jl:140-244).
-    `theta` is (n_theta, outer_p).  Single process (MBP-IBIS trajectories do not migrate between ranks in this round)."""
-    if comm is not None and comm.world > 1:
-        raise NotImplementedError("run_mbp_ibis: multi-rank sharding of trajectories is not implemented in this round")
+    `theta` is (n_theta, outer_p).  With `comm`, theta-particles (and their trajectories) are partitioned over the ranks;
+    theta, weights and every host decision are replicated (same host RNG), trajectories migrate after the outer resample
+    with a two-phase all-to-all (lengths, then the packed events)."""
+    comm = comm or Comm(None)
     rng = rng or np.random.default_rng(seed)
     theta = np.array(theta, dtype=np.float64, order="C")
     d, outer_p = theta.shape
-    if verbose:
+    if verbose and comm.rank == 0:
         print(f"Running: {outer_p}-particle MBP-IBIS analysis (model: {model.model_name})")
+    lo, hi = comm.bounds(outer_p)
+    n_loc = hi - lo
     start_time = time.time_ns()
     ess_crit = ess_rs_crit * outer_p
     make = particles_factory or (lambda n, sd: MbpParticles(device_model(model), n, max_traj, sd))
-    ptcls = make(outer_p, seed)
+    ptcls = make(max(n_loc, 1), seed)
+    ptcls.set_batch_offset(lo)
+
+    def gather(local: np.ndarray) -> np.ndarray:
+        return comm.allgather_f64(local, outer_p)
+
+    def migrate(nidx: np.ndarray) -> None:
+        """ptcls2[p] = deepcopy(ptcls[nidx[p]]) (:196-199) across ranks."""
+        if comm.world == 1:
+            ptcls.permute(nidx)
+            return
+        import torch
+        from .distributed import migration_plan
+
+        local_src, send_slots, send_counts, recv_slots, recv_counts = migration_plan(nidx - 1, outer_p, comm.world, comm.rank)
+        send_lens = ptcls.lengths(send_slots + 1)
+        lens_t = torch.from_numpy(send_lens.astype(np.int32)).to("cuda")
+        recv_lens = comm.all_to_all_v(lens_t, send_counts, recv_counts).cpu().numpy()
+        fixed, times, types = ptcls.export_particles(send_slots + 1, send_lens)
+        ev_send = [int(send_lens[sum(send_counts[:r]):sum(send_counts[:r + 1])].sum()) for r in range(comm.world)]
+        ev_recv = [int(recv_lens[sum(recv_counts[:r]):sum(recv_counts[:r + 1])].sum()) for r in range(comm.world)]
+        fw = MbpParticles.FIXED_WORDS
+        r_fixed = comm.all_to_all_v(fixed, [c * fw for c in send_counts], [c * fw for c in recv_counts])
+        r_times = comm.all_to_all_v(times, ev_send, ev_recv)
+        r_types = comm.all_to_all_v(types, ev_send, ev_recv)
+        if n_loc:
+            ptcls.permute(local_src + 1)
+        ptcls.import_particles(recv_slots + 1, recv_lens, r_fixed, r_times, r_types)
     prior = np.array([model.prior.logpdf(theta[:, p]) for p in range(outer_p)])  # Particle.prior (:153)
     log_like = np.zeros(outer_p)  # Particle.log_like[1], mirrored on the host for the acceptance ratio
     propd = ProposalDensity.identity(d)
@@ -127,7 +189,7 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
     mu, cv = compute_is_mu_covar(theta, w)
     for obs_i in range(1, len(model.obs_data) + 1):
         ptcls.set_stream_key(next_key())
-        lg = ptcls.iterate(theta, obs_i, fresh=(obs_i == 1))  # :176-179
+        lg = gather(ptcls.iterate(theta[:, lo:hi], obs_i, fresh=(obs_i == 1)) if n_loc else np.zeros(0))  # :176-179
         if model.obs_data[obs_i - 1].obs_id > 0:
             log_like = log_like + lg  # -Inf propagates for overflowed trajectories (src/hmm_sim.jl:17-20)
             gx = np.exp(lg)
@@ -139,7 +201,7 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                 propd = get_prop_density(cv, propd)
                 nidx = outer_rs(w.copy(), rng)
                 mtd_gx = gx[nidx - 1].copy()
-                ptcls.permute(nidx)
+                migrate(nidx)
                 theta, prior, log_like = theta[:, nidx - 1], prior[nidx - 1], log_like[nidx - 1]
                 mlr = np.mean(gx[nidx - 1]) * np.exp(lml)
                 k_log[0] += outer_p * n_props
@@ -148,12 +210,13 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                     prior_f = np.array([model.prior.logpdf(theta_f[:, p]) for p in range(outer_p)])
                     valid = prior_f != -np.inf
                     ptcls.set_stream_key(next_key())
-                    ll_f = ptcls.propose(theta, theta_f, valid, obs_i)  # (outer_p, 2)
+                    ll_f = gather(ptcls.propose(theta[:, lo:hi], theta_f[:, lo:hi], valid[lo:hi], obs_i)
+                                  if n_loc else np.zeros((0, 2)))  # (outer_p, 2)
                     u = rng.random(outer_p)
                     with np.errstate(over="ignore", invalid="ignore"):
                         ratio = np.exp(prior_f - prior) * np.exp(ll_f[:, 0] - log_like)  # :212
                     accepted = ratio > u  # NaN compares false, as in the reference
-                    ptcls.accept(np.nonzero(accepted)[0] + 1)
+                    ptcls.accept(np.nonzero(accepted[lo:hi])[0] + 1)
                     mtd_gx[accepted] = np.exp(ll_f[accepted, 1])
                     theta[:, accepted] = theta_f[:, accepted]
                     prior[accepted] = prior_f[accepted]
@@ -167,7 +230,7 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                 bme[1] += np.log(np.sum(w * gx) / np.sum(w))
     mu, cv = compute_is_mu_covar(theta, w)
     output = ImportanceSample(mu, cv, theta, w, time.time_ns() - start_time, -bme)
-    if verbose:
+    if verbose and comm.rank == 0:
         ar = 100.0 * k_log[1] / k_log[0] if k_log[0] else float("nan")
         print(f"- finished in {output.run_time / 1e9:.1f} seconds (AR := {ar:.3g}%)")
     output.k_log = k_log

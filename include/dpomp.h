@@ -196,6 +196,15 @@ int dpomp_mbp_propose(dpomp_mbp* mbp, const double* theta_i, const double* theta
                       int32_t ymax, double* out_loglike);
 int dpomp_mbp_accept(dpomp_mbp* mbp, const int64_t* slots, int32_t n);    /* ptcls[p] = xf (src/hmm_ibis.jl:214), 1-based */
 int dpomp_mbp_permute(dpomp_mbp* mbp, const int64_t* nidx, int32_t n);    /* ptcls2[p] = deepcopy(ptcls[nidx[p]]) (:196-199) */
+/* migration of particles between ranks (lengths first, then one packed payload).  dpomp_mbp_get_lengths
+ * returns the event counts of the listed particles (1-based); offsets[k] = position of particle k's events in the packed
+ * DEVICE buffers dev_times (f64) / dev_types (u8); dev_fixed holds 16 int32 words per particle (length, final state,
+ * log_like[2]).  Import writes into the CURRENT store. */
+int dpomp_mbp_get_lengths(dpomp_mbp* mbp, const int64_t* slots, int32_t n, int32_t* out_len);
+int dpomp_mbp_export(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offsets, int32_t n, void* dev_fixed,
+                     void* dev_times, void* dev_types);
+int dpomp_mbp_import(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
+                     const void* dev_times, const void* dev_types);
 /* read back one particle (which: 0 current, 1 proposal): final state, event list (types 1-based), log_like[2] */
 int dpomp_mbp_get_particle(dpomp_mbp* mbp, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times,
                            int32_t* types, int64_t cap_out, double* loglike2);

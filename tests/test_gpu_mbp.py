@@ -115,3 +115,59 @@ def test_mbp_ibis_seir_stratified(dp):
     r = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=3, outer_rs=dp.rs_stratified, verbose=False)
     assert np.all(np.isfinite(r.bme)) and r.k_log[1] > 0
     assert np.all(r.mu > 0) and np.all(r.mu < [0.02, 1.0, 0.5])
+
+
+def test_export_import_roundtrip(dp):
+    model, y, hmm, theta = _setup(dp)
+    dm = dp.device_model(hmm)
+    a = dp.MbpParticles(dm, 40, 4096, seed=2)
+    b = dp.MbpParticles(dm, 40, 4096, seed=9)
+    th = np.tile(theta[:, None], (1, 40)) * np.linspace(0.8, 1.3, 40)[None, :]
+    a.iterate(th, 1, True); a.iterate(th, 2, False)
+    slots = np.array([3, 17, 40, 1])
+    lens = a.lengths(slots)
+    fixed, times, types = a.export_particles(slots, lens)
+    assert times.numel() == lens.sum() and fixed.numel() == 4 * 16
+    dst = np.array([5, 6, 7, 8])
+    b.import_particles(dst, lens, fixed, times, types)
+    for s, d in zip(slots, dst):
+        assert all(np.array_equal(u, v) for u, v in zip(a.get_particle(int(s)), b.get_particle(int(d))))
+
+
+def _mbp_worker(rank, world, port, out_path):
+    import os, sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import torch
+    import dpomp_b200 as dp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    comm = None
+    if world > 1:
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+        comm = dp.Comm()
+    torch.cuda.set_device(0)
+    model = dp.generate_model("SIS", [100, 1])
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "pooley.csv"))
+    hmm = dp.get_private_model(model, y)
+    th0 = model.prior.rand(501, np.random.default_rng(5))
+    res = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, rng=np.random.default_rng(6), seed=7, comm=comm, max_traj=4096, verbose=False)
+    if rank == 0:
+        np.savez(out_path, bme=res.bme, mu=res.mu, theta=res.theta, w=res.weight)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def test_mbp_ibis_two_ranks_equal_one_rank_bitwise(tmp_path):
+    """theta-particles and their trajectories sharded over 2 ranks (gloo collectives, both on cuda:0): the two-phase
+    trajectory migration must reproduce the single-process run bit for bit."""
+    import socket
+    import torch.multiprocessing as mp
+    one, two = str(tmp_path / "one.npz"), str(tmp_path / "two.npz")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_mbp_worker, args=(1, port, one), nprocs=1, join=True)
+    mp.spawn(_mbp_worker, args=(2, port, two), nprocs=2, join=True)
+    a, b = np.load(one), np.load(two)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
