@@ -247,3 +247,36 @@ def test_generic_rate_table_models_bit_exact(dp, orc, name, ic, theta, fd):
     g = pf.loglik(np.tile(th[:, None], (1, 64)))
     r, _ = orc.pf_partial_batch(pf.dmodel.compiled.desc, np.tile(th[:, None], (1, 64)), 1024, 1, 3, 1, key=99, threads=orc.max_threads())
     assert abs(g.mean() - r.mean()) < 5 * np.sqrt(g.var(ddof=1) / 64 + r.var(ddof=1) / 64) + 1e-9
+
+
+def test_more_tiles_than_one_scan_chunk_bit_exact(dp, orc):
+    """N > 1024 tiles of 1024 particles: the per-filter combine scans the tile partials in several chunks."""
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    n = 1024 * 1024 + 5000  # 1029 tiles, ragged last tile
+    pf = _pf(dp, hmm, n, f64=True)
+    tile, items = pf.geometry()
+    pf.set_stream_key(2026)
+    ll = pf.partial(theta, 1, 2)[0]
+    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 2, 1, 2026, 0, orc.MODE_DEVICE, tile, items,
+                       threads=orc.max_threads())
+    assert pf.last_event_count() == o[3]
+    assert np.array_equal(pf.last_ancestors(), o[2]) and np.array_equal(pf.get_pop(1), o[5])
+    assert abs(ll - o[0]) <= 1e-12 * abs(o[0])
+
+
+def test_degenerate_weights_collapse_to_few_ancestors(dp, orc):
+    """An observation that only a handful of particles explain: one ancestor tile feeds (almost) every offspring, so a
+    single warp of the resample kernel loops over many windows.  Bit-exact against the oracle."""
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    y2 = [dp.Observation(1.0, 1, 1.0, [0, 9, 0]), dp.Observation(2.0, 1, 1.0, [0, 9, 0])]  # I = 9 after one time unit is rare
+    model2 = dp.generate_model("SIR", [100, 1, 0], obs_error=0.25)
+    hmm2 = dp.get_private_model(model2, y2)
+    n = 20000
+    pf = _pf(dp, hmm2, n, f64=True)
+    tile, items = pf.geometry()
+    pf.set_stream_key(77)
+    ll = pf.partial(theta, 1, 1)[0]
+    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 1, 1, 77, 0, orc.MODE_DEVICE, tile, items)
+    anc = pf.last_ancestors()
+    assert np.array_equal(anc, o[2]) and np.array_equal(pf.get_pop(1), o[5]) and abs(ll - o[0]) < 1e-9
+    assert len(np.unique(anc)) < n // 20  # heavy collapse
