@@ -178,7 +178,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     pf->n_batch = n_batch;
     pf->rs_type = rs_type;
     pf->seed = seed;
-    pf->items = n_particles <= 256 ? 1 : 4;  // scan-tree geometry: 256-particle tiles for tiny filters, 1024 otherwise
+    pf->items = n_particles <= 256 ? kItemsSmall : kItemsLarge;  // scan-tree geometry: 256-particle tiles for tiny filters, 1024 otherwise
     pf->tile = kBlockThreads * pf->items;
     pf->ntiles = (int)((n_particles + pf->tile - 1) / pf->tile);
     pf->n_pad = (long long)pf->ntiles * pf->tile;

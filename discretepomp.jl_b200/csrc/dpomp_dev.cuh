@@ -11,7 +11,20 @@
 
 namespace dpomp {
 
-constexpr int kBlockThreads = 256;
+// CTA geometry of the particle-filter kernels.  128 threads x 8 particles per thread (1024-particle tiles) lets 7-8 CTAs
+// share an SM, so the 1024 tiles of a 2^20-particle filter are all resident at once (148 x 7 = 1036 slots): no second
+// wave, and 8 particles per lane keep the warp work queues full longer.  Filters of <= 256 particles use 2 per thread.
+#ifndef DPOMP_BLOCK_THREADS
+#define DPOMP_BLOCK_THREADS 128
+#endif
+#ifndef DPOMP_ITEMS_LARGE
+#define DPOMP_ITEMS_LARGE 8
+#endif
+#ifndef DPOMP_ITEMS_SMALL
+#define DPOMP_ITEMS_SMALL 2
+#endif
+constexpr int kBlockThreads = DPOMP_BLOCK_THREADS;
+constexpr int kItemsLarge = DPOMP_ITEMS_LARGE, kItemsSmall = DPOMP_ITEMS_SMALL;
 
 // Programmatic dependent launch: consecutive kernels of one filter pass are launched with the
 // programmatic-stream-serialization attribute, so the launch latency and block scheduling of kernel k+1 overlap the

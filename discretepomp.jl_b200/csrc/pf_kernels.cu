@@ -60,7 +60,7 @@ int sim_kernel_supported(int n_comp, int n_events) {
 // rows are then copied with coalesced 128-byte writes over i and near-sorted reads over q.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef DPOMP_RS_MINB
-#define DPOMP_RS_MINB 4
+#define DPOMP_RS_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
 template <int ITEMS>
 __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
 
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
-    cudaError_t err = items == 1 ? launch_pdl(pf_resample_kernel<1>, grid, kBlockThreads, 0, stream, a)
-                                 : launch_pdl(pf_resample_kernel<4>, grid, kBlockThreads, 0, stream, a);
+    cudaError_t err = items == kItemsSmall ? launch_pdl(pf_resample_kernel<kItemsSmall>, grid, kBlockThreads, 0, stream, a)
+                                           : launch_pdl(pf_resample_kernel<kItemsLarge>, grid, kBlockThreads, 0, stream, a);
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {
         const long long total = (long long)a.n_filters * a.n_pad;

@@ -57,9 +57,9 @@ DPOMP_BUILTIN(kModelLOTKA, 2, 3, DPOMP_L(1, 0, 0), DPOMP_L(-1, 1, -1), DPOMP_L({
 
 // resident CTAs per SM the register allocation is tuned for (the f64 parity loop is not tuned)
 template <typename Real, int C, int E>
-// measured on B200 (SIR C2): 4 resident CTAs with 64 registers and no spills beat 5 / 6 CTAs with 48 / 40 registers
+// 256-thread CTAs: 4 resident (64 registers, no spills) beat 5 / 6 (48 / 40 registers) on B200; 128-thread CTAs: 7 resident
 #ifndef DPOMP_SIM_MINB
-#define DPOMP_SIM_MINB 4
+#define DPOMP_SIM_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
 constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; }
 
@@ -427,15 +427,15 @@ static cudaError_t launch_sim_typed(const ModelHost& mh, int items, const SimLau
     const int model_id = builtin_model_id(mh.desc);
 #define X(ID)                                                                                                    \
     if (model_id == ID) {                                                                                        \
-        return items == 1 ? launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, 1, ID>(mh, a, stream)          \
-                          : launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, 4, ID>(mh, a, stream);         \
+        return items == kItemsSmall ? launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID>(mh, a, stream)  \
+                                    : launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream); \
     }
     DPOMP_SIM_BUILTINS(X)
 #undef X
 #define X(CC, EE)                                                                             \
     if (c <= CC && e <= EE) {                                                                 \
-        return items == 1 ? launch_sim_inst<Real, CC, EE, 1>(mh, a, stream)                   \
-                          : launch_sim_inst<Real, CC, EE, 4>(mh, a, stream);                  \
+        return items == kItemsSmall ? launch_sim_inst<Real, CC, EE, kItemsSmall>(mh, a, stream)   \
+                                    : launch_sim_inst<Real, CC, EE, kItemsLarge>(mh, a, stream);  \
     }
     DPOMP_SIM_SHAPES(X)
 #undef X
