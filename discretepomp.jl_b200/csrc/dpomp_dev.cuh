@@ -191,7 +191,7 @@ __device__ __forceinline__ double div_by_n(const ResampleCtx& c, double v) {
     return c.pow2 ? v * c.inv_n : __ddiv_rn(v, c.dn);
 }
 
-__device__ __forceinline__ double resample_u(const ResampleCtx& c, long long i /*1-based*/) {
+__device__ __forceinline__ double resample_u(const ResampleCtx& c, int i /*1-based, n < 2^31*/) {
     const double q = div_by_n(c, (double)(i - 1));
     double r = c.r1_over_n;
     if (c.rs_type == DPOMP_RS_STRATIFIED) {
@@ -202,12 +202,13 @@ __device__ __forceinline__ double resample_u(const ResampleCtx& c, long long i /
 }
 
 __device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, double v) {
-    if (!(c.s > 0.0)) return c.n;
+    const int n = (int)c.n;
+    if (!(c.s > 0.0)) return n;
     double g = (c.rs_type == DPOMP_RS_STRATIFIED) ? floor(v * c.inv_s * c.dn)
                                                   : floor((v * c.inv_s - c.r1_over_n) * c.dn) + 1.0;
     g = fmin(fmax(g, 0.0), c.dn);
-    long long e = (long long)g;
-    while (e < c.n && resample_u(c, e + 1) <= v) ++e;
+    int e = (int)g;
+    while (e < n && resample_u(c, e + 1) <= v) ++e;
     while (e > 0 && resample_u(c, e) > v) --e;
     return e;
 }
