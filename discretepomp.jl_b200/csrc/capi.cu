@@ -52,6 +52,9 @@ struct dpomp_pf {
     bool record_anc = false, initialised = false, last_resampled = false;
     double *theta_dev = nullptr, *tile_m = nullptr, *tile_s = nullptr, *tile_f = nullptr, *tile_off = nullptr;
     double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
+    double *grp_m = nullptr, *grp_s = nullptr, *grp_f = nullptr, *grp_off = nullptr;
+    unsigned int* grp_counter = nullptr;
+    int ngroups = 0;
     unsigned int* tile_counter = nullptr;
     unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
     double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
@@ -144,6 +147,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaSetDevice(pf->device);
     cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->wtile); cudaFree(pf->cw); cudaFree(pf->anc);
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
+    cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev);
     cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
@@ -206,6 +210,13 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->tile_s, B * NT * sizeof(double));
     ALLOC(pf->tile_f, B * NT * sizeof(double));
     ALLOC(pf->tile_off, B * (NT + 1) * sizeof(double));
+    pf->ngroups = (pf->ntiles + kGroupTiles - 1) / kGroupTiles;
+    const size_t NG = (size_t)pf->ngroups;
+    ALLOC(pf->grp_m, B * NG * sizeof(double));
+    ALLOC(pf->grp_s, B * NG * sizeof(double));
+    ALLOC(pf->grp_f, B * NG * sizeof(double));
+    ALLOC(pf->grp_off, B * NG * sizeof(double));
+    ALLOC(pf->grp_counter, B * NG * sizeof(unsigned int));
     ALLOC(pf->filt_m, B * sizeof(double));
     ALLOC(pf->filt_s, B * sizeof(double));
     ALLOC(pf->ll_acc, B * sizeof(double));
@@ -224,6 +235,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
               cudaMemsetAsync(pf->pop[0], 0, B * pf->n_comp * NP * sizeof(int32_t), pf->stream) == cudaSuccess &&
               cudaMemsetAsync(pf->pop[1], 0, B * pf->n_comp * NP * sizeof(int32_t), pf->stream) == cudaSuccess &&
               cudaMemsetAsync(pf->tile_counter, 0, B * sizeof(unsigned int), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->grp_counter, 0, B * (size_t)pf->ngroups * sizeof(unsigned int), pf->stream) == cudaSuccess &&
               cudaMemsetAsync(pf->counters, 0, 2 * sizeof(unsigned long long), pf->stream) == cudaSuccess &&
               cudaMemcpyAsync(pf->obs_time_dev, model->h.obs_time.data(), (size_t)d.n_obs * sizeof(double),
                               cudaMemcpyHostToDevice, pf->stream) == cudaSuccess &&
@@ -354,6 +366,8 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         a.obs_ysum = pf->obs_ysum_dev;
         a.tile_m = pf->tile_m; a.tile_s = pf->tile_s; a.tile_f = pf->tile_f; a.tile_off = pf->tile_off;
         a.filt_m = pf->filt_m; a.filt_s = pf->filt_s; a.ll_acc = pf->ll_acc;
+        a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
+        a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups;
         a.tile_counter = pf->tile_counter;
         a.ev_count = pf->counters; a.ovf_count = pf->counters + 1;
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
@@ -368,6 +382,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             ResampleLaunch r{};
             r.pop_src = pf->pop[pf->cur]; r.pop_dst = pf->pop[pf->cur ^ 1];
             r.wtile = pf->wtile; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;
+            r.grp_f = pf->grp_f; r.grp_off = pf->grp_off; r.ngroups = pf->ngroups;
             r.anc = pf->record_anc ? pf->anc : nullptr;
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;

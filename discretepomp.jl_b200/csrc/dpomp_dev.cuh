@@ -53,6 +53,13 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned bl
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
+// Two-level combination of the tile partials (DESIGN.md "deterministic scan tree"): kGroupTiles consecutive tiles form a
+// group that is combined by the last of its tiles to finish (one warp), the groups by the last group to finish.
+//   cw_q = O_g + F_g * (o_{b|g} + f_{b|g} * incl_q)
+constexpr int kGroupTiles = 32;
+__device__ __forceinline__ double tile_cw(double grp_off, double grp_f, double tile_o, double tile_f, double incl) {
+    return __dadd_rn(grp_off, __dmul_rn(grp_f, __dadd_rn(tile_o, __dmul_rn(tile_f, incl))));
+}
 constexpr uint32_t kTagSim = 0u;
 constexpr uint32_t kTagResample = 1u;
 

@@ -41,8 +41,14 @@ struct SimLaunch {
     const double* obs_ysum;  // [T]  sum_v ymask[v] * y.val[v]
     double* tile_m;          // [B][ntiles]
     double* tile_s;          // [B][ntiles]
-    double* tile_f;          // [B][ntiles]
-    double* tile_off;        // [B][ntiles + 1]
+    double* tile_f;          // [B][ntiles]  f_{b|g} = exp(m_b - m_g): tile scale inside its group of kGroupTiles tiles
+    double* tile_off;        // [B][ntiles]  o_{b|g}: exclusive offset of the tile inside its group (group scale)
+    double* grp_m;           // [B][ngroups] group maxima / sums / scales F_g = exp(m_g - M) / exclusive offsets O_g
+    double* grp_s;
+    double* grp_f;
+    double* grp_off;
+    unsigned int* grp_counter;  // [B][ngroups] tickets of the tiles of a group
+    int ngroups;
     double* filt_m;          // [B]
     double* filt_s;          // [B]
     double* ll_acc;          // [B]
@@ -70,6 +76,9 @@ struct ResampleLaunch {
     const double* tile_m;
     const double* tile_f;
     const double* tile_off;
+    const double* grp_f;
+    const double* grp_off;
+    int ngroups;
     const double* filt_s;
     int32_t* anc;            // [B][n_pad] 0-based ancestors, or nullptr
     double* cw;              // [B][n_pad] cumulative weights (multinomial only), or nullptr

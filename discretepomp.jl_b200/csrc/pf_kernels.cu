@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
 
     pdl_wait();
     const double big_s = a.filt_s[b];
-    const double off_b = a.tile_off[(size_t)b * (a.ntiles + 1) + tile];
-    const double off_n = a.tile_off[(size_t)b * (a.ntiles + 1) + tile + 1];
-    const double f_b = a.tile_f[(size_t)b * a.ntiles + tile];
+    const int grp = tile / kGroupTiles;
+    const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
+    const double t_off = a.tile_off[(size_t)b * a.ntiles + tile], t_f = a.tile_f[(size_t)b * a.ntiles + tile];
 
     double incl[ITEMS];
     const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
@@ -101,22 +101,31 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel
         double* cw = a.cw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) cw[k] = __dadd_rn(off_b, __dmul_rn(f_b, incl[k]));
+        for (int k = 0; k < ITEMS; ++k) cw[k] = tile_cw(g_off, g_f, t_off, t_f, incl[k]);
         return;
     }
 
     const Philox4 p = stream_draw(a.key, 0u, gfilter, (uint32_t)a.t, kTagResample, 0u);
     const ResampleCtx ctx = make_resample_ctx(a.rs_type, a.n, big_s, a.key, gfilter, (uint32_t)a.t, u53(p.w0, p.w1));
 
-    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, off_b);
-    if (tid == 32) lohi_s[1] = (tile == a.ntiles - 1) ? a.n : resample_ecount(ctx, off_n);
+    // tile seams: the offset of a tile is its cw at incl = 0
+    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
+    if (tid == 32) {
+        long long hi_b = a.n;
+        if (tile != a.ntiles - 1) {
+            const int g2 = (tile + 1) / kGroupTiles;
+            hi_b = resample_ecount(ctx, tile_cw(a.grp_off[(size_t)b * a.ngroups + g2], a.grp_f[(size_t)b * a.ngroups + g2],
+                                                a.tile_off[(size_t)b * a.ntiles + tile + 1], 1.0, 0.0));
+        }
+        lohi_s[1] = hi_b;
+    }
     const long long rem = a.n - base_n;
     const int nvalid = rem < TILE ? (int)rem : TILE;
     // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
     int er[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        er[k] = (int)resample_ecount(ctx, __dadd_rn(off_b, __dmul_rn(f_b, incl[k])));
+        er[k] = (int)resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
         if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
     }
     // running maximum in item order: lane-serial, then Kogge-Stone over the lanes; the warp maximum goes to shared memory
@@ -220,11 +229,16 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
     const double big_s = a.filt_s[b];
     const Philox4 p = stream_draw(a.key, (uint32_t)i, gfilter, (uint32_t)a.t, kTagResample, 1u);
     const double chs = __dmul_rn(u53(p.w0, p.w1), big_s);
-    const double* off = a.tile_off + (size_t)b * (a.ntiles + 1);
-    int lt = 0, ht = a.ntiles;  // first tile with chs < off[tile + 1]
+    auto tile_end = [&](int t) -> double {  // offset of tile t + 1 (= end of tile t); the filter total after the last tile
+        if (t + 1 >= a.ntiles) return big_s;
+        const int g2 = (t + 1) / kGroupTiles;
+        return tile_cw(a.grp_off[(size_t)b * a.ngroups + g2], a.grp_f[(size_t)b * a.ngroups + g2],
+                       a.tile_off[(size_t)b * a.ntiles + t + 1], 1.0, 0.0);
+    };
+    int lt = 0, ht = a.ntiles;  // first tile with chs < end(tile)
     while (lt < ht) {
         const int mid = (lt + ht) >> 1;
-        if (chs < off[mid + 1]) ht = mid; else lt = mid + 1;
+        if (chs < tile_end(mid)) ht = mid; else lt = mid + 1;
     }
     long long res = a.n - 1;
     if (lt < a.ntiles) {

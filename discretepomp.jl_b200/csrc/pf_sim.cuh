@@ -80,7 +80,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     int* ovf_s = reinterpret_cast<int*>(smem_raw);        // [TILE] 1 = the particle hit the event cap
     SState* st_s = reinterpret_cast<SState*>(ovf_s + TILE);  // [C][TILE]
     __shared__ double warp_scratch[kBlockThreads / 32];
-    __shared__ int is_last_s;
     __shared__ uint32_t stream_s[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -313,50 +312,90 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         }
     }
 
+    // ---- two-level combine of the tile partials, each level done by whoever finishes last (tickets) -----------------
+    // level 1: the kGroupTiles tiles of a group, level 2: the groups of the filter.  Both levels are one warp with the
+    // same tree (one value per lane, Kogge-Stone over the lanes, chunks of 32 chained sequentially): no block barriers on
+    // the serial tail of the kernel.
+    const int grp = tile / kGroupTiles;
+    const int grp_tiles = min(kGroupTiles, a.ntiles - grp * kGroupTiles);
+    __shared__ int flag_s;
     if (tid == 0) {
         a.tile_m[(size_t)b * a.ntiles + tile] = m_b;
         a.tile_s[(size_t)b * a.ntiles + tile] = s_b;
         __threadfence();
-        const unsigned int ticket = atomicAdd(&a.tile_counter[b], 1u);
-        is_last_s = (ticket == (unsigned int)(a.ntiles - 1));
+        const unsigned int ticket = atomicAdd(&a.grp_counter[(size_t)b * a.ngroups + grp], 1u);
+        flag_s = (ticket == (unsigned int)(grp_tiles - 1));
     }
     __syncthreads();
-    if (!is_last_s) return;
+    if (!flag_s || tid >= 32) return;
 
-    // ---- last tile of this filter: combine partials -> M, S, tile scale factors and tile offsets, log-lik increment
-    __threadfence();
-    const double* tm_b = a.tile_m + (size_t)b * a.ntiles;
-    const double* ts_b = a.tile_s + (size_t)b * a.ntiles;
-    double mm = -INFINITY;
-    for (int i = tid; i < a.ntiles; i += kBlockThreads) mm = fmax(mm, __ldcg(tm_b + i));
-    const double big_m = block_max(mm, warp_scratch);
+    // level 1: tiles of this group -> f_{b|g}, o_{b|g}, (m_g, s_g)
+    int last_group = 0;
+    {
+        const int i = grp * kGroupTiles + tid;
+        const bool have = i < a.ntiles;
+        const double mb = have ? __ldcg(a.tile_m + (size_t)b * a.ntiles + i) : -INFINITY;
+        const double sb = have ? __ldcg(a.tile_s + (size_t)b * a.ntiles + i) : 0.0;
+        double mg = mb;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, d));
+        const double f = (mb == -INFINITY) ? 0.0 : exp(mb - mg);
+        double inc = __dmul_rn(f, sb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (tid >= d) inc = __dadd_rn(y, inc);
+        }
+        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (tid == 0) prev = 0.0;
+        if (have) {
+            a.tile_f[(size_t)b * a.ntiles + i] = f;
+            a.tile_off[(size_t)b * a.ntiles + i] = prev;
+        }
+        if (tid == 31) {
+            a.grp_m[(size_t)b * a.ngroups + grp] = mg;
+            a.grp_s[(size_t)b * a.ngroups + grp] = inc;
+            a.grp_counter[(size_t)b * a.ngroups + grp] = 0u;
+            __threadfence();
+            const unsigned int ticket = atomicAdd(&a.tile_counter[b], 1u);
+            last_group = (ticket == (unsigned int)(a.ngroups - 1));
+        }
+        last_group = __shfl_sync(0xffffffffu, last_group, 31);
+    }
+    if (!last_group) return;
+
+    // level 2: groups of the filter -> M, F_g = exp(m_g - M), O_g, S and the log-likelihood increment
+    const double* gm_b = a.grp_m + (size_t)b * a.ngroups;
+    const double* gs_b = a.grp_s + (size_t)b * a.ngroups;
+    double big_m = -INFINITY;
+    for (int i = tid; i < a.ngroups; i += 32) big_m = fmax(big_m, __ldcg(gm_b + i));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) big_m = fmax(big_m, __shfl_xor_sync(0xffffffffu, big_m, d));
     double carry = 0.0;
-    for (int c0 = 0; c0 < a.ntiles; c0 += TILE) {
-        double tb[ITEMS];
+    for (int c0 = 0; c0 < a.ngroups; c0 += 32) {
+        const int i = c0 + tid;
+        const bool have = i < a.ngroups;
+        const double mg = have ? __ldcg(gm_b + i) : -INFINITY;
+        const double f = (mg == -INFINITY) ? 0.0 : exp(mg - big_m);
+        double inc = have ? __dmul_rn(f, __ldcg(gs_b + i)) : 0.0;
 #pragma unroll
-        for (int kk = 0; kk < ITEMS; ++kk) {
-            const int i = c0 + tid * ITEMS + kk;
-            tb[kk] = 0.0;
-            if (i < a.ntiles) {
-                const double mb = __ldcg(tm_b + i);
-                const double f = (mb == -INFINITY) ? 0.0 : exp(mb - big_m);
-                a.tile_f[(size_t)b * a.ntiles + i] = f;
-                tb[kk] = __dmul_rn(f, __ldcg(ts_b + i));
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (tid >= d) inc = __dadd_rn(y, inc);
         }
-        const double tot = tile_scan<ITEMS>(tb, incl, excl, warp_scratch);
-#pragma unroll
-        for (int kk = 0; kk < ITEMS; ++kk) {
-            const int i = c0 + tid * ITEMS + kk;
-            if (i < a.ntiles) a.tile_off[(size_t)b * (a.ntiles + 1) + i] = __dadd_rn(carry, excl[kk]);
+        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (tid == 0) prev = 0.0;
+        if (have) {
+            a.grp_f[(size_t)b * a.ngroups + i] = f;
+            a.grp_off[(size_t)b * a.ngroups + i] = __dadd_rn(carry, prev);
         }
-        carry = __dadd_rn(carry, tot);
+        carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, inc, 31));
     }
     if (tid == 0) {
-        a.tile_off[(size_t)b * (a.ntiles + 1) + a.ntiles] = carry;
         a.filt_s[b] = carry;
         a.filt_m[b] = big_m;
-        if (a.has_lik) a.ll_acc[b] += big_m + log(carry / (double)a.n);  // log(cum_weight[end] / N) (:60), as LSE
+        // log(cum_weight[end] / N) (:60) as log-sum-exp; one add per kernel and filter, so the RED is deterministic
+        if (a.has_lik) atomicAdd(&a.ll_acc[b], big_m + log(carry / (double)a.n));
         a.tile_counter[b] = 0u;
     }
 }

@@ -33,6 +33,7 @@
 
 #define ORC_MODE_LITERAL 0
 #define ORC_MODE_DEVICE 1
+#define ORC_GROUP_TILES 32 /* tiles per group of the two-level combine (kGroupTiles of the device code) */
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants).                                         */
@@ -341,27 +342,63 @@ static double device_normalise_resample(const double* logw, int64_t n, int tile,
         s_b[b] = tile_scan(a, tile, items, NULL, NULL);
         if (mb > big_m) big_m = mb;
     }
-    /* tile offsets: scan of T_b = f_b * s_b, chunks of `tile` chained sequentially */
-    double carry = 0.0;
-    {
-        double* tb = (double*)malloc(sizeof(double) * (size_t)tile);
-        double* ex = (double*)malloc(sizeof(double) * (size_t)tile);
-        for (int64_t c0 = 0; c0 < ntiles; c0 += tile) {
-            for (int q = 0; q < tile; ++q) {
-                int64_t b = c0 + q;
-                if (b < ntiles) {
-                    f_b[b] = (m_b[b] == -INFINITY) ? 0.0 : exp(m_b[b] - big_m);
-                    tb[q] = f_b[b] * s_b[b];
-                } else tb[q] = 0.0;
-            }
-            double tot = tile_scan(tb, tile, items, NULL, ex);
-            for (int q = 0; q < tile; ++q)
-                if (c0 + q < ntiles) off[c0 + q] = carry + ex[q];
-            carry = carry + tot;
+    /* two-level combine (DESIGN.md "deterministic scan tree"): groups of ORC_GROUP_TILES tiles, then the groups.
+     *   level 1: m_g = max m_b; f_{b|g} = exp(m_b - m_g); o_{b|g} = Kogge-Stone exclusive scan of f_{b|g} s_b over the 32 lanes
+     *   level 2: M = max m_g; F_g = exp(m_g - M); O_g = the same 32-lane scan of F_g s_g, chunks of 32 chained sequentially
+     *   cw_q = O_g + F_g * (o_{b|g} + f_{b|g} * incl_q);  off[b] = cw at incl = 0 */
+    const int64_t ngroups = (ntiles + ORC_GROUP_TILES - 1) / ORC_GROUP_TILES;
+    double* g_m = (double*)malloc(sizeof(double) * (size_t)ngroups);
+    double* g_s = (double*)malloc(sizeof(double) * (size_t)ngroups);
+    double* g_f = (double*)malloc(sizeof(double) * (size_t)ngroups);
+    double* g_off = (double*)malloc(sizeof(double) * (size_t)ngroups);
+    double* t_o = (double*)malloc(sizeof(double) * (size_t)ntiles);
+    big_m = -INFINITY;
+    for (int64_t g = 0; g < ngroups; ++g) {
+        double mg = -INFINITY, scan[32];
+        for (int l = 0; l < 32; ++l) {
+            const int64_t b = g * ORC_GROUP_TILES + l;
+            if (b < ntiles && m_b[b] > mg) mg = m_b[b];
         }
-        free(tb); free(ex);
+        for (int l = 0; l < 32; ++l) {
+            const int64_t b = g * ORC_GROUP_TILES + l;
+            double f = 0.0, sb = 0.0;
+            if (b < ntiles) { f = (m_b[b] == -INFINITY) ? 0.0 : exp(m_b[b] - mg); sb = s_b[b]; f_b[b] = f; }
+            scan[l] = f * sb;
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            double nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = (l >= d) ? scan[l - d] + scan[l] : scan[l];
+            memcpy(scan, nxt, sizeof(scan));
+        }
+        for (int l = 0; l < 32; ++l) {
+            const int64_t b = g * ORC_GROUP_TILES + l;
+            if (b < ntiles) t_o[b] = (l > 0) ? scan[l - 1] : 0.0;
+        }
+        g_m[g] = mg; g_s[g] = scan[31];
+        if (mg > big_m) big_m = mg;
+    }
+    double carry = 0.0;
+    for (int64_t c0 = 0; c0 < ngroups; c0 += 32) { /* same tree as level 1: Kogge-Stone over 32 lanes, chunks chained */
+        double scan[32];
+        for (int l = 0; l < 32; ++l) {
+            const int64_t g = c0 + l;
+            if (g < ngroups) {
+                g_f[g] = (g_m[g] == -INFINITY) ? 0.0 : exp(g_m[g] - big_m);
+                scan[l] = g_f[g] * g_s[g];
+            } else scan[l] = 0.0;
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            double nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = (l >= d) ? scan[l - d] + scan[l] : scan[l];
+            memcpy(scan, nxt, sizeof(scan));
+        }
+        for (int l = 0; l < 32; ++l)
+            if (c0 + l < ngroups) g_off[c0 + l] = carry + ((l > 0) ? scan[l - 1] : 0.0);
+        carry = carry + scan[31];
     }
     double big_s = carry;
+#define ORC_CW(b, inc) (g_off[(b) / ORC_GROUP_TILES] + g_f[(b) / ORC_GROUP_TILES] * (t_o[b] + f_b[b] * (inc)))
+    for (int64_t b = 0; b < ntiles; ++b) off[b] = g_off[b / ORC_GROUP_TILES] + g_f[b / ORC_GROUP_TILES] * (t_o[b] + 1.0 * 0.0);
     off[ntiles] = big_s;
     double ll = big_m + log(big_s / (double)n);
     if (do_resample && rs_type != DPOMP_RS_MULTINOMIAL) {
@@ -380,7 +417,7 @@ static double device_normalise_resample(const double* logw, int64_t n, int tile,
             int64_t hi = (b == ntiles - 1) ? n : ecount(&ctx, off[b + 1]);
             int64_t nvalid = (n - b * tile < tile) ? (n - b * tile) : tile;
             for (int q = 0; q < nvalid; ++q) {
-                int64_t ev = ecount(&ctx, off[b] + f_b[b] * incl[q]);
+                int64_t ev = ecount(&ctx, ORC_CW(b, incl[q]));
                 if (ev < lo) ev = lo;
                 if (ev > hi) ev = hi;
                 e[q] = ev;
@@ -405,7 +442,7 @@ static double device_normalise_resample(const double* logw, int64_t n, int tile,
             }
             tile_scan(a, tile, items, incl, NULL);
             for (int q = 0; q < tile; ++q)
-                if (b * tile + q < n) cw[b * tile + q] = off[b] + f_b[b] * incl[q];
+                if (b * tile + q < n) cw[b * tile + q] = ORC_CW(b, incl[q]);
         }
         for (int64_t i = 0; i < n; ++i) {
             uint32_t w4[4];
@@ -430,6 +467,8 @@ static double device_normalise_resample(const double* logw, int64_t n, int tile,
         free(cw);
     }
     free(a); free(incl); free(m_b); free(s_b); free(f_b); free(off);
+    free(g_m); free(g_s); free(g_f); free(g_off); free(t_o);
+#undef ORC_CW
     return ll;
 }
 
