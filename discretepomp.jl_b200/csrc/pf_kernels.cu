@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     constexpr int NW = kBlockThreads / 32;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ int am_s[NW][CHUNK];  // per warp: offspring window -> ancestor index within the warp's chunk
+    extern __shared__ __align__(16) int st_dyn[];  // [NW][n_comp][CHUNK] states of the warp's ancestors (gather source)
     __shared__ int warp_max_s[NW];
     __shared__ long long lohi_s[2];
 
@@ -84,6 +85,23 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
     const double t_off = a.tile_off[(size_t)b * a.ntiles + tile], t_f = a.tile_f[(size_t)b * a.ntiles + tile];
 
+    // stage the states of this warp's CHUNK ancestors (coalesced, independent of everything below): the gather then reads
+    // shared memory instead of paying a second dependent trip to L2
+    int* st_w = st_dyn + (size_t)warp * a.n_comp * CHUNK;
+    {
+        const int32_t* src_w = a.pop_src + (size_t)b * a.n_comp * a.n_pad + base_n + warp * CHUNK + lane * ITEMS;
+        for (int c = 0; c < a.n_comp; ++c) {
+            if constexpr (ITEMS % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < ITEMS; k += 4)
+                    *reinterpret_cast<int4*>(st_w + c * CHUNK + lane * ITEMS + k) =
+                        *reinterpret_cast<const int4*>(src_w + (size_t)c * a.n_pad + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) st_w[c * CHUNK + lane * ITEMS + k] = src_w[(size_t)c * a.n_pad + k];
+            }
+        }
+    }
     double incl[ITEMS];
     const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
     if constexpr (ITEMS % 2 == 0) {  // 128-bit loads
@@ -161,7 +179,6 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     const int wfirst = clamp_off(wprev_raw);                    // the warp owns offspring offsets (wfirst, wlast]
     const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
 
-    const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad + base_n + warp * CHUNK;
     int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
     int* am_w = am_s[warp];
     for (int wlo = wfirst; wlo < wlast; wlo += CHUNK) {
@@ -198,7 +215,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
             srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
         }
         for (int c = 0; c < a.n_comp; ++c) {
-            const int32_t* sc = src_b + (size_t)c * a.n_pad;
+            const int* sc = st_w + c * CHUNK;
             int32_t* dc = dst_b + (size_t)c * a.n_pad + wlo + lane;
             int vals[ITEMS];
 #pragma unroll
@@ -262,8 +279,9 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
 
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
-    cudaError_t err = items == kItemsSmall ? launch_pdl(pf_resample_kernel<kItemsSmall>, grid, kBlockThreads, 0, stream, a)
-                                           : launch_pdl(pf_resample_kernel<kItemsLarge>, grid, kBlockThreads, 0, stream, a);
+    const size_t smem = (size_t)kBlockThreads * items * a.n_comp * sizeof(int);  // staged ancestor states
+    cudaError_t err = items == kItemsSmall ? launch_pdl(pf_resample_kernel<kItemsSmall>, grid, kBlockThreads, smem, stream, a)
+                                           : launch_pdl(pf_resample_kernel<kItemsLarge>, grid, kBlockThreads, smem, stream, a);
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {
         const long long total = (long long)a.n_filters * a.n_pad;
