@@ -7,6 +7,7 @@
 // run_pibis (src/hmm_ibis.jl:71-79, 105-108).
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
+#include "pf_resample.cuh"
 
 namespace dpomp {
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     constexpr int NW = kBlockThreads / 32;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ int am_s[NW][CHUNK];  // per warp: offspring window -> ancestor index within the warp's chunk
-    extern __shared__ __align__(16) int st_dyn[];  // [NW][n_comp][CHUNK] states of the warp's ancestors (gather source)
+    extern __shared__ __align__(16) int st_dyn[];  // [n_comp][TILE] states of the tile's ancestors (gather source)
     __shared__ int warp_max_s[NW];
     __shared__ long long lohi_s[2];
 
@@ -87,18 +88,17 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
 
     // stage the states of this warp's CHUNK ancestors (coalesced, independent of everything below): the gather then reads
     // shared memory instead of paying a second dependent trip to L2
-    int* st_w = st_dyn + (size_t)warp * a.n_comp * CHUNK;
     {
         const int32_t* src_w = a.pop_src + (size_t)b * a.n_comp * a.n_pad + base_n + warp * CHUNK + lane * ITEMS;
         for (int c = 0; c < a.n_comp; ++c) {
             if constexpr (ITEMS % 4 == 0) {
 #pragma unroll
                 for (int k = 0; k < ITEMS; k += 4)
-                    *reinterpret_cast<int4*>(st_w + c * CHUNK + lane * ITEMS + k) =
+                    *reinterpret_cast<int4*>(st_dyn + c * TILE + tid * ITEMS + k) =
                         *reinterpret_cast<const int4*>(src_w + (size_t)c * a.n_pad + k);
             } else {
 #pragma unroll
-                for (int k = 0; k < ITEMS; ++k) st_w[c * CHUNK + lane * ITEMS + k] = src_w[(size_t)c * a.n_pad + k];
+                for (int k = 0; k < ITEMS; ++k) st_dyn[c * TILE + tid * ITEMS + k] = src_w[(size_t)c * a.n_pad + k];
             }
         }
     }
@@ -123,116 +123,9 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
         return;
     }
 
-    const Philox4 p = stream_draw(a.key, 0u, gfilter, (uint32_t)a.t, kTagResample, 0u);
-    const ResampleCtx ctx = make_resample_ctx(a.rs_type, a.n, big_s, a.key, gfilter, (uint32_t)a.t, u53(p.w0, p.w1));
-
-    // tile seams: the offset of a tile is its cw at incl = 0
-    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
-    if (tid == 32) {
-        long long hi_b = a.n;
-        if (tile != a.ntiles - 1) {
-            const int g2 = (tile + 1) / kGroupTiles;
-            hi_b = resample_ecount(ctx, tile_cw(a.grp_off[(size_t)b * a.ngroups + g2], a.grp_f[(size_t)b * a.ngroups + g2],
-                                                a.tile_off[(size_t)b * a.ntiles + tile + 1], 1.0, 0.0));
-        }
-        lohi_s[1] = hi_b;
-    }
-    const long long rem = a.n - base_n;
-    const int nvalid = rem < TILE ? (int)rem : TILE;
-    // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
-    int er[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        er[k] = (int)resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
-        if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
-    }
-    // running maximum in item order: lane-serial, then Kogge-Stone over the lanes; the warp maximum goes to shared memory
-#pragma unroll
-    for (int k = 1; k < ITEMS; ++k) er[k] = max(er[k], er[k - 1]);
-    int inc = er[ITEMS - 1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int y = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc = max(inc, y);
-    }
-    int prev_raw = __shfl_up_sync(FULL, inc, 1);
-    if (lane == 0) prev_raw = -1;
-    if (lane == 31) warp_max_s[warp] = inc;
-    __syncthreads();  // the only block barrier
-    pdl_trigger();
-
-    const long long lo = lohi_s[0], hi = lohi_s[1];
-    int wprev_raw = -1;
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-        if (w < warp) wprev_raw = max(wprev_raw, warp_max_s[w]);
-    prev_raw = max(prev_raw, wprev_raw);
-    // clamp is monotone, so clamp(running max) == running max of the clamped counts; offsets are relative to lo
-    auto clamp_off = [&](int v) -> int {
-        const long long c = v < lo ? lo : (v > hi ? hi : (long long)v);
-        return (int)(c - lo);
-    };
-    int emax[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) emax[k] = clamp_off(max(er[k], prev_raw));
-    const int prev = clamp_off(prev_raw);                       // owned range of item 0: (prev, emax[0]]
-    const int wfirst = clamp_off(wprev_raw);                    // the warp owns offspring offsets (wfirst, wlast]
-    const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
-
-    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
-    int* am_w = am_s[warp];
-    for (int wlo = wfirst; wlo < wlast; wlo += CHUNK) {
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = -1;
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const int first = (k == 0) ? prev : emax[k - 1];
-            if (emax[k] > first && first < wlo + CHUNK && emax[k] > wlo) am_w[max(first - wlo, 0)] = lane * ITEMS + k;
-        }
-        __syncwarp();
-        int am[ITEMS];
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am[k] = am_w[lane * ITEMS + k];
-#pragma unroll
-        for (int k = 1; k < ITEMS; ++k) am[k] = max(am[k], am[k - 1]);
-        int ainc = am[ITEMS - 1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(FULL, ainc, d);
-            if (lane >= d) ainc = max(ainc, y);
-        }
-        int aprev = __shfl_up_sync(FULL, ainc, 1);
-        if (lane == 0) aprev = -1;
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
-        __syncwarp();
-        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
-        int srcq[ITEMS];
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const int pidx = j * 32 + lane;
-            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
-        }
-        for (int c = 0; c < a.n_comp; ++c) {
-            const int* sc = st_w + c * CHUNK;
-            int32_t* dc = dst_b + (size_t)c * a.n_pad + wlo + lane;
-            int vals[ITEMS];
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) vals[j] = sc[srcq[j]];
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) dc[j * 32] = vals[j];
-        }
-        if (a.anc) {
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0)
-                    a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
-        }
-        __syncwarp();
-    }
+    const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
+                    a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
+    resample_tile<ITEMS, int, false>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
 }
 
 // multinomial: offspring i draws chs = r_i * S; ancestor = first p2 < N with chs < cw[p2], else N (src/hmm_resample.jl:9-16)

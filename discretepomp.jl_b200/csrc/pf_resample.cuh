@@ -1,0 +1,164 @@
+// pf_resample.cuh -- the resample phase of one (filter, ancestor tile): counting search + offspring map + gather.
+// Shared by the stand-alone resample kernel (pf_kernels.cu) and the fused step kernel (pf_sim.cuh).
+//
+// Replaces rsp_systematic (src/hmm_pf_resample.jl:24-42) / the intended rsp_stratified (:46-63) and the `old_p .= pop`
+// copy of partial_log_likelihood! (src/hmm_particle_filter.jl:66).
+#pragma once
+#include "dpomp_dev.cuh"
+
+namespace dpomp {
+
+struct RsArgs {              // what the phase needs besides the tile's own data
+    const double* tile_f;    // [B][ntiles]
+    const double* tile_off;  // [B][ntiles]
+    const double* grp_f;     // [B][ngroups]
+    const double* grp_off;   // [B][ngroups]
+    const double* filt_s;    // [B]
+    int32_t* pop_dst;        // [B][C][n_pad]
+    int32_t* anc;            // [B][n_pad] or nullptr
+    long long n, n_pad;
+    int ntiles, ngroups, n_comp, t, rs_type;
+    uint64_t key;
+};
+
+//   cw_q = O_g + F_g * (o_{b|g} + f_{b|g} * incl_q)   (incl_q: tile-local scan, deterministic tree)
+//   e_q  = E(cw_q) = #{ i : u_i <= cw_q }               (counting form of `while u[i] > cw[j]`, src/hmm_pf_resample.jl:34-40)
+//   offspring (lo_b, hi_b] belong to this tile; offspring i takes the first q with e_q >= i, i.e. ancestor q owns
+//   (max_{q'<q} e_q', max_{q'<=q} e_q'].
+// One block barrier publishes (lo_b, hi_b) and the per-warp maxima; afterwards every warp works alone on the 32*ITEMS
+// ancestors it owns: the offspring -> ancestor map of a window of 32*ITEMS offspring is built in the warp's slice of
+// `am_s` by a scatter of the range starts followed by an inclusive max-scan; state rows are copied from the staged
+// ancestor states `st_tile[c * stride + q]` (shared memory) with coalesced 128-byte stores.
+// The combine outputs are read with ld.cg: in the fused kernel they were written by other SMs during the same launch.
+template <typename T, bool CG>
+__device__ __forceinline__ T ld_combine(const T* p) {  // CG: the value was written by another SM during this launch
+    if constexpr (CG) return __ldcg(p); else return *p;
+}
+
+template <int ITEMS, typename SrcT, bool CG>
+__device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, uint32_t gfilter, const double (&incl)[ITEMS],
+                                              const SrcT* st_tile, int stride, int* am_all, int* warp_max_s, long long* lohi_s) {
+    constexpr int TILE = kBlockThreads * ITEMS;
+    constexpr int CHUNK = 32 * ITEMS;
+    constexpr int NW = kBlockThreads / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base_n = (long long)tile * TILE;
+    const double big_s = ld_combine<double, CG>(a.filt_s + b);
+    const int grp = tile / kGroupTiles;
+    const double g_off = ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + grp), g_f = ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + grp);
+    const double t_off = ld_combine<double, CG>(a.tile_off + (size_t)b * a.ntiles + tile), t_f = ld_combine<double, CG>(a.tile_f + (size_t)b * a.ntiles + tile);
+
+    const Philox4 p = stream_draw(a.key, 0u, gfilter, (uint32_t)a.t, kTagResample, 0u);
+    const ResampleCtx ctx = make_resample_ctx(a.rs_type, a.n, big_s, a.key, gfilter, (uint32_t)a.t, u53(p.w0, p.w1));
+
+    // tile seams: the offset of a tile is its cw at incl = 0
+    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
+    if (tid == 32) {
+        long long hi_b = a.n;
+        if (tile != a.ntiles - 1) {
+            const int g2 = (tile + 1) / kGroupTiles;
+            hi_b = resample_ecount(ctx, tile_cw(ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + g2), ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + g2),
+                                                ld_combine<double, CG>(a.tile_off + (size_t)b * a.ntiles + tile + 1), 1.0, 0.0));
+        }
+        lohi_s[1] = hi_b;
+    }
+    const long long rem = a.n - base_n;
+    const int nvalid = rem < TILE ? (int)rem : TILE;
+    // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
+    int er[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        er[k] = (int)resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
+        if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
+    }
+    // running maximum in item order: lane-serial, then Kogge-Stone over the lanes; the warp maximum goes to shared memory
+#pragma unroll
+    for (int k = 1; k < ITEMS; ++k) er[k] = max(er[k], er[k - 1]);
+    int inc = er[ITEMS - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc = max(inc, y);
+    }
+    int prev_raw = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) prev_raw = -1;
+    if (lane == 31) warp_max_s[warp] = inc;
+    __syncthreads();  // the only block barrier
+    pdl_trigger();
+
+    const long long lo = lohi_s[0], hi = lohi_s[1];
+    int wprev_raw = -1;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (w < warp) wprev_raw = max(wprev_raw, warp_max_s[w]);
+    prev_raw = max(prev_raw, wprev_raw);
+    // clamp is monotone, so clamp(running max) == running max of the clamped counts; offsets are relative to lo
+    auto clamp_off = [&](int v) -> int {
+        const long long c = v < lo ? lo : (v > hi ? hi : (long long)v);
+        return (int)(c - lo);
+    };
+    int emax[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) emax[k] = clamp_off(max(er[k], prev_raw));
+    const int prev = clamp_off(prev_raw);                       // owned range of item 0: (prev, emax[0]]
+    const int wfirst = clamp_off(wprev_raw);                    // the warp owns offspring offsets (wfirst, wlast]
+    const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
+
+    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
+    int* am_w = am_all + warp * CHUNK;
+    for (int wlo = wfirst; wlo < wlast; wlo += CHUNK) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = -1;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int first = (k == 0) ? prev : emax[k - 1];
+            if (emax[k] > first && first < wlo + CHUNK && emax[k] > wlo) am_w[max(first - wlo, 0)] = lane * ITEMS + k;
+        }
+        __syncwarp();
+        int am[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am[k] = am_w[lane * ITEMS + k];
+#pragma unroll
+        for (int k = 1; k < ITEMS; ++k) am[k] = max(am[k], am[k - 1]);
+        int ainc = am[ITEMS - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, ainc, d);
+            if (lane >= d) ainc = max(ainc, y);
+        }
+        int aprev = __shfl_up_sync(FULL, ainc, 1);
+        if (lane == 0) aprev = -1;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
+        __syncwarp();
+        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
+        int srcq[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int pidx = j * 32 + lane;
+            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+        }
+        for (int c = 0; c < a.n_comp; ++c) {
+            const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
+            int32_t* dc = dst_b + (size_t)c * a.n_pad + wlo + lane;
+            int vals[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0) dc[j * 32] = vals[j];
+        }
+        if (a.anc) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (srcq[j] >= 0)
+                    a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace dpomp
