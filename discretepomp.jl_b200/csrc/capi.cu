@@ -59,6 +59,13 @@ struct dpomp_pf {
     unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
     double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
     int64_t* slots_dev = nullptr;            // 2 * n_batch
+    unsigned long long* work_counter = nullptr;  // fused step kernel: arrival-order CTA tickets (monotone)
+    unsigned long long work_base = 0;
+    unsigned int* filt_gen = nullptr;            // [n_batch] generation of the last finished combine
+    unsigned int gen = 0;
+    bool fused_enabled = true;
+    int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
+    int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
     uint32_t* filter_ids_dev = nullptr;      // n_batch, valid when use_filter_ids
     bool use_filter_ids = false;
     double* h_theta = nullptr;               // pinned staging
@@ -149,7 +156,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
     cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
-    cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev);
+    cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev); cudaFree(pf->work_counter); cudaFree(pf->filt_gen);
     cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
     for (cudaEvent_t e : pf->kev) cudaEventDestroy(e);
     if (pf->ev0) cudaEventDestroy(pf->ev0);
@@ -226,6 +233,8 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->obs_ysum_dev, (size_t)d.n_obs * sizeof(double));
     ALLOC(pf->slots_dev, 2 * B * sizeof(int64_t));
     ALLOC(pf->filter_ids_dev, B * sizeof(uint32_t));
+    ALLOC(pf->work_counter, sizeof(unsigned long long));
+    ALLOC(pf->filt_gen, B * sizeof(unsigned int));
 #undef ALLOC
     bool ok = cudaMallocHost((void**)&pf->h_theta, B * pf->n_params * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void**)&pf->h_ll, B * sizeof(double)) == cudaSuccess &&
@@ -237,6 +246,8 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
               cudaMemsetAsync(pf->tile_counter, 0, B * sizeof(unsigned int), pf->stream) == cudaSuccess &&
               cudaMemsetAsync(pf->grp_counter, 0, B * (size_t)pf->ngroups * sizeof(unsigned int), pf->stream) == cudaSuccess &&
               cudaMemsetAsync(pf->counters, 0, 2 * sizeof(unsigned long long), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->work_counter, 0, sizeof(unsigned long long), pf->stream) == cudaSuccess &&
+              cudaMemsetAsync(pf->filt_gen, 0, B * sizeof(unsigned int), pf->stream) == cudaSuccess &&
               cudaMemcpyAsync(pf->obs_time_dev, model->h.obs_time.data(), (size_t)d.n_obs * sizeof(double),
                               cudaMemcpyHostToDevice, pf->stream) == cudaSuccess &&
               cudaMemcpyAsync(pf->obs_ysum_dev, model->h.obs_ysum.data(), (size_t)d.n_obs * sizeof(double),
@@ -269,6 +280,12 @@ int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t m) {
 int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t off) {
     if (!pf || off < 0 || off + pf->n_batch > 0xffffffffll) return fail(DPOMP_ERR_ARG, "batch_offset out of range");
     pf->batch_offset = off;
+    return DPOMP_OK;
+}
+int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on) {
+    if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
+    pf->fused_enabled = on != 0;
+    pf->fused_mode = on >= 2 ? 2 : 1;
     return DPOMP_OK;
 }
 int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n) {
@@ -352,6 +369,15 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
     CK(cudaMemsetAsync(pf->counters, 0, sizeof(unsigned long long), st));
     int launches = 0;
     pf->kev_kind.clear();
+    bool fused_ok = false;
+    if (pf->fused_enabled && pf->rs_type != DPOMP_RS_MULTINOMIAL) {
+        int& cap = pf->fused_capacity[pf->sim_precision == DPOMP_SIM_F64 ? 1 : 0];
+        if (cap < 0) cap = sim_fused_capacity(mh, pf->sim_precision, pf->items);
+        // measured on B200: with several tiles per filter the CTAs that wait for the combine hold SM slots and the fused
+        // launch loses to the two-kernel PDL chain (C2 4.25 vs 4.10 ms, SEIR 64 x 65536 18.8 vs 16.9 ms); with one tile per
+        // filter nothing waits and it wins slightly (1024 x 1024: 4.02 vs 4.10 ms).  fused_mode 2 forces it when it fits.
+        fused_ok = cap >= pf->ntiles && (pf->ntiles == 1 || pf->fused_mode == 2);
+    }
     for (int oi = ymin; oi <= ymax; ++oi) {
         const int t = oi - 1;
         const int has_lik = mh.obs_id[t] > 0;
@@ -374,11 +400,26 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
         a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
         a.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
+        // one fused launch (simulate + resample) when every tile of a filter can be resident at once
+        const bool fused = do_rs && fused_ok;
+        if (fused) {
+            a.do_resample = 1;
+            a.rs_type = pf->rs_type;
+            a.pop_dst = pf->pop[pf->cur ^ 1];
+            a.anc = pf->record_anc ? pf->anc : nullptr;
+            a.work_counter = pf->work_counter;
+            a.work_base = pf->work_base;
+            a.filt_gen = pf->filt_gen;
+            a.gen = ++pf->gen;
+            pf->work_base += (unsigned long long)nb * pf->ntiles;
+        }
         if (pf->kernel_timing) CK(kernel_event(pf, 0, st));
-        CK(launch_sim_weight(mh, pf->sim_precision, pf->items, a, st));
+        CK(launch_sim_weight(mh, pf->sim_precision, pf->items, fused ? 1 : 0, a, st));
         if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
         ++launches;
-        if (do_rs) {
+        if (fused) {
+            pf->cur ^= 1;
+        } else if (do_rs) {
             ResampleLaunch r{};
             r.pop_src = pf->pop[pf->cur]; r.pop_dst = pf->pop[pf->cur ^ 1];
             r.wtile = pf->wtile; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;

@@ -63,6 +63,15 @@ struct SimLaunch {
     int t;                   // 0-based observation index
     int fresh;               // 1: start from the initial condition at t_prev = 0 / theta[t0_index]
     int has_lik;             // obs_id[t] > 0
+    // fused step (simulate + resample in ONE launch; all tiles of a filter must be co-resident): see pf_sim.cuh
+    int do_resample;         // fused kernel only: resample after the combine
+    int rs_type;
+    int32_t* pop_dst;        // [B][C][n_pad] offspring populations
+    int32_t* anc;            // [B][n_pad] 0-based ancestors or nullptr
+    unsigned long long* work_counter;  // dynamic logical CTA index (arrival order) = atomicAdd(work_counter) - work_base
+    unsigned long long work_base;
+    unsigned int* filt_gen;  // [B] set to `gen` by the CTA that finished the filter's combine
+    unsigned int gen;
     uint64_t key;
     uint32_t filter0;        // global id of local filter 0
     const uint32_t* filter_ids;  // optional explicit global ids [n_filters] (overrides filter0 + b)
@@ -99,7 +108,9 @@ struct ModelHost {
 };
 
 // launchers implemented in the kernel TUs; all asynchronous on `stream`; return cudaGetLastError()
-cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, const SimLaunch& a, cudaStream_t stream);
+cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, int fused, const SimLaunch& a, cudaStream_t stream);
+// co-resident CTAs of the fused step kernel for this model / geometry on the current device (0 = unavailable)
+int sim_fused_capacity(const ModelHost& m, int sim_precision, int items);
 int builtin_model_id(const dpomp_model_desc& d);  // 0 = generic rate table, > 0 = hand-specialised predefined model
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream);
 cudaError_t launch_gather_filters(int32_t* dst, const int32_t* src, const int64_t* dst_slots_dev,

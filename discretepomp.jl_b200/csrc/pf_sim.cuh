@@ -17,6 +17,7 @@
 
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
+#include "pf_resample.cuh"
 
 namespace dpomp {
 
@@ -66,7 +67,12 @@ constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; 
 template <int N>
 struct alignas(4 * N) IntVec { int v[N]; };
 
-template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
+// FUSED: the same CTA also resamples its tile after the filter's combine (one launch per observation).  The CTA takes
+// its logical index from an arrival-order ticket, so every resident CTA has a lower index than any CTA not yet started;
+// the host only selects this variant when all tiles of a filter fit on the device at once, hence waiting for the
+// combine of the CTA's own filter cannot deadlock.  The tile's states and its scan stay in shared memory / registers
+// between the two phases: neither the states nor the scans of a resampling step go through HBM.
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, bool FUSED = false>
 __global__ void __launch_bounds__(kBlockThreads, sim_min_blocks<Real, C, E>())
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -83,11 +89,19 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     __shared__ uint32_t stream_s[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x % a.ntiles;
-    const int b = blockIdx.x / a.ntiles;
+    unsigned int logical = blockIdx.x;
+    if constexpr (FUSED) {
+        __shared__ unsigned int logical_s;
+        if (tid == 0) logical_s = (unsigned int)(atomicAdd(a.work_counter, 1ull) - a.work_base);
+        __syncthreads();
+        logical = logical_s;
+    }
+    const int tile = logical % a.ntiles;
+    const int b = logical / a.ntiles;
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double* th = a.theta + (size_t)b * m.n_params;
+    const bool resample_here = FUSED && a.do_resample;
 
     Real par[E];
 #pragma unroll
@@ -263,7 +277,8 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                 for (int kk = 0; kk < ITEMS; ++kk) v.v[kk] = (int)st_s[c * TILE + tid * ITEMS + kk];
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) xs[kk] += m.xmask_i[c] * v.v[kk];
-                *reinterpret_cast<Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS) = v;  // padding slots included
+                if (!resample_here)  // (fused + resampling: the pre-resampling states are never read from HBM again)
+                    *reinterpret_cast<Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS) = v;  // padding slots included
             }
         const Vec of = *reinterpret_cast<const Vec*>(ovf_s + tid * ITEMS);
 #pragma unroll
@@ -301,7 +316,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
     for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
     const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
-    {   // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs: cw = off_b + f_b * incl
+    if (!resample_here) {  // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs
         double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
         if constexpr (ITEMS % 2 == 0) {
 #pragma unroll
@@ -327,8 +342,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         flag_s = (ticket == (unsigned int)(grp_tiles - 1));
     }
     __syncthreads();
-    if (!flag_s || tid >= 32) return;
-
+    if (flag_s && tid < 32) {
     // level 1: tiles of this group -> f_{b|g}, o_{b|g}, (m_g, s_g)
     int last_group = 0;
     {
@@ -362,8 +376,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         }
         last_group = __shfl_sync(0xffffffffu, last_group, 31);
     }
-    if (!last_group) return;
-
+    if (last_group) {
     // level 2: groups of the filter -> M, F_g = exp(m_g - M), O_g, S and the log-likelihood increment
     const double* gm_b = a.grp_m + (size_t)b * a.ngroups;
     const double* gs_b = a.grp_s + (size_t)b * a.ngroups;
@@ -397,6 +410,29 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         // log(cum_weight[end] / N) (:60) as log-sum-exp; one add per kernel and filter, so the RED is deterministic
         if (a.has_lik) atomicAdd(&a.ll_acc[b], big_m + log(carry / (double)a.n));
         a.tile_counter[b] = 0u;
+    }
+    if constexpr (FUSED) {  // publish the combine to the CTAs of this filter that wait below
+        __syncwarp();
+        __threadfence();
+        if (tid == 0) atomicExch(&a.filt_gen[b], a.gen);
+    }
+    }  // last_group
+    }  // group-last warp
+
+    if constexpr (FUSED) {
+        if (!a.do_resample) return;
+        // ---- wait for this filter's combine, then resample the tile from shared memory ---------------------------------
+        if (tid == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(a.filt_gen + b) != a.gen) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+        __shared__ int warp_max_s[kBlockThreads / 32];
+        __shared__ long long lohi_s[2];
+        const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
+                        a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
+        // ovf_s (TILE ints) is free after the weight pass: it becomes the per-warp offspring windows
+        resample_tile<ITEMS, SState, true>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s, warp_max_s, lohi_s);
     }
 }
 
@@ -441,19 +477,32 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
     return m;
 }
 
+// mode 0: launch the plain kernel, 1: launch the fused kernel, 2: return the fused kernel's co-resident CTA capacity
 template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
-static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream) {
+static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream, int mode) {
     constexpr int TILE = kBlockThreads * ITEMS;
-    const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
     const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
-    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL>;
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, false>;
+    auto kern_fused = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, true>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(kern_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    return launch_pdl(kern, (unsigned)(a.n_filters * a.ntiles), kBlockThreads, smem, stream, m, a);
+    if (mode == 2) {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_fused, kBlockThreads, smem) != cudaSuccess) return 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return per_sm * sms;
+    }
+    const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
+    const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
+    return (int)(mode == 1 ? launch_pdl(kern_fused, grid, kBlockThreads, smem, stream, m, a)
+                           : launch_pdl(kern, grid, kBlockThreads, smem, stream, m, a));
 }
 
 // the instantiated generic (C, E) shapes; a model runs on the smallest shape that covers it
@@ -461,24 +510,24 @@ static cudaError_t launch_sim_inst(const ModelHost& mh, const SimLaunch& a, cuda
 #define DPOMP_SIM_BUILTINS(X) X(kModelSI) X(kModelSIR) X(kModelSIS) X(kModelSEI) X(kModelSEIR) X(kModelSEIS) X(kModelLOTKA)
 
 template <typename Real>
-static cudaError_t launch_sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStream_t stream) {
+static int sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStream_t stream, int mode) {
     const int c = mh.desc.n_compartments, e = mh.desc.n_events;
     const int model_id = builtin_model_id(mh.desc);
-#define X(ID)                                                                                                    \
-    if (model_id == ID) {                                                                                        \
-        return items == kItemsSmall ? launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID>(mh, a, stream)  \
-                                    : launch_sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream); \
+#define X(ID)                                                                                                             \
+    if (model_id == ID) {                                                                                                 \
+        return items == kItemsSmall ? sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID>(mh, a, stream, mode)   \
+                                    : sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream, mode);  \
     }
     DPOMP_SIM_BUILTINS(X)
 #undef X
-#define X(CC, EE)                                                                             \
-    if (c <= CC && e <= EE) {                                                                 \
-        return items == kItemsSmall ? launch_sim_inst<Real, CC, EE, kItemsSmall>(mh, a, stream)   \
-                                    : launch_sim_inst<Real, CC, EE, kItemsLarge>(mh, a, stream);  \
+#define X(CC, EE)                                                                                      \
+    if (c <= CC && e <= EE) {                                                                          \
+        return items == kItemsSmall ? sim_inst<Real, CC, EE, kItemsSmall>(mh, a, stream, mode)         \
+                                    : sim_inst<Real, CC, EE, kItemsLarge>(mh, a, stream, mode);        \
     }
     DPOMP_SIM_SHAPES(X)
 #undef X
-    return cudaErrorInvalidValue;
+    return mode == 2 ? 0 : (int)cudaErrorInvalidValue;
 }
 
 }  // namespace dpomp

@@ -2,7 +2,7 @@
 // draw-for-draw parity against the oracle.
 #include "pf_sim.cuh"
 namespace dpomp {
-cudaError_t launch_sim_f64(const ModelHost& m, int items, const SimLaunch& a, cudaStream_t stream) {
-    return launch_sim_typed<double>(m, items, a, stream);
+int sim_f64(const ModelHost& m, int items, const SimLaunch& a, cudaStream_t stream, int mode) {
+    return sim_typed<double>(m, items, a, stream, mode);
 }
 }  // namespace dpomp

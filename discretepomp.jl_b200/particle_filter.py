@@ -113,6 +113,12 @@ class ParticleFilter:
     def set_batch_offset(self, off: int) -> None:
         _capi.check(_capi.lib().dpomp_pf_set_batch_offset(self._h, int(off)))
 
+    def set_fused(self, mode) -> None:
+        """Fused simulate+resample launch per observation: 0/False never, 1 (default) for one-tile filters, 2/True
+        whenever all tiles of a filter fit on the device at once."""
+        mode = 2 if mode is True else int(mode)
+        _capi.check(_capi.lib().dpomp_pf_set_fused(self._h, mode))
+
     def set_filter_ids(self, ids) -> None:
         """Explicit 0-based GLOBAL ids of the first len(ids) filters (random-stream keying); None resets."""
         if ids is None:

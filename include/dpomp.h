@@ -118,6 +118,8 @@ int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t max_events);        /* per par
                                                                          reference PF has no cap (src/hmm_particle_filter.jl:19-27) */
 int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t batch_offset);    /* global id of local filter 0 (0): makes the
                                                                          random streams independent of the sharding  */
+int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on);                     /* fused simulate+resample launch per observation: 0 never, (1) for
+                                                                         filters of one tile, 2 whenever all tiles of a filter are co-resident */
 int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n); /* explicit 0-based GLOBAL ids of the first n
                                                                          filters for the random streams; NULL = batch_offset + b */
 int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key);              /* force the Philox key of the NEXT call (tests) */

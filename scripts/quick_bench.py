@@ -14,6 +14,7 @@ model = dp.generate_model(mname, ic)
 y = dp.get_observations(f"tests/golden/{case if case != 'pooley' else 'pooley'}.csv")
 dm = dp.device_model(dp.get_private_model(model, y))
 pf = dp.ParticleFilter(dm, n, nb, 1, seed=1)
+if os.environ.get("FUSED") is not None: pf.set_fused(os.environ["FUSED"] == "1")
 th = torch.tensor(np.tile(np.asarray(theta)[None, :], (nb, 1)), dtype=torch.float64, device="cuda")
 out = torch.zeros(nb, dtype=torch.float64, device="cuda")
 for _ in range(3): pf.loglik_device(th.data_ptr(), nb, out.data_ptr())

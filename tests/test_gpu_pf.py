@@ -280,3 +280,24 @@ def test_degenerate_weights_collapse_to_few_ancestors(dp, orc):
     anc = pf.last_ancestors()
     assert np.array_equal(anc, o[2]) and np.array_equal(pf.get_pop(1), o[5]) and abs(ll - o[0]) < 1e-9
     assert len(np.unique(anc)) < n // 20  # heavy collapse
+
+
+@pytest.mark.parametrize("case,n,nb,f64", [("sir_c2", 3000, 3, True), ("sir_c2", 200, 5, False), ("seir_c3", 70000, 2, False),
+                                            ("lotka_c4", 1024, 4, False), ("sis_pooley", 1 << 18, 1, False)])
+@pytest.mark.parametrize("rs_type", [1, 2])
+def test_fused_step_kernel_equals_two_kernel_path(dp, case, n, nb, f64, rs_type):
+    """The fused simulate+resample launch and the two-kernel path are the same computation: bit-identical log-likelihoods,
+    populations and ancestors (f32 and f64 loops, ragged tiles, several filters)."""
+    model, y, hmm, theta = load_case(dp, case)
+    thetas = theta[:, None] * np.linspace(0.9, 1.1, nb)[None, :]
+    out = []
+    for fused in (True, False):
+        pf = _pf(dp, hmm, n, nb, rs=rs_type, f64=f64, seed=4)
+        pf.set_fused(fused)
+        pf.set_stream_key(555)
+        ll = pf.partial(thetas, 1, min(len(y), 6))
+        out.append((ll, [pf.get_pop(b + 1) for b in range(nb)], pf.last_ancestors(nb), pf.last_timing()[1]))
+    (ll_a, pops_a, anc_a, launches_a), (ll_b, pops_b, anc_b, launches_b) = out
+    assert np.array_equal(ll_a, ll_b) and np.array_equal(anc_a, anc_b)
+    assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
+    assert launches_a < launches_b  # one launch per resampling observation instead of two
