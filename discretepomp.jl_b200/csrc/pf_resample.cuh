@@ -54,7 +54,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 
     // tile seams: the offset of a tile is its cw at incl = 0
     if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
-    if (tid == 32) {
+    if (tid == kBlockThreads / 2) {
         long long hi_b = a.n;
         if (tile != a.ntiles - 1) {
             const int g2 = (tile + 1) / kGroupTiles;
