@@ -25,4 +25,5 @@ from .distributed import Comm, migration_plan, partition_bounds, partition_owner
 from .ibis import (compute_is_mu_covar, get_mv_param, get_prop_density, run_ibis_analysis, run_pibis)
 from .mcmc import gelman_diagnostic_sre, handle_rej_samples, run_pmcmc, run_pmcmc_analysis
 from .mbp_ibis import MbpParticles, run_mbp_ibis
+from .sim import generate_observations, gillespie_sim
 from . import _capi

@@ -636,22 +636,36 @@ int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double*
     std::vector<double> cw(w, w + n);
     if (!on_cumulative)  // cumsum / cumsum! (src/hmm_resample.jl:5,45,67): sequential f64, bit-exact by construction
         for (int64_t i = 1; i < n; ++i) cw[(size_t)i] = cw[(size_t)i - 1] + cw[(size_t)i];
-    double *cw_d = nullptr, *u_d = nullptr;
-    int64_t* out_d = nullptr;
-    CK(cudaMalloc((void**)&cw_d, (size_t)n * sizeof(double)));
-    cudaError_t e1 = cudaMalloc((void**)&u_d, (size_t)need_u * sizeof(double));
-    cudaError_t e2 = cudaMalloc((void**)&out_d, (size_t)n_out * sizeof(int64_t));
-    int rc = DPOMP_OK;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(DPOMP_ERR_CUDA, "cudaMalloc failed in dpomp_resample_indices");
-    if (!rc) {
-        cudaError_t s = cudaMemcpy(cw_d, cw.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
-        if (s == cudaSuccess) s = cudaMemcpy(u_d, u, (size_t)need_u * sizeof(double), cudaMemcpyHostToDevice);
-        if (s == cudaSuccess) s = launch_search_hook(rs_type, cw_d, n, u_d, n_out, out_d, 0);
-        if (s == cudaSuccess) s = cudaMemcpy(out_idx, out_d, (size_t)n_out * sizeof(int64_t), cudaMemcpyDeviceToHost);
-        if (s != cudaSuccess) rc = fail(DPOMP_ERR_CUDA, std::string("dpomp_resample_indices: ") + cudaGetErrorString(s));
-    }
-    cudaFree(cw_d); cudaFree(u_d); cudaFree(out_d);
-    return rc;
+    // persistent per-device workspace (grown on demand): the outer layers call this once per resampling step
+    struct HookWs {
+        double* cw = nullptr; double* u = nullptr; int64_t* out = nullptr;
+        size_t cap_cw = 0, cap_u = 0, cap_out = 0;
+        cudaStream_t stream = nullptr;
+    };
+    static thread_local HookWs ws_all[64];
+    int dev = device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= 64) return fail(DPOMP_ERR_ARG, "device index out of range");
+    HookWs& ws = ws_all[dev];
+    if (!ws.stream) CK(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+    auto grow = [](void** ptr, size_t* cap, size_t need, size_t elem) -> cudaError_t {
+        if (need <= *cap) return cudaSuccess;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr; *cap = 0;
+        const size_t want = need + need / 2 + 1024;
+        cudaError_t e2 = cudaMalloc(ptr, want * elem);
+        if (e2 == cudaSuccess) *cap = want;
+        return e2;
+    };
+    CK(grow((void**)&ws.cw, &ws.cap_cw, (size_t)n, sizeof(double)));
+    CK(grow((void**)&ws.u, &ws.cap_u, (size_t)need_u, sizeof(double)));
+    CK(grow((void**)&ws.out, &ws.cap_out, (size_t)n_out, sizeof(int64_t)));
+    CK(cudaMemcpyAsync(ws.cw, cw.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ws.stream));
+    CK(cudaMemcpyAsync(ws.u, u, (size_t)need_u * sizeof(double), cudaMemcpyHostToDevice, ws.stream));
+    CK(launch_search_hook(rs_type, ws.cw, n, ws.u, n_out, ws.out, ws.stream));
+    CK(cudaMemcpyAsync(out_idx, ws.out, (size_t)n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, ws.stream));
+    CK(cudaStreamSynchronize(ws.stream));
+    return DPOMP_OK;
 }
 
 }  // extern "C"

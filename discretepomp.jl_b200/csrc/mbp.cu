@@ -542,6 +542,16 @@ int dpomp_mbp_import(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets,
     return mbp_pack(h, slots, offsets, n, const_cast<void*>(dev_fixed), const_cast<void*>(dev_times), const_cast<void*>(dev_types), 1);
 }
 
+int dpomp_mbp_get_states(dpomp_mbp* h, int32_t n, int64_t* out) {
+    if (!h || !out) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    if (n < 1 || n > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "n out of range");
+    MCK(cudaSetDevice(h->device));
+    std::vector<int> tmp((size_t)n * h->dm.n_comp);
+    MCK(cudaMemcpy(tmp.data(), h->store[h->cur].fc, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
+    return DPOMP_OK;
+}
+
 int dpomp_mbp_get_particle(dpomp_mbp* h, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times, int32_t* types,
                            int64_t cap_out, double* loglike2) {
     if (!h || !fc || !len || !loglike2) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");

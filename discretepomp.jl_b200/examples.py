@@ -46,6 +46,12 @@ class UniformProduct:
             return -np.inf
         return float(-np.sum(np.log(self.upper - self.lower)))
 
+    def logpdf_batch(self, theta: np.ndarray) -> np.ndarray:
+        """logpdf of every column of an (n_theta, n) matrix (vectorised; same values as logpdf)."""
+        theta = np.asarray(theta, dtype=np.float64)
+        inside = np.all((theta >= self.lower[:, None]) & (theta <= self.upper[:, None]), axis=0)
+        return np.where(inside, float(-np.sum(np.log(self.upper - self.lower))), -np.inf)
+
     def rand(self, n: int = 1, rng: Optional[np.random.Generator] = None) -> np.ndarray:
         """rand(prior, n) -> (n_theta, n) like Julia."""
         rng = rng or np.random.default_rng()

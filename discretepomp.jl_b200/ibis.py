@@ -44,6 +44,14 @@ C_DF_MBPI_MUT = 3
 C_ACCEPTANCE_ALPHA = 1.002  # src/DiscretePOMP.jl:43
 
 
+def prior_logpdf_columns(prior, theta: np.ndarray) -> np.ndarray:
+    """logpdf(prior, theta[:, i]) for every column (src/hmm_ibis.jl:22-24, :88); vectorised when the prior offers it."""
+    batch = getattr(prior, "logpdf_batch", None)
+    if batch is not None:
+        return np.asarray(batch(theta), dtype=np.float64)
+    return np.array([prior.logpdf(theta[:, i]) for i in range(theta.shape[1])], dtype=np.float64)
+
+
 def compute_is_mu_covar(theta: np.ndarray, w: np.ndarray):
     """compute_is_mu_covar! (src/cmn.jl:91-99): weighted mean and (biased) covariance; theta is (n_theta, n)."""
     sw = np.sum(w)
@@ -174,7 +182,7 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
     start_time = time.time_ns()
     ess_crit = ess_rs_crit * outer_p
     w = np.ones(outer_p)
-    aw = np.array([model.prior.logpdf(theta[:, i]) for i in range(outer_p)])
+    aw = prior_logpdf_columns(model.prior, theta)
     bank = FilterBank(model, outer_p, np_, comm, seed, pf_factory)
     k_log = np.zeros(2, dtype=np.int64)
     bme = np.zeros(2)
@@ -205,7 +213,7 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
                         theta_f = mu[:, None] + propd.rand(rng, outer_p)
                     else:
                         theta_f = get_mv_param(propd, tj, theta, rng)
-                    prtf = np.array([model.prior.logpdf(theta_f[:, p]) for p in range(outer_p)])
+                    prtf = prior_logpdf_columns(model.prior, theta_f)
                     valid = prtf != -np.inf
                     aw_f, gx_f = bank.propose(theta_f, valid, obs_i)
                     aw_f = aw_f + np.where(valid, prtf, 0.0)

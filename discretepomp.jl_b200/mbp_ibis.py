@@ -23,7 +23,8 @@ import numpy as np
 
 from . import _capi
 from .distributed import Comm
-from .ibis import (_M64, ProposalDensity, compute_is_mu_covar, get_mv_param, get_prop_density, splitmix64)
+from .ibis import (_M64, ProposalDensity, compute_is_mu_covar, get_mv_param, get_prop_density, prior_logpdf_columns,
+                   splitmix64)
 from .particle_filter import compute_ess, device_model
 from .resample import rs_systematic
 from .structs import HiddenMarkovModel, ImportanceSample
@@ -116,6 +117,12 @@ class MbpParticles:
             _capi.check(_capi.lib().dpomp_mbp_import(self._h, _capi.ptr(s), _capi.ptr(o), len(s), C.c_void_p(fixed.data_ptr()),
                                                      C.c_void_p(times.data_ptr()), C.c_void_p(types.data_ptr())))
 
+    def final_conditions(self) -> np.ndarray:
+        """(n, C) final states of all particles."""
+        out = np.zeros((self.n, self.n_comp), dtype=np.int64)
+        _capi.check(_capi.lib().dpomp_mbp_get_states(self._h, self.n, _capi.ptr(out)))
+        return out
+
     def get_particle(self, p: int, proposal: bool = False):
         """(final_condition, times, types(1-based), log_like[2]) of particle p (1-based)."""
         fc = np.zeros(self.n_comp, dtype=np.int64); ln = C.c_int64()
@@ -172,7 +179,7 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
         if n_loc:
             ptcls.permute(local_src + 1)
         ptcls.import_particles(recv_slots + 1, recv_lens, r_fixed, r_times, r_types)
-    prior = np.array([model.prior.logpdf(theta[:, p]) for p in range(outer_p)])  # Particle.prior (:153)
+    prior = prior_logpdf_columns(model.prior, theta)  # Particle.prior (:153)
     log_like = np.zeros(outer_p)  # Particle.log_like[1], mirrored on the host for the acceptance ratio
     propd = ProposalDensity.identity(d)
     tj = 0.2
@@ -207,7 +214,7 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                 k_log[0] += outer_p * n_props
                 for _ in range(n_props):  # :203-219, one sweep over all particles
                     theta_f = (mu[:, None] + propd.rand(rng, outer_p)) if ind_prop else get_mv_param(propd, tj, theta, rng)
-                    prior_f = np.array([model.prior.logpdf(theta_f[:, p]) for p in range(outer_p)])
+                    prior_f = prior_logpdf_columns(model.prior, theta_f)
                     valid = prior_f != -np.inf
                     ptcls.set_stream_key(next_key())
                     ll_f = gather(ptcls.propose(theta[:, lo:hi], theta_f[:, lo:hi], valid[lo:hi], obs_i)

@@ -207,6 +207,8 @@ int dpomp_mbp_export(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offset
                      void* dev_times, void* dev_types);
 int dpomp_mbp_import(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
                      const void* dev_times, const void* dev_types);
+/* final states of particles 1..n, row-major n x C */
+int dpomp_mbp_get_states(dpomp_mbp* mbp, int32_t n, int64_t* out);
 /* read back one particle (which: 0 current, 1 proposal): final state, event list (types 1-based), log_like[2] */
 int dpomp_mbp_get_particle(dpomp_mbp* mbp, int32_t p, int32_t which, int64_t* fc, int64_t* len, double* times,
                            int32_t* types, int64_t cap_out, double* loglike2);

@@ -171,3 +171,30 @@ def test_mbp_ibis_two_ranks_equal_one_rank_bitwise(tmp_path):
     a, b = np.load(one), np.load(two)
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_gillespie_sim_entry_point(dp, orc):
+    """gillespie_sim(model, theta; tmax, num_obs, n_sims) (src/DiscretePOMP.jl:134-152): result structs, consistency of the
+    recorded trajectory with the observed states, and the law of the final state against the oracle's simulator."""
+    model = dp.generate_model("SIS", [100, 1])
+    theta = np.array([0.003, 0.1])
+    x = dp.gillespie_sim(model, theta, verbose=False)  # reference test: test/runtests.jl:22-26
+    assert isinstance(x, dp.SimResults) and len(x.observations) == 5 and [o.time for o in x.observations] == [20.0, 40.0, 60.0, 80.0, 100.0]
+    assert len(x.population) == len(x.particle.trajectory) and np.all(np.diff([e.time for e in x.particle.trajectory]) >= 0)
+    if x.population:
+        assert np.array_equal(x.population[-1], x.particle.final_condition) and x.population[-1].sum() == 101
+    assert np.array_equal(x.observations[-1].val, x.particle.final_condition)  # dmy_obs_fn: y.val .= population
+    # state at each observation time = initial condition + transitions of the events up to that time
+    tm = model.m_transition
+    for o in x.observations:
+        k = sum(e.time <= o.time for e in x.particle.trajectory)
+        st = model.initial_condition + sum((tm[e.event_type - 1] for e in x.particle.trajectory[:k]), np.zeros(2, dtype=np.int64))
+        assert np.array_equal(o.val, st)
+    sims = dp.gillespie_sim(model, theta, n_sims=2000, seed=5, verbose=False)
+    gpu_final = np.array([s.particle.final_condition[1] for s in sims], dtype=float)
+    y = [dp.Observation(20.0 * (i + 1), 1, 1.0, [0, 0]) for i in range(5)]
+    cm = dp.compile_model(model, y)
+    ref_final = np.array([orc.gillespie_sim(cm.desc, theta, key=900 + i)[0][-1, 1] for i in range(2000)], dtype=float)
+    # mixture of early extinctions (I = 0) and the endemic state (I ~ 67): compare extinction rate and endemic mean
+    assert abs((gpu_final == 0).mean() - (ref_final == 0).mean()) < 0.05
+    assert abs(gpu_final[gpu_final > 0].mean() - ref_final[ref_final > 0].mean()) < 1.0
