@@ -88,6 +88,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two PF kernels from the committed
+    `ncu --set full` capture of this command (profiles/r1_ncu_full_metrics.csv); None when the file is missing."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_metrics.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        rows = {r[0]: r for r in csv.reader(open(path)) if r}
+        names = rows["Kernel Name"][2:]
+        out = {}
+        for key in ("pf_sim_weight_kernel", "pf_resample_kernel"):
+            cols = [i for i, n in enumerate(names) if key in n]
+            tot = 0.0
+            for metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                r = rows[metric]
+                tot += sum(float(r[2 + i].replace(",", "")) for i in cols) / max(len(cols), 1) * scale.get(r[1], 1.0)
+            out[key] = tot if cols else None
+        return out
+    except Exception:
+        return {}
+
+
 def cpu_baseline(dp, model, y, theta, n_particles: int, threads: int):
     """The oracle port (kind 'port': Julia is not installed, the reference itself cannot run) on the host cores."""
     from oracle import oracle as orc
@@ -311,12 +334,13 @@ def main():
         # search R8 W4, gather R 4+4C W 4C)
         alg = {"pf_sim_weight_kernel": 8 * C + 8, "pf_resample_kernel": 8 * C + 40}
         names = ["pf_sim_weight_kernel", "pf_resample_kernel"]
+        traffic = ncu_traffic()
         kernels = {}
         for i, nm in enumerate(names):
             if k_n[i]:
                 avg_ms = k_ms[i] / k_n[i]
                 ach = alg[nm] * N_PARTICLES / (avg_ms * 1e-3) / 1e9
-                kernels[nm] = {"avg_launch_us": 1e3 * avg_ms, "launches_per_step": int(k_n[i] // roof_steps),
+                kernels[nm] = {"ncu_dram_bytes_per_launch": traffic.get(nm), "avg_launch_us": 1e3 * avg_ms, "launches_per_step": int(k_n[i] // roof_steps),
                                "share_of_kernel_time": float(k_ms[i] / k_ms.sum()), "alg_bytes_per_particle": alg[nm],
                                "achieved_gbs": ach, "frac_of_hbm_peak": ach / hbm_peak}
         dom = max(kernels, key=lambda k: kernels[k]["share_of_kernel_time"])
@@ -337,7 +361,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic.get(dom), "peak_source": peak_src,
+                         "traffic_source": "profiles/r1_ncu_full_metrics.csv (ncu --set full of this command; bytes per launch; the 33 MB working set is L2 resident)",
                          "note": "the simulate kernel is instruction-issue bound, not HBM bound (DESIGN.md); frac is its HBM-roofline fraction"},
             "roofline_kernels": kernels,
             "roofline_pipeline": {"alg_bytes_per_step": 16 * C + 48, "achieved_gbs": (16 * C + 48) * value / world / 1e9,
