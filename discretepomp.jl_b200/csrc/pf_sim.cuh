@@ -333,16 +333,17 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     // the serial tail of the kernel.
     const int grp = tile / kGroupTiles;
     const int grp_tiles = min(kGroupTiles, a.ntiles - grp * kGroupTiles);
-    __shared__ int flag_s;
+    // Only warp 0 stays for the tickets; in the two-kernel path the other warps are done (no block barrier on the tail).
+    int grp_last = 0;
     if (tid == 0) {
         a.tile_m[(size_t)b * a.ntiles + tile] = m_b;
         a.tile_s[(size_t)b * a.ntiles + tile] = s_b;
         __threadfence();
         const unsigned int ticket = atomicAdd(&a.grp_counter[(size_t)b * a.ngroups + grp], 1u);
-        flag_s = (ticket == (unsigned int)(grp_tiles - 1));
+        grp_last = (ticket == (unsigned int)(grp_tiles - 1));
     }
-    __syncthreads();
-    if (flag_s && tid < 32) {
+    if (tid < 32) grp_last = __shfl_sync(0xffffffffu, grp_last, 0);
+    if (grp_last && tid < 32) {
     // level 1: tiles of this group -> f_{b|g}, o_{b|g}, (m_g, s_g)
     int last_group = 0;
     {
