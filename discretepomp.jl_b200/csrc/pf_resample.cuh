@@ -42,6 +42,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     constexpr int CHUNK = 32 * ITEMS;
     constexpr int NW = kBlockThreads / 32;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kHeavyFactor = 8;  // offspring / ancestors of a tile above which the CTA-wide path is used
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base_n = (long long)tile * TILE;
     const double big_s = ld_combine<double, CG>(a.filt_s + b);
@@ -106,6 +107,25 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
 
     int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
+    // Heavy tile (weight collapse: this tile feeds far more offspring than it has ancestors): per-warp windows would leave
+    // the warp that owns the heavy ancestors looping alone, so the whole CTA walks the tile's offspring range instead and
+    // finds each ancestor by binary search over the running maxima (block-uniform decision: lo and hi are shared).
+    if (hi - lo > (long long)kHeavyFactor * TILE) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) am_all[tid * ITEMS + k] = emax[k];
+        __syncthreads();
+        const int total = (int)(hi - lo);
+        for (int o = 1 + tid; o <= total; o += kBlockThreads) {  // 1-based offset in the tile's offspring range
+            int lq = 0, hq = TILE - 1;                             // first q with emax_q >= o (emax of the last items = total)
+            while (lq < hq) {
+                const int mid = (lq + hq) >> 1;
+                if (am_all[mid] >= o) hq = mid; else lq = mid + 1;
+            }
+            for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + o - 1] = (int)st_tile[(size_t)c * stride + lq];
+            if (a.anc) a.anc[(size_t)b * a.n_pad + lo + o - 1] = (int32_t)(base_n + lq);
+        }
+        return;
+    }
     int* am_w = am_all + warp * CHUNK;
     for (int wlo = wfirst; wlo < wlast; wlo += CHUNK) {
 #pragma unroll
