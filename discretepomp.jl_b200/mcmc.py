@@ -74,9 +74,11 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
     c = np.full(n_loc, C_INITIAL)
     accepted_total = np.zeros(n_loc, dtype=np.int64)
 
+    from .ibis import prior_logpdf_columns
+
     def target(thetas: np.ndarray, step: int) -> np.ndarray:
         """model prior + estimate_likelihood(model, theta, p, ps, rsp_systematic) for each local chain (:356-358)."""
-        lp = np.array([model.prior.logpdf(thetas[k]) for k in range(n_loc)])
+        lp = prior_logpdf_columns(model.prior, thetas.T)
         valid = np.nonzero(lp != -np.inf)[0]
         out = np.full(n_loc, -np.inf)
         if len(valid):
@@ -88,24 +90,21 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
     chains[:, 0, :] = theta_init[:, lo:hi].T
     ll_i = target(chains[:, 0, :], 0)
     for i in range(1, steps):
-        prop = np.empty((n_loc, d))
-        for k in range(n_loc):
-            prop[k] = chains[k, i - 1] + c[k] * (chol[k] @ rngs[k].standard_normal(d))  # get_mv_param(propd, c, ...) (:181)
+        # get_mv_param(propd, c, theta[mc, i-1, :]) (:181) for every chain (each chain keeps its own random stream)
+        z = np.stack([rngs[k].standard_normal(d) for k in range(n_loc)]) if n_loc else np.zeros((0, d))
+        prop = chains[:, i - 1, :] + c[:, None] * np.einsum("kij,kj->ki", chol, z)
         ll_f = target(prop, i)
-        for k in range(n_loc):
-            ok = False
-            if ll_f[k] != -np.inf:
-                mh = np.exp(min(ll_f[k] - ll_i[k], 700.0))
-                ok = bool(mh > 1 or mh > rngs[k].random())  # :189-190
-            if ok:
-                ll_i[k] = ll_f[k]
-                chains[k, i] = prop[k]
-                accepted_total[k] += 1
-            else:
-                chains[k, i] = chains[k, i - 1]
-            if i + 1 < adapt_period:  # Julia's 1-based step index is i + 1 (:198)
-                c[k] *= 1.002 if ok else 0.999
-                if (i + 1) % adapt_interval == 0:
+        u = np.array([rngs[k].random() for k in range(n_loc)])
+        with np.errstate(over="ignore", invalid="ignore"):
+            mh = np.exp(np.minimum(ll_f - ll_i, 700.0))
+        ok = (ll_f != -np.inf) & ((mh > 1) | (mh > u))  # :189-190
+        ll_i = np.where(ok, ll_f, ll_i)
+        chains[:, i, :] = np.where(ok[:, None], prop, chains[:, i - 1, :])
+        accepted_total += ok
+        if i + 1 < adapt_period:  # Julia's 1-based step index is i + 1 (:198)
+            c *= np.where(ok, 1.002, 0.999)
+            if (i + 1) % adapt_interval == 0:
+                for k in range(n_loc):
                     covar = np.atleast_2d(np.cov(chains[k, : i + 1].T))
                     if covar.sum() == 0:
                         if verbose:
