@@ -125,9 +125,10 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 //   P_w   = W_0 + ... + W_{w-1}      (left to right over warps, W_w = I_31 of warp w)
 //   incl_k = (P_w + I_{l-1}) + r_k ,  excl_k = (P_w + I_{l-1}) + r_{k-1}
 // Returns the tile total P_{nw-1} + W_{nw-1}.  All adds are round-to-nearest f64, never contracted.
-// `warp_tot` is shared scratch of kBlockThreads/32 doubles.  Contains two __syncthreads().
+// `warp_tot` is shared scratch of kBlockThreads/32 doubles.  Contains two __syncthreads(); the trailing one (TAIL_SYNC)
+// only protects `warp_tot` against reuse and may be dropped when nothing writes the scratch afterwards.
 // ------------------------------------------------------------------------------------------------------------
-template <int ITEMS>
+template <int ITEMS, bool TAIL_SYNC = true>
 __device__ __forceinline__ double tile_scan(const double (&a)[ITEMS], double (&incl)[ITEMS], double (&excl)[ITEMS],
                                             double* warp_tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -157,7 +158,7 @@ __device__ __forceinline__ double tile_scan(const double (&a)[ITEMS], double (&i
         incl[k] = __dadd_rn(base, r[k]);
         excl[k] = __dadd_rn(base, k > 0 ? r[k - 1] : 0.0);
     }
-    __syncthreads();
+    if constexpr (TAIL_SYNC) __syncthreads();
     return total;
 }
 

@@ -67,6 +67,63 @@ constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; 
 template <int N>
 struct alignas(4 * N) IntVec { int v[N]; };
 
+// rate_function + cumsum! (src/hmm_particle_filter.jl:20-21): cumulative event rates of state x
+template <typename Real, int C, int E, int MODEL>
+__device__ __forceinline__ void cum_rates(const DevModel<Real, C, E>& m, const Real (&par)[E], const Real (&x)[C], Real (&cum)[E]) {
+    if constexpr (MODEL != kModelGeneric) {
+        using BM = Builtin<MODEL>;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            Real rate = Arith<Real>::mul(par[e], x[BM::A(e)]);
+            if (BM::B(e) >= 0) rate = Arith<Real>::mul(rate, x[BM::B(e) >= 0 ? BM::B(e) : 0]);
+            cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            Real l1 = m.k1[e], l2 = m.k2[e];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                l1 += m.f1[e][c] * x[c];
+                l2 += m.f2[e][c] * x[c];
+            }
+            Real rate = Arith<Real>::mul(Arith<Real>::mul(par[e], l1), l2);
+            if (m.any_den && m.has_den[e]) {
+                Real dn = m.kd[e];
+#pragma unroll
+                for (int c = 0; c < C; ++c) dn += m.dn[e][c] * x[c];
+                rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
+            }
+            cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+        }
+    }
+}
+
+// choose_event (src/hmm_cmn.jl:4-10): transition row of the first event i < E with cum[i] > etc, else of event E
+template <typename Real, int C, int E, int MODEL>
+__device__ __forceinline__ void chosen_transition(const DevModel<Real, C, E>& m, const Real (&cum)[E], Real etc, Real (&dx)[C]) {
+    if constexpr (MODEL != kModelGeneric) {
+        using BM = Builtin<MODEL>;
+#pragma unroll
+        for (int c = 0; c < C; ++c) dx[c] = (Real)BM::T(E - 1, c);
+#pragma unroll
+        for (int i = E - 2; i >= 0; --i) {
+            const bool hit = cum[i] > etc;
+#pragma unroll
+            for (int c = 0; c < C; ++c) dx[c] = hit ? (Real)BM::T(i, c) : dx[c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
+#pragma unroll
+        for (int i = E - 2; i >= 0; --i) {
+            const bool hit = cum[i] > etc;
+#pragma unroll
+            for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
+        }
+    }
+}
+
 // FUSED: the same CTA also resamples its tile after the filter's combine (one launch per observation).  The CTA takes
 // its logical index from an arrival-order ticket, so every resident CTA has a lower index than any CTA not yet started;
 // the host only selects this variant when all tiles of a filter fit on the device at once, hence waiting for the
@@ -86,6 +143,8 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     int* ovf_s = reinterpret_cast<int*>(smem_raw);        // [TILE] 1 = the particle hit the event cap
     SState* st_s = reinterpret_cast<SState*>(ovf_s + TILE);  // [C][TILE]
     __shared__ double warp_scratch[kBlockThreads / 32];
+    __shared__ unsigned warp_min_s[kBlockThreads / 32];
+    __shared__ double wtab_s[kBlockThreads];  // exp(logw(d_min + j) - m_b), j = 0..kBlockThreads-1
     __shared__ uint32_t stream_s[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -125,14 +184,23 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         for (int kk = 0; kk < ITEMS; ++kk) z.v[kk] = 0;
         *reinterpret_cast<Vec*>(ovf_s + tid * ITEMS) = z;
     }
+    // compartments present: a compile-time constant for the predefined models
+    const int n_comp = (MODEL != kModelGeneric) ? C : a.n_comp;
     if (!a.fresh) {
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (c < a.n_comp)
+            if (c < n_comp)
             {
                 const Vec v = *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) st_s[c * TILE + tid * ITEMS + kk] = (SState)v.v[kk];
+            }
+    } else {  // fn_initial_condition() rows (src/hmm_particle_filter.jl:44-46): the work queue always refills from shared memory
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (c < n_comp) {
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) st_s[c * TILE + tid * ITEMS + kk] = (SState)m.ic[c];
             }
     }
     __syncthreads();
@@ -152,41 +220,35 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     uint32_t k = 0;
     unsigned long long ev_local = 0, ovf_local = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-        x[c] = (active && c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
+    for (int c = 0; c < C; ++c) x[c] = (c < n_comp) ? (Real)st_s[c * TILE + q] : (Real)0;  // idle lanes: harmless values
 
     while (__any_sync(FULL, active)) {
         bool fin = false, ovf = false;
-        if (active) {
-            // rate_function + cumsum! (src/hmm_particle_filter.jl:20-21)
+        if constexpr (kF32) {
+            // One attempt for every lane, branch free: an absorbed state (`cum_rates[end] == 0.0 && break`, :22) makes the
+            // waiting time -inf / NaN, so `tmn >= 0` is false; the event cap is folded into the same predicate.
             Real cum[E];
-            if constexpr (MODEL != kModelGeneric) {
-                using BM = Builtin<MODEL>;
+            cum_rates<Real, C, E, MODEL>(m, par, x, cum);
+            const Real rtot = cum[E - 1];
+            const uint2 w = philox2x32_10((uint32_t)(base_n + q) ^ ss.a, k ^ ss.b, ss.k);
+            // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
+            const Real tmn = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm);
+            const bool capped = k >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
+            const bool go = (rtot > (Real)0) && !capped && (tmn >= (Real)0);  // `time > tmax && break` (:24)
+            Real dx[C];
+            chosen_transition<Real, C, E, MODEL>(m, cum, u32_open_f32(w.y) * rtot, dx);  // choose_event + fn_transition (:25-26)
+            if (go) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    Real rate = Arith<Real>::mul(par[e], x[BM::A(e)]);
-                    if (BM::B(e) >= 0) rate = Arith<Real>::mul(rate, x[BM::B(e) >= 0 ? BM::B(e) : 0]);
-                    cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
-                }
-            } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                Real l1 = m.k1[e], l2 = m.k2[e];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    l1 += m.f1[e][c] * x[c];
-                    l2 += m.f2[e][c] * x[c];
-                }
-                Real rate = Arith<Real>::mul(Arith<Real>::mul(par[e], l1), l2);
-                if (m.any_den && m.has_den[e]) {
-                    Real dn = m.kd[e];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) dn += m.dn[e][c] * x[c];
-                    rate = (dn == (Real)0) ? (Real)0 : Arith<Real>::div(rate, dn);
-                }
-                cum[e] = (e == 0) ? rate : Arith<Real>::add(cum[e - 1], rate);
+                for (int c = 0; c < C; ++c) x[c] += dx[c];
+                ++k;
+                tm = tmn;
             }
-            }
+            fin = active && !go;
+            ovf = capped && (rtot > (Real)0);
+        } else {
+        if (active) {
+            Real cum[E];
+            cum_rates<Real, C, E, MODEL>(m, par, x, cum);
             const Real rtot = cum[E - 1];
             fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
             if (!fin) {
@@ -195,40 +257,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     ovf = true;
                 } else {
                     const uint2 w = philox2x32_10((uint32_t)(base_n + q) ^ ss.a, k ^ ss.b, ss.k);
-                    Real etc;
-                    if constexpr (kF32) {
-                        // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
-                        tm = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm);
-                        fin = tm < 0.0f;  // `time > tmax && break` (:24)
-                        etc = u32_open_f32(w.y) * rtot;
-                    } else {
-                        tm = tm - log(u32_open_f64(w.x)) / rtot;
-                        fin = tm > t_obs;
-                        etc = __dmul_rn(u32_open_f64(w.y), rtot);
-                    }
+                    tm = tm - log(u32_open_f64(w.x)) / rtot;  // time -= log(rand()) / R (:23)
+                    fin = tm > t_obs;                          // `time > tmax && break` (:24)
                     if (!fin) {
-                        // choose_event (src/hmm_cmn.jl:4-10) + `ptemp .+= fn_transition(et)` (:26)
                         Real dx[C];
-                        if constexpr (MODEL != kModelGeneric) {
-                            using BM = Builtin<MODEL>;
-#pragma unroll
-                            for (int c = 0; c < C; ++c) dx[c] = (Real)BM::T(E - 1, c);
-#pragma unroll
-                            for (int i = E - 2; i >= 0; --i) {
-                                const bool hit = cum[i] > etc;
-#pragma unroll
-                                for (int c = 0; c < C; ++c) dx[c] = hit ? (Real)BM::T(i, c) : dx[c];
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < C; ++c) dx[c] = m.trans[E - 1][c];
-#pragma unroll
-                            for (int i = E - 2; i >= 0; --i) {
-                                const bool hit = cum[i] > etc;
-#pragma unroll
-                                for (int c = 0; c < C; ++c) dx[c] = hit ? m.trans[i][c] : dx[c];
-                            }
-                        }
+                        chosen_transition<Real, C, E, MODEL>(m, cum, __dmul_rn(u32_open_f64(w.y), rtot), dx);
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[c] += dx[c];
                         ++k;
@@ -236,22 +269,24 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                 }
             }
         }
+        }
         const unsigned fmask = __ballot_sync(FULL, fin);
         if (fmask) {  // warp-uniform: finished lanes park their particle and pull the next slot of the chunk
             if (fin) {
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    if (c < a.n_comp) st_s[c * TILE + q] = (SState)x[c];
-                if (ovf) ovf_s[q] = 1;
+                    if (c < n_comp) st_s[c * TILE + q] = (SState)x[c];
+                if (ovf) {
+                    ovf_s[q] = 1;
+                    ++ovf_local;
+                }
                 ev_local += k;
-                ovf_local += ovf ? 1u : 0u;
                 const int slot = next + __popc(fmask & lt_mask);
                 active = slot < chunk_valid;
                 if (active) {
                     q = chunk0 + slot;
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        x[c] = (c < a.n_comp) ? (Real)(a.fresh ? m.ic[c] : st_s[c * TILE + q]) : (Real)0;
+                    for (int c = 0; c < C; ++c) x[c] = (c < n_comp) ? (Real)st_s[c * TILE + q] : (Real)0;
                     tm = tm0;
                     k = 0;
                 }
@@ -259,19 +294,33 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             next += __popc(fmask);
         }
     }
-    __syncthreads();
+    // every thread's ITEMS particles of the blocked pass below lie in its own warp's chunk
+    __syncwarp();
 
     pdl_trigger();
     // ---- convergent pass (blocked: thread owns ITEMS consecutive particles): observation log-weight
     // (src/hmm_examples.jl:63-65, exp deferred) and vectorised write-back of states and log weights
-    double it[ITEMS], av[ITEMS], incl[ITEMS], excl[ITEMS];
+    // The log-weight depends on the particle only through the integer |sum(y) - sum(x)| =: d (Int64 observations and
+    // counts), and it is non-increasing in d, so: the tile maximum m_b is the log-weight of the smallest d (an integer
+    // min-reduction), and exp(logw - m_b) comes from a per-CTA table indexed by d - d_min, each entry evaluated with
+    // exactly the per-particle f64 expression (bit-identical to the direct evaluation, one exp per thread instead of
+    // ITEMS).  Offsets beyond the table and non-integer / huge sum(y) take the direct expression.
+    double av[ITEMS], incl[ITEMS], excl[ITEMS];
+    auto logw_of = [&](double d) -> double {  // tmp1 - (y - x)^2 / tmp2 (src/hmm_examples.jl:63-65)
+        const double dd = __dmul_rn(d, d);
+        const double quot = m.obs_tmp2_pow2 ? __dmul_rn(dd, m.obs_inv_tmp2) : __ddiv_rn(dd, m.obs_tmp2);
+        return m.obs_tmp1 - quot;
+    };
+    constexpr unsigned kExcluded = 0xffffffffu;  // padding slot or particle that hit the event cap: weight 0
+    const bool int_obs = fabs(ysum) < 1073741824.0 && ysum == rint(ysum);  // CTA-uniform
+    double m_b;
     {
         int xs[ITEMS];
 #pragma unroll
         for (int kk = 0; kk < ITEMS; ++kk) xs[kk] = 0;
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (c < a.n_comp) {
+            if (c < n_comp) {
                 Vec v;
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) v.v[kk] = (int)st_s[c * TILE + tid * ITEMS + kk];
@@ -281,41 +330,76 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     *reinterpret_cast<Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS) = v;  // padding slots included
             }
         const Vec of = *reinterpret_cast<const Vec*>(ovf_s + tid * ITEMS);
+        bool excluded[ITEMS];
 #pragma unroll
-        for (int kk = 0; kk < ITEMS; ++kk) {
-            const double d = ysum - (double)xs[kk];
-            const double dd = __dmul_rn(d, d);
-            const double quot = m.obs_tmp2_pow2 ? __dmul_rn(dd, m.obs_inv_tmp2) : __ddiv_rn(dd, m.obs_tmp2);
-            const bool valid = base_n + tid * ITEMS + kk < a.n;
-            it[kk] = (valid && of.v[kk] == 0) ? m.obs_tmp1 - quot : -INFINITY;
-        }
-        if (a.record_logw) {
-            double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
-#pragma unroll
-            for (int kk = 0; kk < ITEMS; ++kk) lw_b[kk] = it[kk];
-        }
-    }
+        for (int kk = 0; kk < ITEMS; ++kk) excluded[kk] = !(base_n + tid * ITEMS + kk < a.n) || of.v[kk] != 0;
 
-    // event statistics: one atomic per warp
+        // event statistics: one atomic per warp
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
-        ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
-    }
-    if ((tid & 31) == 0) {
-        if (ev_local) atomicAdd(a.ev_count, ev_local);
-        if (ovf_local) atomicAdd(a.ovf_count, ovf_local);
-    }
+        for (int d = 16; d > 0; d >>= 1) {
+            ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
+            ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
+        }
+        if ((tid & 31) == 0) {
+            if (ev_local) atomicAdd(a.ev_count, ev_local);
+            if (ovf_local) atomicAdd(a.ovf_count, ovf_local);
+        }
 
+        if (int_obs) {
+            const int ys = (int)ysum;
+            unsigned du[ITEMS], dloc = kExcluded;
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) {
+                const long long df = (long long)ys - (long long)xs[kk];
+                du[kk] = excluded[kk] ? kExcluded : (unsigned)(df < 0 ? -df : df);  // < 2^32 - 1
+                dloc = min(dloc, du[kk]);
+            }
+            dloc = __reduce_min_sync(0xffffffffu, dloc);
+            if (lane == 0) warp_min_s[warp] = dloc;
+            __syncthreads();
+            unsigned dmin = warp_min_s[0];
+#pragma unroll
+            for (int w = 1; w < kBlockThreads / 32; ++w) dmin = min(dmin, warp_min_s[w]);
+            if (dmin == kExcluded) {  // no particle with a weight in this tile
+                m_b = -INFINITY;
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) av[kk] = 0.0;
+            } else {
+                m_b = logw_of((double)dmin);
+                wtab_s[tid] = exp(logw_of((double)dmin + (double)tid) - m_b);
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) {
+                    const unsigned off = du[kk] - dmin;
+                    av[kk] = du[kk] == kExcluded ? 0.0
+                           : (off < (unsigned)kBlockThreads ? wtab_s[off] : exp(logw_of((double)du[kk]) - m_b));
+                }
+            }
+            if (a.record_logw) {
+                double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) lw_b[kk] = du[kk] == kExcluded ? -INFINITY : logw_of((double)du[kk]);
+            }
+        } else {
+            double it[ITEMS], mloc = -INFINITY;
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) {
+                it[kk] = excluded[kk] ? -INFINITY : logw_of(ysum - (double)xs[kk]);
+                mloc = fmax(mloc, it[kk]);
+            }
+            if (a.record_logw) {
+                double* lw_b = a.logw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+#pragma unroll
+                for (int kk = 0; kk < ITEMS; ++kk) lw_b[kk] = it[kk];
+            }
+            m_b = block_max(mloc, warp_scratch);
+            const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
+        }
+    }
     // tile partials (m_b, s_b) in the blocked item order of the scan tree
-    double mloc = -INFINITY;
-#pragma unroll
-    for (int kk = 0; kk < ITEMS; ++kk) mloc = fmax(mloc, it[kk]);
-    const double m_b = block_max(mloc, warp_scratch);
-    const double ref = (m_b == -INFINITY) ? 0.0 : m_b;
-#pragma unroll
-    for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
-    const double s_b = tile_scan<ITEMS>(av, incl, excl, warp_scratch);
+    const double s_b = tile_scan<ITEMS, false>(av, incl, excl, warp_scratch);
     if (!resample_here) {  // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs
         double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
         if constexpr (ITEMS % 2 == 0) {
