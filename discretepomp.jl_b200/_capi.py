@@ -20,7 +20,8 @@ RS_SYSTEMATIC, RS_STRATIFIED, RS_MULTINOMIAL = 1, 2, 3
 SIM_F32, SIM_F64 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdpomp.so")
+# DPOMP_LIB_PATH selects another build of the same library (kernel A/B measurements); there is still no fallback
+LIB_PATH = os.environ.get("DPOMP_LIB_PATH") or os.path.join(_HERE, "lib", "libdpomp.so")
 
 
 class DpompError(RuntimeError):

@@ -45,6 +45,34 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """Build lib/variants/libdpomp_<name>.so with extra nvcc flags (kernel A/B measurements; select it at run time
+    with DPOMP_LIB_PATH).  Not used by the product path."""
+    vdir = os.path.join(LIBDIR, "variants")
+    odir = os.path.join(vdir, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    out = os.path.join(vdir, f"libdpomp_{name}.so")
+    nvcc, ccbin = _nvcc(), _host_cxx_args()
+
+    def one(src: str) -> str:
+        obj = os.path.join(odir, src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, *ccbin, "-c", os.path.join(CSRC, src), "-o", obj],
+                             capture_output=True, text=True)
+        with open(obj.replace(".o", ".ptxas.log"), "w") as f:
+            f.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(one, SOURCES))
+    res = subprocess.run([nvcc, "-shared", *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-lcudart"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libdpomp.so")
@@ -81,4 +109,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

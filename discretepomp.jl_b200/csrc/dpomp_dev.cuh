@@ -212,8 +212,21 @@ __device__ __forceinline__ double resample_u(const ResampleCtx& c, int i /*1-bas
 __device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, double v) {
     const int n = (int)c.n;
     if (!(c.s > 0.0)) return n;
-    double g = (c.rs_type == DPOMP_RS_STRATIFIED) ? floor(v * c.inv_s * c.dn)
-                                                  : floor((v * c.inv_s - c.r1_over_n) * c.dn) + 1.0;
+    double g;
+    if (c.rs_type == DPOMP_RS_STRATIFIED) {
+        g = floor(v * c.inv_s * c.dn);
+    } else {
+        // u_i <= v  <=>  i <= t + 1 with t = v N / S - r in exact arithmetic.  The f64 evaluation of t and the rounding of
+        // the reference's expression for u_i are both off by < 2^-20 index units for N < 2^31, so unless t lies within
+        // 2^-12 of an integer (or outside (0, N - 1)) the count is floor(t) + 1 and needs no verification.
+        const double t = (v * c.inv_s - c.r1_over_n) * c.dn;
+        const double fl = floor(t);
+        const double frac = t - fl;
+#ifndef DPOMP_NO_ECOUNT_FAST
+        if (frac > 0x1.0p-12 && frac < 1.0 - 0x1.0p-12 && t > 0.0 && t < c.dn - 1.0) return (long long)fl + 1;
+#endif
+        g = fl + 1.0;
+    }
     g = fmin(fmax(g, 0.0), c.dn);
     int e = (int)g;
     while (e < n && resample_u(c, e + 1) <= v) ++e;
