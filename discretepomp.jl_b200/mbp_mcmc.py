@@ -78,7 +78,7 @@ def run_mbp_mcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int, a
 
     rngs = [np.random.default_rng([seed, 0x4D43, lo + k]) for k in range(n_loc)]  # per-chain host streams
     chains = np.zeros((n_loc, steps, d))
-    theta = np.ascontiguousarray(theta_init[:, lo:hi])  # (d, n_loc) current theta of every local chain
+    theta = np.array(theta_init[:, lo:hi], dtype=np.float64, order="C")  # own copy (d, n_loc): current theta of every local chain
     a_cnt = np.zeros((n_loc, 2), dtype=np.int64)
     if n_loc:
         log_like = generate_x0(model, ptcls, theta, next_key)  # x0.log_like[1]

@@ -198,3 +198,44 @@ def test_gillespie_sim_entry_point(dp, orc):
     # mixture of early extinctions (I = 0) and the endemic state (I ~ 67): compare extinction rate and endemic mean
     assert abs((gpu_final == 0).mean() - (ref_final == 0).mean()) < 0.05
     assert abs(gpu_final[gpu_final > 0].mean() - ref_final[ref_final > 0].mean()) < 1.0
+
+
+def test_mbp_mcmc_chains_match_oracle_store(dp, orc):
+    """run_mbp_mcmc (src/hmm_mcmc.jl:330-345): the same host driver on the CUDA trajectory store and on the oracle-backed
+    store, identical host streams and Philox keys -- the chains must agree step for step (proposal log-likelihoods agree
+    to ~1e-12, so accept/reject decisions are identical away from knife edges)."""
+    import os, sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_mbp import OracleMbp
+    for case, prior_hi, t0 in (("sis_pooley", [0.01, 0.5], False), ("seir_c3", [0.02, 1.0, 0.5], False), ("sis_pooley", [0.01, 0.5, 10.0], True)):
+        model, y, hmm, theta = _setup(dp, case, t0)
+        y = y[:20]
+        model.prior = dp.UniformProduct([0.0] * len(prior_hi), prior_hi)
+        hmm = dp.get_private_model(model, y)
+        cm = dp.compile_model(model, y)
+        mk = lambda n, sd: OracleMbp(cm.desc, [o.time for o in y], hmm.t0_index, n, 4096, sd)
+        th0 = theta[:, None] * np.random.default_rng(2).uniform(0.8, 1.2, size=(len(theta), 4))
+        a = dp.run_mbp_mcmc(hmm, th0, 300, 100, False, seed=31, max_traj=4096, verbose=False)
+        b = dp.run_mbp_mcmc(hmm, th0, 300, 100, False, seed=31, particles_factory=mk, verbose=False)
+        assert np.allclose(a.samples.theta, b.samples.theta, rtol=1e-9, atol=0), case
+        assert np.array_equal(a.a_cnt, b.a_cnt) and a.a_cnt[:, 1].sum() > 0
+
+
+def test_run_mcmc_analysis_default_algorithm_posterior(dp):
+    """run_mcmc_analysis(model, y) -- MBP-MCMC is the reference's default (src/DiscretePOMP.jl:185-193): posterior of
+    SIS / pooley.csv against the anchors (theta ~ (0.00327, 0.109); the reference's seeded run of
+    test/runtests.jl:40-44 gives samples.mu[1] = 0.003318) with 16 lock-step chains started around the mode."""
+    model, y, hmm, theta = _setup(dp)
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    th0 = theta[:, None] * np.random.default_rng(8).uniform(0.7, 1.3, size=(2, 16))
+    r = dp.run_mcmc_analysis(model, y, n_chains=16, initial_parameters=th0, steps=3000, adapt_period=600, seed=5, verbose=False)
+    assert r.samples.theta.shape == (2, 3000, 16) and np.array_equal(r.samples.theta[:, 0, :], th0)
+    # short chains (one slow-mixing mode sits near 0.0028, see the 50000-step CPU test for the tight anchor)
+    assert abs(r.samples.mu[0] - 0.00327) < 0.0006 and abs(r.samples.mu[1] - 0.109) < 0.03, r.samples.mu
+    assert np.all(r.a_cnt[:, 1] > 0.05 * 2400)
+    # chains drawn from the prior by default, like the reference
+    r2 = dp.run_mcmc_analysis(model, y, n_chains=3, steps=50, seed=6, verbose=False)
+    assert r2.samples.theta.shape == (2, 50, 3) and r2.adapt_period == 10
+    with pytest.raises(NotImplementedError):
+        dp.run_mcmc_analysis(model, y, mbp=False)

@@ -61,6 +61,12 @@ def _pibis_worker(rank, world, port, out_path, kind):
         res = dp.run_pibis(hmm, theta0, 0.5, True, 1.002, 40, rng=np.random.default_rng(9), seed=5, comm=comm,
                            pf_factory=factory, outer_rs=lambda w, rng: _host_rs_systematic(w, rng), verbose=False)
         out = dict(bme=res.bme, mu=res.mu, theta=res.theta, w=res.weight, k=res.k_log)
+    elif kind == "mbp_mcmc":
+        from fake_mbp import OracleMbp
+        theta0 = model.prior.rand(5, np.random.default_rng(4)) * 0.5 + np.array([[0.002], [0.05]])
+        mk = lambda n, sd: OracleMbp(desc.desc, [o.time for o in y], 0, n, 4096, sd)
+        res = dp.run_mbp_mcmc(hmm, theta0, 120, 50, False, seed=8, comm=comm, particles_factory=mk, verbose=False)
+        out = dict(theta=res.samples.theta, mu=res.samples.mu, acc=res.a_cnt)
     else:
         theta0 = model.prior.rand(5, np.random.default_rng(4)) * 0.5 + np.array([[0.002], [0.05]])
         res = dp.run_pmcmc(hmm, theta0, steps=40, adapt_period=20, p=40, seed=6, comm=comm, pf_factory=factory, verbose=False)
@@ -83,7 +89,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("kind", ["pibis", "pmcmc"])
+@pytest.mark.parametrize("kind", ["pibis", "pmcmc", "mbp_mcmc"])
 def test_world_size_2_gloo_matches_single_process(tmp_path, kind):
     """Sharding theta-particles / chains over 2 ranks (gloo) gives bit-identical results to one process: the streams are
     keyed by global filter ids and call counters, the host RNG is replicated."""
@@ -125,3 +131,35 @@ def test_prop_density_guard(dp):
     assert np.allclose(new.chol @ new.chol.T, [[2.0, 0.5], [0.5, 1.0]])
     mu, cv = dp.compute_is_mu_covar(np.array([[1.0, 3.0], [2.0, 2.0]]), np.array([1.0, 3.0]))
     assert np.allclose(mu, [2.5, 2.0]) and np.allclose(cv, [[0.75, 0.0], [0.0, 0.0]])
+
+
+def test_mbp_mcmc_host_driver_on_oracle_store(dp, orc):
+    """run_mbp_mcmc (src/hmm_mcmc.jl:330-345, met_hastings_alg! :123-141) on the oracle-backed trajectory store: the
+    posterior of SIS / pooley.csv against the anchors of SURVEY.md 8c (theta ~ (0.00327, 0.109)), acceptance bookkeeping
+    and the shape contract of the result."""
+    from fake_mbp import OracleMbp
+    model = dp.generate_model("SIS", [100, 1])
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "pooley.csv"))
+    hmm = dp.get_private_model(model, y)
+    cm = dp.compile_model(model, y)
+    mk = lambda n, sd: OracleMbp(cm.desc, [o.time for o in y], 0, n, 4096, sd)
+    # the configuration of the reference's own test (test/runtests.jl:40-44: run_mcmc_analysis defaults, 3 chains from the
+    # prior, 50000 steps, adaptation 10000), whose seeded run gives samples.mu[1] = 0.003318
+    th0 = model.prior.rand(3, np.random.default_rng(1))
+    steps, adapt = 50000, 10000
+    r = dp.run_mbp_mcmc(hmm, th0, steps, adapt, False, seed=1, particles_factory=mk, verbose=False)
+    assert r.samples.theta.shape == (2, steps, 3) and r.adapt_period == adapt
+    assert abs(r.samples.mu[0] - 0.003318) < 0.0003, r.samples.mu
+    assert np.array_equal(r.samples.theta[:, 0, :], th0)  # theta[:,1,mc] .= xi.theta
+    assert np.all(r.a_cnt[:, 0] >= 1) and np.all(r.a_cnt.sum(axis=1) <= steps)
+    # accepted moves change theta, rejected ones repeat it
+    moved = np.any(np.diff(r.samples.theta, axis=1) != 0, axis=0).sum(axis=0) + 1
+    assert np.array_equal(moved, r.a_cnt.sum(axis=1))
+    assert abs(r.samples.mu[0] - 0.00327) < 0.0003 and abs(r.samples.mu[1] - 0.109) < 0.015, r.samples.mu
+    assert np.all(r.sre[:, 1] < 1.1) and np.all(np.abs(r.a_cnt[:, 1] / (steps - adapt) - 0.333) < 0.03)  # 1.002 / 0.999 scaling
+    # finite adaptation freezes the scale after the adaptation period; an impossible prior rejects every proposal
+    model.prior = dp.UniformProduct([0, 0], [1e-9, 1e-9])
+    hmm2 = dp.get_private_model(model, y)
+    r2 = dp.run_mbp_mcmc(hmm2, th0[:, :2], 30, 10, True, seed=2, particles_factory=mk, verbose=False)
+    assert np.all(r2.samples.theta == th0[:, :2][:, None, :]) and np.array_equal(r2.a_cnt, [[1, 0], [1, 0]])
