@@ -23,6 +23,25 @@ namespace dpomp {
 #ifndef DPOMP_ITEMS_SMALL
 #define DPOMP_ITEMS_SMALL 2
 #endif
+// Debug build only (-DDPOMP_PHASE_TIMERS, scripts/phase_probe.py): thread 0 of every CTA stamps %globaltimer at phase
+// boundaries of the launches of observation index DPOMP_PHASE_OBS into a device array read back by dpomp_debug_phases.
+#ifdef DPOMP_PHASE_TIMERS
+#ifndef DPOMP_PHASE_OBS
+#define DPOMP_PHASE_OBS 50
+#endif
+static __device__ unsigned long long g_dpomp_phase[2][4096][8];  // one copy per translation unit (no -rdc)
+__device__ __forceinline__ unsigned long long dpomp_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DPOMP_STAMP(K, P)                                                                                   \
+    do {                                                                                                    \
+        if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS && blockIdx.x < 4096) g_dpomp_phase[K][blockIdx.x][P] = dpomp_gtime(); \
+    } while (0)
+#else
+#define DPOMP_STAMP(K, P) do { } while (0)
+#endif
 constexpr int kBlockThreads = DPOMP_BLOCK_THREADS;
 constexpr int kItemsLarge = DPOMP_ITEMS_LARGE, kItemsSmall = DPOMP_ITEMS_SMALL;
 

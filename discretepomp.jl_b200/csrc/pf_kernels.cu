@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
 
+    DPOMP_STAMP(1, 0);
     pdl_wait();
+    DPOMP_STAMP(1, 1);
     const double big_s = a.filt_s[b];
     const int grp = tile / kGroupTiles;
     const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
@@ -130,7 +132,9 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
 
     const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
                     a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
+    DPOMP_STAMP(1, 2);
     resample_tile<ITEMS, int, false>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
+    DPOMP_STAMP(1, 4);
 }
 
 // multinomial: offspring i draws chs = r_i * S; ancestor = first p2 < N with chs < cw[p2], else N (src/hmm_resample.jl:9-16)
@@ -271,3 +275,9 @@ cudaError_t launch_search_hook(int rs_type, const double* cw_dev, long long n, c
 }
 
 }  // namespace dpomp
+
+#ifdef DPOMP_PHASE_TIMERS
+extern "C" int dpomp_debug_phases_rs(unsigned long long* out /* [2][4096][8] */) {
+    return (int)cudaMemcpyFromSymbol(out, dpomp::g_dpomp_phase, sizeof(unsigned long long) * 2 * 4096 * 8);
+}
+#endif

@@ -87,6 +87,9 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     if (lane == 31) warp_max_s[warp] = inc;
     __syncthreads();  // the only block barrier
     pdl_trigger();
+#ifdef DPOMP_PHASE_TIMERS
+    if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS && blockIdx.x < 4096) g_dpomp_phase[1][blockIdx.x][3] = dpomp_gtime();
+#endif
 
     const long long lo = lohi_s[0], hi = lohi_s[1];
     int wprev_raw = -1;

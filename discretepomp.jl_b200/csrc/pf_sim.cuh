@@ -57,11 +57,16 @@ DPOMP_BUILTIN(kModelLOTKA, 2, 3, DPOMP_L(1, 0, 0), DPOMP_L(-1, 1, -1), DPOMP_L({
 #undef DPOMP_BUILTIN
 
 // resident CTAs per SM the register allocation is tuned for (the f64 parity loop is not tuned)
-template <typename Real, int C, int E>
+// particles a lane of the f32 event loop works on at once (2 measured on B200: C2 3.76 vs 3.66 ms, SEIR batch 15.0 vs 14.6 ms,
+// LOTKA batch 76.1 vs 77.6 ms -- the second slot costs more in the refill path than it hides in the dependency chains)
+#ifndef DPOMP_SIM_ILP
+#define DPOMP_SIM_ILP 1
+#endif
 // 256-thread CTAs: 4 resident (64 registers, no spills) beat 5 / 6 (48 / 40 registers) on B200; 128-thread CTAs: 7 resident
 #ifndef DPOMP_SIM_MINB
 #define DPOMP_SIM_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
+template <typename Real, int C, int E>
 constexpr int sim_min_blocks() { return sizeof(Real) == 4 ? DPOMP_SIM_MINB : 1; }
 
 template <int N>
@@ -171,11 +176,13 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     int32_t* pop_b = a.pop + (size_t)b * a.n_comp * a.n_pad;
     const uint32_t max_ev = (uint32_t)a.max_events;
 
+    DPOMP_STAMP(0, 0);
     if (tid == 0) {  // independent of the predecessor kernel: overlaps its tail
         const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)a.t);
         stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;
     }
     pdl_wait();  // everything below reads or writes buffers shared with the predecessor kernel
+    DPOMP_STAMP(0, 1);
     // stage the tile: each thread moves ITEMS consecutive particles per compartment with one vector access
     using Vec = IntVec<ITEMS>;
     {
@@ -204,98 +211,121 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             }
     }
     __syncthreads();
+    DPOMP_STAMP(0, 2);
     const SimStream ss{stream_s[0], stream_s[1], stream_s[2]};
 
     // ---- event loop: each warp drains its chunk of CHUNK particles through a ballot-based work queue ----------
+    // A lane can work on S particles at once (DPOMP_SIM_ILP, default 1): independent instruction streams per lane.
+    constexpr int S = (kF32 && C <= 4 && E <= 3) ? DPOMP_SIM_ILP : 1;  // the wide generic shapes would spill
     const int chunk0 = warp * CHUNK;
     const long long left = a.n - (base_n + chunk0);
     const int chunk_valid = left < CHUNK ? (left > 0 ? (int)left : 0) : CHUNK;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int next = 32;  // warp-uniform: next unassigned slot of the chunk
-    int q = chunk0 + lane;
-    bool active = lane < chunk_valid;
-    Real x[C];
-    Real tm = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;  // f32: remaining time; f64: absolute time
-    const Real tm0 = tm;
-    uint32_t k = 0;
+    int next = 32 * S;  // warp-uniform: next unassigned slot of the chunk
+    int parked = 0;     // warp-uniform: particles of the chunk that are done
+    int q[S];
+    bool active[S];
+    Real x[S][C];
+    Real tm[S];
+    const Real tm0 = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;  // f32: remaining time; f64: absolute time
+    uint32_t k[S];
     unsigned long long ev_local = 0, ovf_local = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) x[c] = (c < n_comp) ? (Real)st_s[c * TILE + q] : (Real)0;  // idle lanes: harmless values
+    for (int s = 0; s < S; ++s) {
+        const int slot = lane + 32 * s;
+        active[s] = slot < chunk_valid;
+        q[s] = chunk0 + (slot < CHUNK ? slot : lane);
+        tm[s] = tm0;
+        k[s] = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;  // idle lanes: harmless values
+    }
 
-    while (__any_sync(FULL, active)) {
-        bool fin = false, ovf = false;
-        if constexpr (kF32) {
-            // One attempt for every lane, branch free: an absorbed state (`cum_rates[end] == 0.0 && break`, :22) makes the
-            // waiting time -inf / NaN, so `tmn >= 0` is false; the event cap is folded into the same predicate.
-            Real cum[E];
-            cum_rates<Real, C, E, MODEL>(m, par, x, cum);
-            const Real rtot = cum[E - 1];
-            const uint2 w = philox2x32_10((uint32_t)(base_n + q) ^ ss.a, k ^ ss.b, ss.k);
-            // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
-            const Real tmn = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm);
-            const bool capped = k >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
-            const bool go = (rtot > (Real)0) && !capped && (tmn >= (Real)0);  // `time > tmax && break` (:24)
-            Real dx[C];
-            chosen_transition<Real, C, E, MODEL>(m, cum, u32_open_f32(w.y) * rtot, dx);  // choose_event + fn_transition (:25-26)
-            if (go) {
+    while (parked < chunk_valid) {
+        bool fin[S], ovf[S];
 #pragma unroll
-                for (int c = 0; c < C; ++c) x[c] += dx[c];
-                ++k;
-                tm = tmn;
-            }
-            fin = active && !go;
-            ovf = capped && (rtot > (Real)0);
-        } else {
-        if (active) {
-            Real cum[E];
-            cum_rates<Real, C, E, MODEL>(m, par, x, cum);
-            const Real rtot = cum[E - 1];
-            fin = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
-            if (!fin) {
-                if (k >= max_ev) {  // event cap: documented divergence, the reference loop is unbounded
-                    fin = true;
-                    ovf = true;
-                } else {
-                    const uint2 w = philox2x32_10((uint32_t)(base_n + q) ^ ss.a, k ^ ss.b, ss.k);
-                    tm = tm - log(u32_open_f64(w.x)) / rtot;  // time -= log(rand()) / R (:23)
-                    fin = tm > t_obs;                          // `time > tmax && break` (:24)
-                    if (!fin) {
-                        Real dx[C];
-                        chosen_transition<Real, C, E, MODEL>(m, cum, __dmul_rn(u32_open_f64(w.y), rtot), dx);
+        for (int s = 0; s < S; ++s) {
+            fin[s] = false;
+            ovf[s] = false;
+            if constexpr (kF32) {
+                // One attempt for every lane, branch free: an absorbed state (`cum_rates[end] == 0.0 && break`, :22) makes
+                // the waiting time -inf / NaN, so `tmn >= 0` is false; the event cap is folded into the same predicate.
+                Real cum[E];
+                cum_rates<Real, C, E, MODEL>(m, par, x[s], cum);
+                const Real rtot = cum[E - 1];
+                const uint2 w = philox2x32_10((uint32_t)(base_n + q[s]) ^ ss.a, k[s] ^ ss.b, ss.k);
+                // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
+                const Real tmn = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm[s]);
+                const bool capped = k[s] >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
+                const bool go = (rtot > (Real)0) && !capped && (tmn >= (Real)0);  // `time > tmax && break` (:24)
+                Real dx[C];
+                chosen_transition<Real, C, E, MODEL>(m, cum, u32_open_f32(w.y) * rtot, dx);  // choose_event + fn_transition (:25-26)
+                if (go) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) x[c] += dx[c];
-                        ++k;
+                    for (int c = 0; c < C; ++c) x[s][c] += dx[c];
+                    ++k[s];
+                    tm[s] = tmn;
+                }
+                fin[s] = active[s] && !go;
+                ovf[s] = capped && (rtot > (Real)0);
+            } else {
+                if (active[s]) {
+                    Real cum[E];
+                    cum_rates<Real, C, E, MODEL>(m, par, x[s], cum);
+                    const Real rtot = cum[E - 1];
+                    fin[s] = !(rtot > (Real)0);  // `cum_rates[end] == 0.0 && break` (:22)
+                    if (!fin[s]) {
+                        if (k[s] >= max_ev) {  // event cap: documented divergence, the reference loop is unbounded
+                            fin[s] = true;
+                            ovf[s] = true;
+                        } else {
+                            const uint2 w = philox2x32_10((uint32_t)(base_n + q[s]) ^ ss.a, k[s] ^ ss.b, ss.k);
+                            tm[s] = tm[s] - log(u32_open_f64(w.x)) / rtot;  // time -= log(rand()) / R (:23)
+                            fin[s] = tm[s] > t_obs;                           // `time > tmax && break` (:24)
+                            if (!fin[s]) {
+                                Real dx[C];
+                                chosen_transition<Real, C, E, MODEL>(m, cum, __dmul_rn(u32_open_f64(w.y), rtot), dx);
+#pragma unroll
+                                for (int c = 0; c < C; ++c) x[s][c] += dx[c];
+                                ++k[s];
+                            }
+                        }
                     }
                 }
             }
         }
-        }
-        const unsigned fmask = __ballot_sync(FULL, fin);
-        if (fmask) {  // warp-uniform: finished lanes park their particle and pull the next slot of the chunk
-            if (fin) {
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    if (c < n_comp) st_s[c * TILE + q] = (SState)x[c];
-                if (ovf) {
-                    ovf_s[q] = 1;
-                    ++ovf_local;
-                }
-                ev_local += k;
-                const int slot = next + __popc(fmask & lt_mask);
-                active = slot < chunk_valid;
-                if (active) {
-                    q = chunk0 + slot;
+        for (int s = 0; s < S; ++s) {
+            const unsigned fmask = __ballot_sync(FULL, fin[s]);
+            if (fmask) {  // warp-uniform: finished lanes park their particle and pull the next slot of the chunk
+                if (fin[s]) {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) x[c] = (c < n_comp) ? (Real)st_s[c * TILE + q] : (Real)0;
-                    tm = tm0;
-                    k = 0;
+                    for (int c = 0; c < C; ++c)
+                        if (c < n_comp) st_s[c * TILE + q[s]] = (SState)x[s][c];
+                    if (ovf[s]) {
+                        ovf_s[q[s]] = 1;
+                        ++ovf_local;
+                    }
+                    ev_local += k[s];
+                    const int slot = next + __popc(fmask & lt_mask);
+                    active[s] = slot < chunk_valid;
+                    if (active[s]) {
+                        q[s] = chunk0 + slot;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;
+                        tm[s] = tm0;
+                        k[s] = 0;
+                    }
                 }
+                const int nf = __popc(fmask);
+                next += nf;
+                parked += nf;
             }
-            next += __popc(fmask);
         }
     }
     // every thread's ITEMS particles of the blocked pass below lie in its own warp's chunk
     __syncwarp();
+    DPOMP_STAMP(0, 3);
 
     pdl_trigger();
     // ---- convergent pass (blocked: thread owns ITEMS consecutive particles): observation log-weight
@@ -398,6 +428,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             for (int kk = 0; kk < ITEMS; ++kk) av[kk] = (it[kk] == -INFINITY) ? 0.0 : exp(it[kk] - ref);
         }
     }
+    DPOMP_STAMP(0, 4);
     // tile partials (m_b, s_b) in the blocked item order of the scan tree
     const double s_b = tile_scan<ITEMS, false>(av, incl, excl, warp_scratch);
     if (!resample_here) {  // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs
@@ -415,6 +446,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     // level 1: the kGroupTiles tiles of a group, level 2: the groups of the filter.  Both levels are one warp with the
     // same tree (one value per lane, Kogge-Stone over the lanes, chunks of 32 chained sequentially): no block barriers on
     // the serial tail of the kernel.
+    DPOMP_STAMP(0, 5);
     const int grp = tile / kGroupTiles;
     const int grp_tiles = min(kGroupTiles, a.ntiles - grp * kGroupTiles);
     // Only warp 0 stays for the tickets; in the two-kernel path the other warps are done (no block barrier on the tail).
@@ -503,6 +535,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
     }  // last_group
     }  // group-last warp
+    DPOMP_STAMP(0, 6);
 
     if constexpr (FUSED) {
         if (!a.do_resample) return;

@@ -5,3 +5,9 @@ int sim_f32(const ModelHost& m, int items, const SimLaunch& a, cudaStream_t stre
     return sim_typed<float>(m, items, a, stream, mode);
 }
 }  // namespace dpomp
+
+#ifdef DPOMP_PHASE_TIMERS
+extern "C" int dpomp_debug_phases_sim(unsigned long long* out /* [2][4096][8] */) {
+    return (int)cudaMemcpyFromSymbol(out, dpomp::g_dpomp_phase, sizeof(unsigned long long) * 2 * 4096 * 8);
+}
+#endif

@@ -76,7 +76,6 @@ def run_mbp_mcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int, a
         call += 1
         return splitmix64((seed & _M64) ^ splitmix64(0x4D43 + call))
 
-    rngs = [np.random.default_rng([seed, 0x4D43, lo + k]) for k in range(n_loc)]  # per-chain host streams
     chains = np.zeros((n_loc, steps, d))
     theta = np.array(theta_init[:, lo:hi], dtype=np.float64, order="C")  # own copy (d, n_loc): current theta of every local chain
     a_cnt = np.zeros((n_loc, 2), dtype=np.int64)
@@ -84,20 +83,26 @@ def run_mbp_mcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int, a
         log_like = generate_x0(model, ptcls, theta, next_key)  # x0.log_like[1]
         prior = prior_logpdf_columns(model.prior, theta)       # x0.prior
         # @initialise_mcmc: covar[i,i] = theta[i] == 0 ? 1 : theta[i]^2; propd = MvNormal(covar); c = C_INITIAL
-        propd = [ProposalDensity(np.diag(np.where(theta[:, k] == 0.0, 1.0, np.abs(theta[:, k])))) for k in range(n_loc)]
+        chol = np.zeros((n_loc, d, d))  # Cholesky factor of every chain's proposal covariance
+        chol[:, np.arange(d), np.arange(d)] = np.where(theta.T == 0.0, 1.0, np.abs(theta.T))
         c = np.full(n_loc, C_INITIAL)
         chains[:, 0, :] = theta.T
         a_cnt[:, 0] = 1
+        sum_x = theta.T.copy()                                   # running sums of the samples of every chain: the
+        sum_xx = np.einsum("ki,kj->kij", theta.T, theta.T)       # covariance of @mcmc_adapt_period without a pass over them
         adapt_interval = adapt_period / C_MCMC_ADAPT_INTERVALS  # Float64, like the reference
         n_obs = len(model.obs_data)
         for i in range(2, steps + 1):  # Julia's 1-based step index
-            z = np.stack([propd[k].chol @ rngs[k].standard_normal(d) for k in range(n_loc)], axis=1)  # rand(propd)
-            theta_f = theta + c[None, :] * z  # get_mv_param(propd, c, theta[:, i-1, mc]) (:126)
+            # host draws of step i for ALL chains from one stream keyed by (seed, i); a rank uses the rows of its chains, so
+            # the chains do not depend on the number of ranks
+            g = np.random.default_rng([seed & 0xFFFFFFFF, 0x4D43, i])
+            z = g.standard_normal((n_chains, d))[lo:hi]
+            u = g.random(n_chains)[lo:hi]
+            theta_f = theta + (c[:, None] * np.einsum("kij,kj->ki", chol, z)).T  # get_mv_param(propd, c, theta[:, i-1, mc]) (:126)
             prior_f = prior_logpdf_columns(model.prior, theta_f)
             valid = prior_f != -np.inf
             ptcls.set_stream_key(next_key())
             ll_f = ptcls.propose(theta, theta_f, valid, n_obs)[:, 0]  # xf.log_like[1]
-            u = np.array([rngs[k].random() for k in range(n_loc)])
             with np.errstate(over="ignore", invalid="ignore"):
                 mh_prob = np.exp(prior_f - prior) * np.exp(ll_f - log_like)  # :131
             accepted = valid & (ll_f != -np.inf) & ((mh_prob > 1) | (mh_prob > u))  # :127-133, NaN compares false
@@ -107,12 +112,23 @@ def run_mbp_mcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int, a
             log_like[accepted] = ll_f[accepted]
             a_cnt[accepted, 1 if i > adapt_period else 0] += 1
             chains[:, i - 1, :] = theta.T
+            sum_x += theta.T
+            sum_xx += np.einsum("ki,kj->kij", theta.T, theta.T)
             if (not fin_adapt) or i < adapt_period:  # @met_hastings_adapt
                 c *= np.where(accepted, 1.002, 0.999)
                 if adapt_interval > 0 and math.fmod(i, adapt_interval) == 0:  # @mcmc_adapt_period
-                    for k in range(n_loc):
-                        covar = np.atleast_2d(np.cov(chains[k, :i].T))
-                        propd[k] = get_prop_density(covar, propd[k])
+                    # covar = cov(transpose(theta[:, 1:i, mc])); propd = get_prop_density(covar, propd): kept when the
+                    # covariance is not positive definite (src/hmm_cmn.jl:33-42)
+                    mean = sum_x / i
+                    covar = (sum_xx - i * np.einsum("ki,kj->kij", mean, mean)) / (i - 1)
+                    sym = np.triu(covar) + np.transpose(np.triu(covar, 1), (0, 2, 1))  # Hermitian(): the upper triangle
+                    ok = np.linalg.eigvalsh(sym).min(axis=1) > 0
+                    if ok.any():
+                        try:
+                            chol[ok] = np.linalg.cholesky(sym[ok])
+                        except np.linalg.LinAlgError:  # borderline matrices: decide chain by chain
+                            for k in np.nonzero(ok)[0]:
+                                chol[k] = get_prop_density(sym[k], ProposalDensity(chol[k])).chol
     flat = comm.allgather_f64(chains.reshape(n_loc, steps * d), n_chains)
     samples = np.ascontiguousarray(flat.reshape(n_chains, steps, d).transpose(2, 1, 0))
     rejs = handle_rej_samples(samples, adapt_period)
