@@ -135,7 +135,8 @@ def run_smc2(dp, world, rank, barrier):
     model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
     y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "lotka_c4.csv"))
     comm = dp.Comm() if world > 1 else None
-    dp.run_ibis_analysis(model, y[:3], np=256 * world, npf=SMC2_NPF, seed=3, comm=comm, verbose=False)  # warm-up
+    # warm-up long enough to reach a resample-mutate step: NCCL sets up its all-to-all connections lazily on first use
+    dp.run_ibis_analysis(model, y[:12], np=max(SMC2_OUTER // 8, 8 * world), npf=SMC2_NPF, seed=3, comm=comm, verbose=False)
     barrier()
     t0 = time.perf_counter()
     res = dp.run_ibis_analysis(model, y, np=SMC2_OUTER, npf=SMC2_NPF, seed=1, comm=comm, verbose=False)
@@ -153,7 +154,8 @@ def run_smc2(dp, world, rank, barrier):
            "config": {"workload": f"C4: LOTKA [70,70], {SMC2_OUTER} theta x {SMC2_NPF} state particles, T={len(y)}, prior U(0,(1,0.01,1)), "
                                   "ess_rs_crit 0.3, ind_prop, n_props 1", "resample_mutate_steps": n_rs},
            "minus_log_evidence": [float(v) for v in res.bme], "posterior_mean": [float(v) for v in res.mu],
-           "acceptance_rate": float(res.k_log[1] / max(res.k_log[0], 1))}
+           "acceptance_rate": float(res.k_log[1] / max(res.k_log[0], 1)),
+           "rank0_phase_seconds": {k: round(float(v), 4) for k, v in sorted(getattr(res, "timers", {}).items())}}
     if world == 1 and rank == 0:
         from oracle import oracle as orc
 

@@ -25,6 +25,7 @@ class Comm:
             if dist.is_available() and dist.is_initialized():
                 self.dist = dist
                 self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._ag_bufs = {}  # staging buffers of allgather_f64, by block size
         self.device = None  # torch device of the exchange buffers (cuda:k under NCCL, cpu under gloo)
         if self.dist is not None:
             import torch
@@ -51,12 +52,29 @@ class Comm:
         sizes = [partition_bounds(n_total, self.world, r) for r in range(self.world)]
         width = local.shape[1] if local.ndim == 2 else 1
         maxn = max(hi - lo for lo, hi in sizes)
-        buf = torch.zeros(maxn * width, dtype=torch.float64, device=self.device)
-        buf[: local.size] = torch.from_numpy(local.reshape(-1)).to(self.device)
-        out = [torch.empty_like(buf) for _ in range(self.world)]
-        self.dist.all_gather(out, buf)
-        parts = [o[: (hi - lo) * width].cpu().numpy() for o, (lo, hi) in zip(out, sizes)]
-        res = np.concatenate(parts)
+        # one staged copy each way: pinned host block -> device, all_gather_into_tensor, device -> pinned host
+        key = (maxn * width, self.world)
+        bufs = self._ag_bufs.get(key)
+        if bufs is None:
+            pin = self.device.type == "cuda"
+            bufs = (torch.zeros(maxn * width, dtype=torch.float64, pin_memory=pin),
+                    torch.zeros(maxn * width, dtype=torch.float64, device=self.device),
+                    torch.zeros(self.world * maxn * width, dtype=torch.float64, device=self.device),
+                    torch.zeros(self.world * maxn * width, dtype=torch.float64, pin_memory=pin))
+            self._ag_bufs[key] = bufs
+        h_in, d_in, d_out, h_out = bufs
+        h_in[: local.size] = torch.from_numpy(local.reshape(-1))
+        d_in.copy_(h_in, non_blocking=True)
+        if self.dist.get_backend() == "nccl":
+            self.dist.all_gather_into_tensor(d_out, d_in)
+        else:  # gloo builds without all_gather_into_tensor
+            parts_t = list(d_out.view(self.world, -1).unbind(0))
+            self.dist.all_gather(parts_t, d_in)
+        h_out.copy_(d_out, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        allv = h_out.numpy().reshape(self.world, maxn * width)
+        res = np.concatenate([allv[r, : (hi - lo) * width] for r, (lo, hi) in enumerate(sizes)])
         return res.reshape(-1, width) if local.ndim == 2 else res
 
     def all_to_all_blocks(self, send, send_counts: Sequence[int], recv_counts: Sequence[int], block_words: int):
@@ -99,6 +117,8 @@ class Comm:
                 q.wait()
         else:
             self.dist.all_to_all_single(recv, send, rs, ss)
+            # NCCL only enqueues the exchange on torch's stream; the library reads `recv` on its own stream next
+            torch.cuda.current_stream().synchronize()
 
     def all_to_all_v(self, send, send_counts: Sequence[int], recv_counts: Sequence[int]):
         """Variable-size all-to-all of a 1-d torch tensor of any dtype; counts are element counts per rank."""
@@ -129,6 +149,7 @@ class Comm:
             recv.copy_(host_recv)
         else:
             self.dist.all_to_all_single(recv, send, rs, ss)
+            torch.cuda.current_stream().synchronize()  # consumers run on the library's own stream
         return recv
 
     def barrier(self):

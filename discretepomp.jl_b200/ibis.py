@@ -106,6 +106,12 @@ class FilterBank:
         self.prop = make(nb, seed + 0x5DEECE66D)
         self.main.set_batch_offset(self.lo)
         self.seed, self._call = seed, 0
+        self.timers = {}  # seconds per phase on this rank: kernels vs waiting for the other ranks (scaling diagnostics)
+
+    def _tick(self, name: str, t0: float) -> float:
+        t1 = time.perf_counter()
+        self.timers[name] = self.timers.get(name, 0.0) + (t1 - t0)
+        return t1
 
     def _next_key(self) -> int:
         """Call keys are derived from a counter every rank advances identically, so the random streams do not depend on
@@ -117,24 +123,34 @@ class FilterBank:
         """Batched partial_log_likelihood! for ALL theta-particles (columns of theta); each rank runs its block."""
         key = self._next_key()
         loc = np.zeros(0)
+        t0 = time.perf_counter()
         if self.n_local:
             self.main.set_stream_key(key)
             loc = self.main.partial(theta[:, self.lo:self.hi], ymin, ymax)
-        return self.comm.allgather_f64(loc, self.outer_p)
+        t0 = self._tick("filter_step", t0)
+        out = self.comm.allgather_f64(loc, self.outer_p)
+        self._tick("allgather", t0)
+        return out
 
     def resample(self, nidx: np.ndarray) -> None:
         """pop2[p] .= pop[nidx[p]] (src/hmm_ibis.jl:74) across ranks; nidx is 1-based global."""
         nidx0 = np.asarray(nidx, dtype=np.int64) - 1
+        t0 = time.perf_counter()
         if self.comm.world == 1:
             self.main.permute(nidx0 + 1)
+            self._tick("resample_local", t0)
             return
         local_src, send_slots, send_counts, recv_slots, recv_counts = migration_plan(
             nidx0, self.outer_p, self.comm.world, self.comm.rank)
+        t0 = self._tick("migration_plan", t0)
         send = self.main.export_tensor(send_slots + 1)
+        t0 = self._tick("migration_pack", t0)
         recv = self.comm.all_to_all_blocks(send, send_counts, recv_counts, self.main.filter_words)
+        t0 = self._tick("migration_all_to_all", t0)
         if self.n_local:
             self.main.permute(local_src + 1)
         self.main.import_tensor(recv_slots + 1, recv)
+        self._tick("resample_local", t0)
 
     def propose(self, theta_f: np.ndarray, valid: np.ndarray, obs_i: int):
         """Fresh filters for the valid proposals (src/hmm_ibis.jl:90-101).  Returns global (aw_f, gx_f) and the local
@@ -143,6 +159,7 @@ class FilterBank:
         self._prop_owner = mine
         aw_l, gx_l = np.zeros(self.n_local), np.zeros(self.n_local)
         key1, key2 = self._next_key(), self._next_key()
+        t0 = time.perf_counter()
         if len(mine):
             th = theta_f[:, mine]
             self.prop.set_filter_ids(mine)  # proposal slot j simulates theta-particle mine[j] (global id)
@@ -157,17 +174,22 @@ class FilterBank:
                 g = self.prop.partial(th, obs_i, obs_i)
                 a = a + g
             aw_l[mine - self.lo], gx_l[mine - self.lo] = a, g
-        return self.comm.allgather_f64(aw_l, self.outer_p), self.comm.allgather_f64(gx_l, self.outer_p)
+        t0 = self._tick("proposal_filters", t0)
+        out = self.comm.allgather_f64(np.stack([aw_l, gx_l], axis=1), self.outer_p)
+        self._tick("allgather", t0)
+        return np.ascontiguousarray(out[:, 0]), np.ascontiguousarray(out[:, 1])
 
     def accept(self, accepted: np.ndarray) -> None:
         """pop[p] .= pop_f for accepted proposals (src/hmm_ibis.jl:108)."""
         mine = self._prop_owner
         if len(mine) == 0:
             return
+        t0 = time.perf_counter()
         acc = accepted[mine]
         src = np.nonzero(acc)[0] + 1
         dst = mine[acc] - self.lo + 1
         self.main.copy_from(self.prop, dst, src)
+        self._tick("accept_copy", t0)
 
 
 def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, ind_prop: bool, alpha: float, np_: int,
@@ -238,6 +260,7 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
         ar = 100.0 * k_log[1] / k_log[0] if k_log[0] else float("nan")
         print(f"- finished in {output.run_time / 1e9:.1f} seconds (AR = {ar:.3g}%)")
     output.k_log = k_log
+    output.timers = dict(bank.timers)
     return output
 
 

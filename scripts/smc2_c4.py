@@ -15,11 +15,27 @@ if world > 1:
 model = dp.generate_model("LOTKA", [70, 70])
 model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
 y = dp.get_observations("tests/golden/lotka_c4.csv")
+dp.run_ibis_analysis(model, y[:12], np=max(outer_p // 8, 8 * world), npf=npf, seed=7, comm=comm, verbose=False)  # warm-up (CUDA / NCCL init)
+if world > 1:
+    torch.distributed.barrier()
+torch.cuda.synchronize()
 t0 = time.time()
 res = dp.run_ibis_analysis(model, y, np=outer_p, npf=npf, seed=1, comm=comm, verbose=False)
 dt = time.time() - t0
 if rank == 0:
     print(f"SMC2 C4 outer_p={outer_p} npf={npf} world={world}: {dt:.2f} s  theta-particle-obs/s={outer_p*len(y)/dt:.1f} "
           f"bme={res.bme} mu={res.mu} k_log={res.k_log}")
+tm = res.timers
+keys = sorted(tm)
+vals = torch.tensor([tm[k] for k in keys] + [dt], dtype=torch.float64, device="cuda")
+if world > 1:
+    allv = [torch.zeros_like(vals) for _ in range(world)]
+    torch.distributed.all_gather(allv, vals)
+else:
+    allv = [vals]
+if rank == 0:
+    m = torch.stack(allv).cpu().numpy()
+    for j, k in enumerate(keys + ["total"]):
+        print(f"  {k:22s} min {m[:, j].min():7.3f}  mean {m[:, j].mean():7.3f}  max {m[:, j].max():7.3f} s over ranks")
 if world > 1:
     torch.distributed.destroy_process_group()
