@@ -79,6 +79,43 @@ constexpr int kGroupTiles = 32;
 __device__ __forceinline__ double tile_cw(double grp_off, double grp_f, double tile_o, double tile_f, double incl) {
     return __dadd_rn(grp_off, __dmul_rn(grp_f, __dadd_rn(tile_o, __dmul_rn(tile_f, incl))));
 }
+// ------------------------------------------------------------------------------------------------------------
+// Level 2 of the combine (DESIGN.md "deterministic scan tree"), executed by ONE warp: the groups of a filter ->
+// M = max m_g, F_g = exp(m_g - M), O_g = exclusive offsets (Kogge-Stone over the 32 lanes of a chunk, chunks chained
+// sequentially), S = total.
+// ------------------------------------------------------------------------------------------------------------
+struct Level2 {
+    double big_m, big_s;
+};
+__device__ __forceinline__ Level2 combine_level2(const double* gm_b, const double* gs_b, int ngroups, double* grp_f_out,
+                                                 double* grp_off_out) {
+    const int lane = threadIdx.x & 31;
+    double big_m = -INFINITY;
+    for (int i = lane; i < ngroups; i += 32) big_m = fmax(big_m, __ldcg(gm_b + i));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) big_m = fmax(big_m, __shfl_xor_sync(0xffffffffu, big_m, d));
+    double carry = 0.0;
+    for (int c0 = 0; c0 < ngroups; c0 += 32) {
+        const int i = c0 + lane;
+        const bool have = i < ngroups;
+        const double mg = have ? __ldcg(gm_b + i) : -INFINITY;
+        const double f = (mg == -INFINITY) ? 0.0 : exp(mg - big_m);
+        double inc = have ? __dmul_rn(f, __ldcg(gs_b + i)) : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc = __dadd_rn(y, inc);
+        }
+        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) prev = 0.0;
+        if (have) {
+            grp_f_out[i] = f;
+            grp_off_out[i] = __dadd_rn(carry, prev);
+        }
+        carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, inc, 31));
+    }
+    return Level2{big_m, carry};
+}
 constexpr uint32_t kTagSim = 0u;
 constexpr uint32_t kTagResample = 1u;
 

@@ -88,26 +88,24 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     DPOMP_STAMP(1, 0);
     pdl_wait();
     DPOMP_STAMP(1, 1);
-    const double big_s = a.filt_s[b];
     const int grp = tile / kGroupTiles;
-    const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
-    const double t_off = a.tile_off[(size_t)b * a.ntiles + tile], t_f = a.tile_f[(size_t)b * a.ntiles + tile];
-
     // stage the states of this warp's CHUNK ancestors (coalesced, independent of everything below): the gather then reads
     // shared memory instead of paying a second dependent trip to L2
     {
         const int32_t* src_w = a.pop_src + (size_t)b * a.n_comp * a.n_pad + base_n + warp * CHUNK + lane * ITEMS;
         for (int c = 0; c < a.n_comp; ++c) {
-            if constexpr (ITEMS % 4 == 0) {
+            if constexpr (ITEMS % 4 == 0) {  // 16-byte asynchronous copies global -> shared (no registers, waited for below)
 #pragma unroll
-                for (int k = 0; k < ITEMS; k += 4)
-                    *reinterpret_cast<int4*>(st_dyn + c * TILE + tid * ITEMS + k) =
-                        *reinterpret_cast<const int4*>(src_w + (size_t)c * a.n_pad + k);
+                for (int k = 0; k < ITEMS; k += 4) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(st_dyn + c * TILE + tid * ITEMS + k);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_w + (size_t)c * a.n_pad + k) : "memory");
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < ITEMS; ++k) st_dyn[c * TILE + tid * ITEMS + k] = src_w[(size_t)c * a.n_pad + k];
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     double incl[ITEMS];
     const double* wt = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
@@ -123,13 +121,15 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
         for (int k = 0; k < ITEMS; ++k) incl[k] = wt[k];
     }
 
-    if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel
+    if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel 
+        const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
+        const double t_off = a.tile_off[(size_t)b * a.ntiles + tile], t_f = a.tile_f[(size_t)b * a.ntiles + tile];
         double* cw = a.cw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) cw[k] = tile_cw(g_off, g_f, t_off, t_f, incl[k]);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         return;
     }
-
     const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
                     a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
     DPOMP_STAMP(1, 2);

@@ -87,6 +87,10 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     if (lane == 31) warp_max_s[warp] = inc;
     __syncthreads();  // the only block barrier
     pdl_trigger();
+    // the stand-alone kernel stages the ancestor states with cp.async while the counts above are computed: this thread's
+    // copies are complete after the wait, its warp's after the __syncwarp (a no-op wait in the fused kernel)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 #ifdef DPOMP_PHASE_TIMERS
     if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS && blockIdx.x < 4096) g_dpomp_phase[1][blockIdx.x][3] = dpomp_gtime();
 #endif

@@ -495,37 +495,13 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
     if (last_group) {
     // level 2: groups of the filter -> M, F_g = exp(m_g - M), O_g, S and the log-likelihood increment
-    const double* gm_b = a.grp_m + (size_t)b * a.ngroups;
-    const double* gs_b = a.grp_s + (size_t)b * a.ngroups;
-    double big_m = -INFINITY;
-    for (int i = tid; i < a.ngroups; i += 32) big_m = fmax(big_m, __ldcg(gm_b + i));
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) big_m = fmax(big_m, __shfl_xor_sync(0xffffffffu, big_m, d));
-    double carry = 0.0;
-    for (int c0 = 0; c0 < a.ngroups; c0 += 32) {
-        const int i = c0 + tid;
-        const bool have = i < a.ngroups;
-        const double mg = have ? __ldcg(gm_b + i) : -INFINITY;
-        const double f = (mg == -INFINITY) ? 0.0 : exp(mg - big_m);
-        double inc = have ? __dmul_rn(f, __ldcg(gs_b + i)) : 0.0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, inc, d);
-            if (tid >= d) inc = __dadd_rn(y, inc);
-        }
-        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (tid == 0) prev = 0.0;
-        if (have) {
-            a.grp_f[(size_t)b * a.ngroups + i] = f;
-            a.grp_off[(size_t)b * a.ngroups + i] = __dadd_rn(carry, prev);
-        }
-        carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, inc, 31));
-    }
+    const Level2 l2 = combine_level2(a.grp_m + (size_t)b * a.ngroups, a.grp_s + (size_t)b * a.ngroups, a.ngroups,
+                                     a.grp_f + (size_t)b * a.ngroups, a.grp_off + (size_t)b * a.ngroups);
     if (tid == 0) {
-        a.filt_s[b] = carry;
-        a.filt_m[b] = big_m;
+        a.filt_s[b] = l2.big_s;
+        a.filt_m[b] = l2.big_m;
         // log(cum_weight[end] / N) (:60) as log-sum-exp; one add per kernel and filter, so the RED is deterministic
-        if (a.has_lik) atomicAdd(&a.ll_acc[b], big_m + log(carry / (double)a.n));
+        if (a.has_lik) atomicAdd(&a.ll_acc[b], l2.big_m + log(l2.big_s / (double)a.n));
         a.tile_counter[b] = 0u;
     }
     if constexpr (FUSED) {  // publish the combine to the CTAs of this filter that wait below
