@@ -16,6 +16,7 @@ model = dp.generate_model("LOTKA", [70, 70])
 model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
 y = dp.get_observations("tests/golden/lotka_c4.csv")
 dp.run_ibis_analysis(model, y[:12], np=max(outer_p // 8, 8 * world), npf=npf, seed=7, comm=comm, verbose=False)  # warm-up (CUDA / NCCL init)
+import gc; gc.collect()
 if world > 1:
     torch.distributed.barrier()
 torch.cuda.synchronize()
