@@ -99,6 +99,7 @@ _SIGS = {
     "dpomp_mbp_destroy": (C.c_int, [_P]),
     "dpomp_mbp_set_batch_offset": (C.c_int, [_P, C.c_int64]),
     "dpomp_mbp_set_stream_key": (C.c_int, [_P, C.c_uint64]),
+    "dpomp_mbp_set_mode": (C.c_int, [_P, C.c_int32]),
     "dpomp_mbp_reset": (C.c_int, [_P]),
     "dpomp_mbp_iterate": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "dpomp_mbp_propose": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),

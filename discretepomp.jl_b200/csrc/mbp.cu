@@ -87,18 +87,69 @@ __device__ __forceinline__ double mbp_obs_ll(const MbpModel& m, double ysum, con
     return m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
 }
 
-// iterate_particle! (src/hmm_sim.jl:6-25) for every particle
-__global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant__ MbpModel m, MbpStore st, const double* theta,
-                                                           const double* obs_time, const double* obs_ysum, int n, int cap, int t,
-                                                           int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+// ---- event-list access policies -------------------------------------------------------------------------------------
+// The walks below are written once against an IO policy, so the thread-per-trajectory and the warp-per-trajectory kernels
+// execute literally the same arithmetic in the same order (bit-identical trajectories).
+//   ThreadIO: one thread per trajectory, event lists read / written in HBM directly (many trajectories: throughput).
+//   WarpIO:   one WARP per trajectory; every lane executes the (warp-uniform) walk redundantly, the old event list is
+//             prefetched into shared memory in windows of kMbpWin events with coalesced loads, new events are staged in
+//             shared memory and flushed with coalesced stores (few trajectories: latency -- no divergence between
+//             trajectories, no dependent trip to HBM per event).
+constexpr int kMbpWin = 256;
+constexpr int kMbpWarpsPerCta = 4;
+// trajectories per launch up to which the warp-per-trajectory kernels are used (B200, SIS / pooley.csv, propose call:
+// 16 trajectories 3.3 vs 4.1 ms, 1024: 4.3 vs 5.7 ms, 4096: 7.6 vs 6.4 ms, 16384: 19 vs 7 ms)
+constexpr int kMbpWarpThreshold = 2048;
+struct ThreadIO {
+    const double* it; const unsigned char* iy; int ilen;   // old trajectory (unused by the simulator)
+    double* ft; unsigned char* fy;                          // new trajectory
+    __device__ __forceinline__ double in_time(int e) { return it[e]; }
+    __device__ __forceinline__ int in_type(int e) { return iy[e]; }
+    __device__ __forceinline__ void push(int pos, double t, int type1) { ft[pos] = t; fy[pos] = (unsigned char)type1; }
+    __device__ __forceinline__ void finish(int) {}
+};
+struct WarpIO {
+    const double* it; const unsigned char* iy; int ilen;
+    double* ft; unsigned char* fy;
+    double* s_it; unsigned char* s_iy;   // [kMbpWin] window of the old list: events [ibase, ibase + kMbpWin)
+    double* s_ft; unsigned char* s_fy;   // [kMbpWin] staged new events [fbase, fbase + kMbpWin)
+    int ibase, fbase;
+    __device__ __forceinline__ void load(int start) {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        ibase = start;
+        for (int i = lane; i < kMbpWin && start + i < ilen; i += 32) { s_it[i] = it[start + i]; s_iy[i] = iy[start + i]; }
+        __syncwarp();
+    }
+    __device__ __forceinline__ double in_time(int e) { if (e >= ibase + kMbpWin) load(e); return s_it[e - ibase]; }
+    __device__ __forceinline__ int in_type(int e) { if (e >= ibase + kMbpWin) load(e); return s_iy[e - ibase]; }
+    __device__ __forceinline__ void flush(int upto) {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        for (int i = lane; fbase + i < upto; i += 32) { ft[fbase + i] = s_ft[i]; fy[fbase + i] = s_fy[i]; }
+        __syncwarp();
+        fbase = upto;
+    }
+    __device__ __forceinline__ void push(int pos, double t, int type1) {
+        if (pos - fbase >= kMbpWin) flush(pos);
+        if ((threadIdx.x & 31) == 0) { s_ft[pos - fbase] = t; s_fy[pos - fbase] = (unsigned char)type1; }
+    }
+    __device__ __forceinline__ void finish(int flen) { flush(flen); }
+};
+struct WarpShared {  // per warp
+    double it[kMbpWin], ft[kMbpWin];
+    unsigned char iy[kMbpWin], fy[kMbpWin];
+};
+
+// iterate_particle! (src/hmm_sim.jl:6-25) of particle p; `writer`: this thread stores the particle's scalars
+template <class IO>
+__device__ __forceinline__ void mbp_iterate_body(const MbpModel& m, MbpStore& st, IO& io, int p, bool writer, const double* theta,
+                                                 const double* obs_time, const double* obs_ysum, int cap, int t, int fresh, int has_lik,
+                                                 uint64_t key, uint32_t id0, double* out_logg) {
     const double* th = theta + (size_t)p * m.n_params;
     int x[DPOMP_MAX_COMPARTMENTS];
     for (int c = 0; c < m.n_comp; ++c) x[c] = st.fc[(size_t)p * m.n_comp + c];
     int len = st.len[p];
-    double* et = st.ev_time + (size_t)p * cap;
-    unsigned char* ey = st.ev_type + (size_t)p * cap;
     double time = fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : obs_time[t - 1];
     const double t_obs = obs_time[t];
     MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, (uint32_t)t, 0u);
@@ -115,44 +166,56 @@ __global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant_
         const int e = mbp_choose(cum, m.n_events, u32_open_f64(w.y));
         for (int c = 0; c < m.n_comp; ++c) x[c] += m.trans[e][c];
         if (len >= cap) { overflow = true; break; }
-        et[len] = time;
-        ey[len] = (unsigned char)(e + 1);
+        io.push(len, time, e + 1);
         ++len;
     }
+    io.finish(len);
+    const double out = overflow ? -INFINITY : mbp_obs_ll(m, obs_ysum[t], x);
+    if (!writer) return;
     for (int c = 0; c < m.n_comp; ++c) st.fc[(size_t)p * m.n_comp + c] = x[c];
     st.len[p] = len;
-    double out;
-    if (overflow) {
-        st.ll[2 * (size_t)p] = -INFINITY;
-        out = -INFINITY;
-    } else {
-        out = mbp_obs_ll(m, obs_ysum[t], x);
-        if (has_lik) st.ll[2 * (size_t)p] += out;
-    }
+    if (overflow) st.ll[2 * (size_t)p] = -INFINITY;
+    else if (has_lik) st.ll[2 * (size_t)p] += out;
     out_logg[p] = out;
 }
 
-// partial_model_based_proposal (src/hmm_mbp.jl:83-108): xi = current store, xf = proposal store
-__global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant__ MbpModel m, MbpStore xi, MbpStore xf,
-                                                           const double* theta_i, const double* theta_f, const unsigned char* valid,
-                                                           const double* obs_time, const double* obs_ysum, const int* obs_haslik,
-                                                           int n, int cap, int ymax, uint64_t key, uint32_t id0, double* out_ll) {
+__global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant__ MbpModel m, MbpStore st, const double* theta,
+                                                           const double* obs_time, const double* obs_ysum, int n, int cap, int t,
+                                                           int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    ThreadIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap};
+    mbp_iterate_body(m, st, io, p, true, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
+}
+__global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_iterate_warp_kernel(const __grid_constant__ MbpModel m, MbpStore st,
+                                                           const double* theta, const double* obs_time, const double* obs_ysum, int n,
+                                                           int cap, int t, int fresh, int has_lik, uint64_t key, uint32_t id0,
+                                                           double* out_logg) {
+    __shared__ WarpShared sh[kMbpWarpsPerCta];
+    const int warp = threadIdx.x >> 5, p = blockIdx.x * kMbpWarpsPerCta + warp;
+    if (p >= n) return;
+    WarpShared& w = sh[warp];
+    const int len0 = st.len[p];
+    WarpIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, len0};
+    mbp_iterate_body(m, st, io, p, (threadIdx.x & 31) == 0, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
+}
+
+// partial_model_based_proposal (src/hmm_mbp.jl:83-108): xi = current store (through io), xf = proposal store
+template <class IO>
+__device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf, IO& io, int p, bool writer, bool is_valid,
+                                                 const double* theta_i, const double* theta_f, const double* obs_time,
+                                                 const double* obs_ysum, const int* obs_haslik, int cap, int ymax, uint64_t key,
+                                                 uint32_t id0, double* out_ll) {
     double ll0 = 0.0, ll1 = 0.0;
     int flen = 0;
     int xfc[DPOMP_MAX_COMPARTMENTS], pop_i[DPOMP_MAX_COMPARTMENTS];
     for (int c = 0; c < m.n_comp; ++c) xfc[c] = pop_i[c] = m.ic[c];
-    if (!valid[p]) {
+    if (!is_valid) {
         ll0 = ll1 = -INFINITY;
     } else {
         const double* thi = theta_i + (size_t)p * m.n_params;
         const double* thf = theta_f + (size_t)p * m.n_params;
-        const double* it = xi.ev_time + (size_t)p * cap;
-        const unsigned char* iy = xi.ev_type + (size_t)p * cap;
-        const int ilen = xi.len[p];
-        double* ft = xf.ev_time + (size_t)p * cap;
-        unsigned char* fy = xf.ev_type + (size_t)p * cap;
+        const int ilen = io.ilen;
         MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, 0u, 1u);
         double lf[DPOMP_MAX_EVENTS], li[DPOMP_MAX_EVENTS], ld[DPOMP_MAX_EVENTS];
         const int E = m.n_events;
@@ -172,12 +235,12 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
                     if (t > t0i) break;
                     const int e = mbp_choose(lf, E, u32_open_f64(w.y));
                     if (flen >= cap) { overflow = true; break; }
-                    ft[flen] = t; fy[flen] = (unsigned char)(e + 1); ++flen;
+                    io.push(flen, t, e + 1); ++flen;
                     for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
                 }
             } else {
-                while (evt < ilen && !(it[evt] > t0f)) {
-                    const int e = iy[evt] - 1;
+                while (evt < ilen && !(io.in_time(evt) > t0f)) {
+                    const int e = io.in_type(evt) - 1;
                     for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
                     ++evt;
                 }
@@ -187,7 +250,8 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
         for (int oi = 0; oi < ymax && !overflow; ++oi) {
             const double t_obs = obs_time[oi];
             for (;;) {  // iterate_mbp! (:14-42)
-                const double tmax = (evt >= ilen) ? t_obs : (t_obs < it[evt] ? t_obs : it[evt]);
+                const double t_next = (evt >= ilen) ? INFINITY : io.in_time(evt);
+                const double tmax = (evt >= ilen) ? t_obs : (t_obs < t_next ? t_obs : t_next);
                 mbp_rates(m, thi, pop_i, li);
                 for (;;) {
                     mbp_rates(m, thf, xfc, lf);
@@ -203,13 +267,13 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
                     const int e = mbp_choose(ld, E, u32_open_f64(w.y));
                     for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
                     if (flen >= cap) { overflow = true; break; }
-                    ft[flen] = time; fy[flen] = (unsigned char)(e + 1); ++flen;
+                    io.push(flen, time, e + 1); ++flen;
                 }
                 if (overflow) break;
                 if (evt >= ilen) break;
-                if (it[evt] > t_obs) break;
-                const int e = iy[evt] - 1;
-                time = it[evt];
+                if (t_next > t_obs) break;
+                const int e = io.in_type(evt) - 1;
+                time = t_next;
                 const double prob_keep = __ddiv_rn(lf[e], li[e]);
                 bool keep = prob_keep > 1.0;
                 if (!keep) {
@@ -218,7 +282,7 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
                 }
                 if (keep) {
                     if (flen >= cap) { overflow = true; break; }
-                    ft[flen] = time; fy[flen] = (unsigned char)(e + 1); ++flen;
+                    io.push(flen, time, e + 1); ++flen;
                     for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
                 }
                 for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
@@ -231,12 +295,41 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
         }
         if (overflow) ll0 = -INFINITY;
     }
+    io.finish(flen);
+    if (!writer) return;
     for (int c = 0; c < m.n_comp; ++c) xf.fc[(size_t)p * m.n_comp + c] = xfc[c];
     xf.len[p] = flen;
     xf.ll[2 * (size_t)p] = ll0;
     xf.ll[2 * (size_t)p + 1] = ll1;
     out_ll[2 * (size_t)p] = ll0;
     out_ll[2 * (size_t)p + 1] = ll1;
+}
+
+__global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant__ MbpModel m, MbpStore xi, MbpStore xf,
+                                                           const double* theta_i, const double* theta_f, const unsigned char* valid,
+                                                           const double* obs_time, const double* obs_ysum, const int* obs_haslik,
+                                                           int n, int cap, int ymax, uint64_t key, uint32_t id0, double* out_ll) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    ThreadIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
+                xf.ev_type + (size_t)p * cap};
+    mbp_propose_body(m, xf, io, p, true, valid[p] != 0, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap, ymax, key, id0, out_ll);
+}
+__global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_propose_warp_kernel(const __grid_constant__ MbpModel m, MbpStore xi,
+                                                           MbpStore xf, const double* theta_i, const double* theta_f,
+                                                           const unsigned char* valid, const double* obs_time, const double* obs_ysum,
+                                                           const int* obs_haslik, int n, int cap, int ymax, uint64_t key, uint32_t id0,
+                                                           double* out_ll) {
+    __shared__ WarpShared sh[kMbpWarpsPerCta];
+    const int warp = threadIdx.x >> 5, p = blockIdx.x * kMbpWarpsPerCta + warp;
+    if (p >= n) return;
+    WarpShared& w = sh[warp];
+    WarpIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
+              xf.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, 0};
+    const bool is_valid = valid[p] != 0;
+    if (is_valid) io.load(0);
+    mbp_propose_body(m, xf, io, p, (threadIdx.x & 31) == 0, is_valid, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap, ymax, key,
+                     id0, out_ll);
 }
 
 // dst[dst_slot[k]] <- src[src_slot[k]] : one CTA per particle, only the live part of the trajectory moves
@@ -317,6 +410,7 @@ struct dpomp_mbp {
     MbpModel dm{};
     MbpStore store[3]{};   // [cur], [cur ^ 1] (resample workspace), [2] proposal
     int cur = 0;
+    int mode = 0;          // 0 automatic, 1 one thread per trajectory, 2 one warp per trajectory
     uint64_t seed = 0, call_index = 0, forced_key = 0;
     bool key_forced = false;
     long long batch_offset = 0;
@@ -338,6 +432,8 @@ static uint64_t mbp_next_key(dpomp_mbp* h) {
     h->call_index += 1;
     return k;
 }
+// one warp per trajectory while the warps of a launch fit on the device a few times over, else one thread per trajectory
+static bool mbp_use_warps(const dpomp_mbp* h, int n) { return h->mode == 2 || (h->mode == 0 && n <= kMbpWarpThreshold); }
 static void mbp_free(dpomp_mbp* h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -421,6 +517,11 @@ int dpomp_mbp_set_batch_offset(dpomp_mbp* h, int64_t off) {
     h->batch_offset = off;
     return DPOMP_OK;
 }
+int dpomp_mbp_set_mode(dpomp_mbp* h, int32_t mode) {
+    if (!h || mode < 0 || mode > 2) return dpomp_set_error(DPOMP_ERR_ARG, "mode must be 0 (automatic), 1 (thread) or 2 (warp per trajectory)");
+    h->mode = mode;
+    return DPOMP_OK;
+}
 int dpomp_mbp_set_stream_key(dpomp_mbp* h, uint64_t key) {
     if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "null handle");
     h->forced_key = key; h->key_forced = true;
@@ -442,9 +543,15 @@ int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_
     MCK(cudaSetDevice(h->device));
     const uint64_t key = mbp_next_key(h);
     MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    mbp_iterate_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap,
-                                                               obs_i - 1, fresh ? 1 : 0, h->model->h.obs_id[obs_i - 1] > 0, key,
-                                                               (uint32_t)h->batch_offset, h->out);
+    if (mbp_use_warps(h, n))
+        mbp_iterate_warp_kernel<<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(
+            h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0,
+            h->model->h.obs_id[obs_i - 1] > 0, key, (uint32_t)h->batch_offset, h->out);
+    else
+        mbp_iterate_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n,
+                                                                   h->cap, obs_i - 1, fresh ? 1 : 0,
+                                                                   h->model->h.obs_id[obs_i - 1] > 0, key,
+                                                                   (uint32_t)h->batch_offset, h->out);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));
@@ -462,9 +569,14 @@ int dpomp_mbp_propose(dpomp_mbp* h, const double* theta_i, const double* theta_f
     MCK(cudaMemcpyAsync(h->theta_i, theta_i, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->theta_f, theta_f, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->valid, valid, (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    mbp_propose_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid,
-                                                               h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap, ymax, key,
-                                                               (uint32_t)h->batch_offset, h->out);
+    if (mbp_use_warps(h, n))
+        mbp_propose_warp_kernel<<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(
+            h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid, h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap,
+            ymax, key, (uint32_t)h->batch_offset, h->out);
+    else
+        mbp_propose_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f,
+                                                                   h->valid, h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap, ymax,
+                                                                   key, (uint32_t)h->batch_offset, h->out);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));

@@ -229,6 +229,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     Real tm[S];
     const Real tm0 = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;  // f32: remaining time; f64: absolute time
     uint32_t k[S];
+    uint32_t pc[S];  // first Philox counter word of the lane's particle: (global particle index) ^ A, fixed until the refill
     unsigned long long ev_local = 0, ovf_local = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -237,6 +238,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         q[s] = chunk0 + (slot < CHUNK ? slot : lane);
         tm[s] = tm0;
         k[s] = 0;
+        pc[s] = (uint32_t)(base_n + q[s]) ^ ss.a;
 #pragma unroll
         for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;  // idle lanes: harmless values
     }
@@ -253,7 +255,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                 Real cum[E];
                 cum_rates<Real, C, E, MODEL>(m, par, x[s], cum);
                 const Real rtot = cum[E - 1];
-                const uint2 w = philox2x32_10((uint32_t)(base_n + q[s]) ^ ss.a, k[s] ^ ss.b, ss.k);
+                const uint2 w = philox2x32_10(pc[s], k[s] ^ ss.b, ss.k);
                 // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
                 const Real tmn = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm[s]);
                 const bool capped = k[s] >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
@@ -279,7 +281,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                             fin[s] = true;
                             ovf[s] = true;
                         } else {
-                            const uint2 w = philox2x32_10((uint32_t)(base_n + q[s]) ^ ss.a, k[s] ^ ss.b, ss.k);
+                            const uint2 w = philox2x32_10(pc[s], k[s] ^ ss.b, ss.k);
                             tm[s] = tm[s] - log(u32_open_f64(w.x)) / rtot;  // time -= log(rand()) / R (:23)
                             fin[s] = tm[s] > t_obs;                           // `time > tmax && break` (:24)
                             if (!fin[s]) {
@@ -311,6 +313,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     active[s] = slot < chunk_valid;
                     if (active[s]) {
                         q[s] = chunk0 + slot;
+                        pc[s] = (uint32_t)(base_n + q[s]) ^ ss.a;
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;
                         tm[s] = tm0;

@@ -55,6 +55,10 @@ class MbpParticles:
     def set_batch_offset(self, off: int) -> None:
         _capi.check(_capi.lib().dpomp_mbp_set_batch_offset(self._h, int(off)))
 
+    def set_mode(self, mode: int) -> None:
+        """Trajectory walks: 0 automatic, 1 one thread per trajectory, 2 one warp per trajectory (identical results)."""
+        _capi.check(_capi.lib().dpomp_mbp_set_mode(self._h, int(mode)))
+
     def reset(self) -> None:
         _capi.check(_capi.lib().dpomp_mbp_reset(self._h))
 

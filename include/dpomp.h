@@ -186,6 +186,9 @@ int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_
 int dpomp_mbp_destroy(dpomp_mbp* mbp);
 int dpomp_mbp_set_batch_offset(dpomp_mbp* mbp, int64_t batch_offset);  /* global id of local particle 0 */
 int dpomp_mbp_set_stream_key(dpomp_mbp* mbp, uint64_t key);            /* Philox key of the NEXT call */
+int dpomp_mbp_set_mode(dpomp_mbp* mbp, int32_t mode);                  /* trajectory walks: (0) automatic, 1 one thread per trajectory
+                                                                         (throughput, many trajectories), 2 one warp per trajectory (latency,
+                                                                         up to a few thousand); identical results */
 int dpomp_mbp_reset(dpomp_mbp* mbp);  /* every particle back to the initial condition, empty trajectory, log_like = 0 */
 /* iterate_particle! (src/hmm_sim.jl:6-25) for particles 1..n up to observation obs_i (1-based); theta is n_params x n
  * column-major; fresh != 0 starts at t = 0 / theta[t0_index], else at the previous observation time.

@@ -13,7 +13,7 @@ def timed(cls, name):
         t = time.perf_counter(); r = f(self, *a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t; return r
     setattr(cls, name, g)
 for nm in ("propose", "accept", "iterate", "set_stream_key"): timed(dp.MbpParticles, nm)
-for n in (16, 1024, 16384):
+for n in (16, 1024, 4096, 16384):
     acc.clear()
     th0 = np.array([0.003, 0.1])[:, None] * np.random.default_rng(1).uniform(0.8, 1.2, size=(2, n))
     steps = 200
@@ -21,7 +21,12 @@ for n in (16, 1024, 16384):
     print("  host-side split (s):", {k: round(v, 3) for k, v in acc.items()}, "total", round(dt, 3))
     pt = r.particles
     th = th0.copy()
-    t = time.time()
-    for _ in range(20): pt.propose(th, th * 1.01, np.ones(n, dtype=bool), len(y))
-    dp_ = (time.time() - t) / 20
-    print(f"chains {n}: {1e3*dt/steps:.2f} ms per MCMC step ({n*steps/dt:.3e} chain-steps/s); propose call alone {1e3*dp_:.2f} ms")
+    per_mode = []
+    for mode in (1, 2):
+        pt.set_mode(mode)
+        pt.propose(th, th * 1.01, np.ones(n, dtype=bool), len(y))
+        t = time.time()
+        for _ in range(20): pt.propose(th, th * 1.01, np.ones(n, dtype=bool), len(y))
+        per_mode.append((time.time() - t) / 20)
+    print(f"chains {n}: {1e3*dt/steps:.2f} ms per MCMC step ({n*steps/dt:.3e} chain-steps/s); propose call alone: "
+          f"thread per trajectory {1e3*per_mode[0]:.2f} ms, warp per trajectory {1e3*per_mode[1]:.2f} ms")

@@ -239,3 +239,41 @@ def test_run_mcmc_analysis_default_algorithm_posterior(dp):
     assert r2.samples.theta.shape == (2, 50, 3) and r2.adapt_period == 10
     with pytest.raises(NotImplementedError):
         dp.run_mcmc_analysis(model, y, mbp=False)
+
+
+@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False)])
+def test_warp_and_thread_per_trajectory_kernels_are_identical(dp, case, t0):
+    """dpomp_mbp_set_mode: the warp-per-trajectory kernels (shared-memory windows of the event lists) and the
+    thread-per-trajectory kernels execute the same walk -- trajectories, states and log-likelihoods bit for bit, including a
+    tiny event capacity (overflow) and event lists longer than one window."""
+    model, y, hmm, theta = _setup(dp, case, t0)
+    dm = dp.device_model(hmm)
+    rng = np.random.default_rng(4)
+    for n, cap in ((70, 4096), (33, 40)):
+        thetas = theta[:, None] * rng.uniform(0.8, 1.25, size=(len(theta), n))
+        if t0:
+            thetas[2] = rng.uniform(1.0, 8.0, n)
+        theta_f = thetas * rng.uniform(0.85, 1.2, size=thetas.shape)
+        valid = np.ones(n, dtype=bool); valid[3] = False
+        res = []
+        for mode in (1, 2):
+            pt = dp.MbpParticles(dm, n, cap, seed=5)
+            pt.set_mode(mode)
+            lg = []
+            for obs_i in range(1, len(y) + 1 if cap > 100 else 3):
+                pt.set_stream_key(9000 + obs_i)
+                lg.append(pt.iterate(thetas, obs_i, fresh=(obs_i == 1)))
+            pt.set_stream_key(777)
+            ll_f = pt.propose(thetas, theta_f, valid, len(lg))
+            cur = [pt.get_particle(p + 1) for p in range(n)]
+            prop = [pt.get_particle(p + 1, proposal=True) for p in range(n) if valid[p]]
+            res.append((np.array(lg), ll_f, cur, prop))
+        a, b = res
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True)
+        for u, v in zip(a[2] + a[3], b[2] + b[3]):
+            assert all(np.array_equal(x, z, equal_nan=True) for x, z in zip(u, v))
+        if cap > 100:
+            if case == "sis_pooley":
+                assert max(len(c[1]) for c in a[2]) > 256  # event lists longer than one shared-memory window
+        else:
+            assert np.isneginf(a[0]).any()  # the tiny capacity overflows
