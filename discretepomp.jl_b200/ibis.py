@@ -205,7 +205,9 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
     ess_crit = ess_rs_crit * outer_p
     w = np.ones(outer_p)
     aw = prior_logpdf_columns(model.prior, theta)
+    t_setup = time.perf_counter()
     bank = FilterBank(model, outer_p, np_, comm, seed, pf_factory)
+    bank.timers["setup_alloc"] = time.perf_counter() - t_setup
     k_log = np.zeros(2, dtype=np.int64)
     bme = np.zeros(2)
     propd = ProposalDensity.identity(theta.shape[0])
