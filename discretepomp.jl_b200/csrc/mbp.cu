@@ -20,6 +20,7 @@
 
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
+#include "dpomp_models.cuh"
 
 namespace dpomp {
 
@@ -57,32 +58,92 @@ __device__ __forceinline__ uint2 mbp_draw(MbpStream& s) {
     return w;
 }
 
-__device__ __forceinline__ void mbp_rates(const MbpModel& m, const double* th, const int* x, double* out) {
-    for (int e = 0; e < m.n_events; ++e) {
-        long long l1 = m.k1[e], l2 = m.k2[e], dn = m.kd[e];
-        for (int c = 0; c < m.n_comp; ++c) {
-            l1 += (long long)m.f1[e][c] * x[c];
-            l2 += (long long)m.f2[e][c] * x[c];
-            dn += (long long)m.dn[e][c] * x[c];
-        }
-        const double p = m.par[e] >= 0 ? th[m.par[e]] : 1.0;
-        double r = __dmul_rn(__dmul_rn(p, (double)l1), (double)l2);
-        if (m.has_den[e]) r = (dn == 0) ? 0.0 : __ddiv_rn(r, (double)dn);
-        out[e] = r;
+// ---- rate policies ----------------------------------------------------------------------------------------------------
+// MbpRates<kModelGeneric>: the integer rate table with run-time C / E (any model the table compiler accepts).
+// MbpRates<ID>: a predefined model with compile-time structure -- loops unroll, states and rates stay in registers, and
+// rate[e] = (theta[e] * x_a) * x_b is the same f64 expression the table evaluates (l1 = x_a, l2 = x_b or 1 exactly), so both
+// give bit-identical walks; a walk is one dependent instruction chain, so its length is what the kernels' time is made of.
+template <int MODEL>
+struct MbpRates {
+    using BM = Builtin<MODEL>;
+    static constexpr int C = BM::C, E = BM::E, CMAX = BM::C, EMAX = BM::E, PMAX = BM::E;  // parameter e drives event e
+    static __device__ __forceinline__ void load_params(const MbpModel&, const double* src, double (&th)[PMAX]) {
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) th[i] = src[i];
     }
-}
-__device__ __forceinline__ void mbp_cumsum(double* v, int n) {
+    static __device__ __forceinline__ void rates(const MbpModel&, const double (&th)[PMAX], const int (&x)[CMAX], double (&out)[EMAX]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double r = __dmul_rn(th[e], (double)x[BM::A(e)]);
+            r = __dmul_rn(r, BM::B(e) >= 0 ? (double)x[BM::B(e) >= 0 ? BM::B(e) : 0] : 1.0);
+            out[e] = r;
+        }
+    }
+    static __device__ __forceinline__ void apply(const MbpModel&, int e, int (&x)[CMAX]) {
+#pragma unroll
+        for (int i = 0; i < E; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] += (e == i) ? BM::T(i, c) : 0;
+    }
+    static __device__ __forceinline__ double pick(const double (&v)[EMAX], int e) {
+        double r = v[0];
+#pragma unroll
+        for (int i = 1; i < E; ++i) r = (e == i) ? v[i] : r;
+        return r;
+    }
+};
+template <>
+struct MbpRates<kModelGeneric> {
+    static constexpr int C = 0, E = 0, CMAX = DPOMP_MAX_COMPARTMENTS, EMAX = DPOMP_MAX_EVENTS, PMAX = DPOMP_MAX_PARAMS;
+    static __device__ __forceinline__ void load_params(const MbpModel& m, const double* src, double (&th)[PMAX]) {
+        for (int i = 0; i < m.n_params; ++i) th[i] = src[i];
+    }
+    static __device__ __forceinline__ void rates(const MbpModel& m, const double (&th)[PMAX], const int (&x)[CMAX], double (&out)[EMAX]) {
+        for (int e = 0; e < m.n_events; ++e) {
+            long long l1 = m.k1[e], l2 = m.k2[e], dn = m.kd[e];
+            for (int c = 0; c < m.n_comp; ++c) {
+                l1 += (long long)m.f1[e][c] * x[c];
+                l2 += (long long)m.f2[e][c] * x[c];
+                dn += (long long)m.dn[e][c] * x[c];
+            }
+            const double p = m.par[e] >= 0 ? th[m.par[e]] : 1.0;
+            double r = __dmul_rn(__dmul_rn(p, (double)l1), (double)l2);
+            if (m.has_den[e]) r = (dn == 0) ? 0.0 : __ddiv_rn(r, (double)dn);
+            out[e] = r;
+        }
+    }
+    static __device__ __forceinline__ void apply(const MbpModel& m, int e, int (&x)[CMAX]) {
+        for (int c = 0; c < m.n_comp; ++c) x[c] += m.trans[e][c];
+    }
+    static __device__ __forceinline__ double pick(const double (&v)[EMAX], int e) { return v[e]; }
+};
+template <class R> __device__ __forceinline__ int mbp_nc(const MbpModel& m) { if constexpr (R::C > 0) return R::C; else return m.n_comp; }
+template <class R> __device__ __forceinline__ int mbp_ne(const MbpModel& m) { if constexpr (R::E > 0) return R::E; else return m.n_events; }
+
+template <class R>
+__device__ __forceinline__ void mbp_cumsum(const MbpModel& m, double (&v)[R::EMAX]) {
+    const int n = mbp_ne<R>(m);
+#pragma unroll
     for (int i = 1; i < n; ++i) v[i] = __dadd_rn(v[i - 1], v[i]);
 }
-__device__ __forceinline__ int mbp_choose(const double* cum, int n, double u) {
-    const double etc = __dmul_rn(u, cum[n - 1]);
-    for (int i = 0; i < n - 1; ++i)
-        if (cum[i] > etc) return i;
-    return n - 1;
+// choose_event (src/hmm_cmn.jl:4-10): first i < E - 1 with cum[i] > etc, else the last event (0-based)
+template <class R>
+__device__ __forceinline__ int mbp_choose(const MbpModel& m, const double (&cum)[R::EMAX], double u) {
+    const int n = mbp_ne<R>(m);
+    const double etc = __dmul_rn(u, R::pick(cum, n - 1));
+    int e = n - 1;
+#pragma unroll
+    for (int i = R::EMAX - 2; i >= 0; --i)
+        if (i < n - 1 && cum[i] > etc) e = i;
+    return e;
 }
-__device__ __forceinline__ double mbp_obs_ll(const MbpModel& m, double ysum, const int* x) {
+template <class R>
+__device__ __forceinline__ double mbp_obs_ll(const MbpModel& m, double ysum, const int (&x)[R::CMAX]) {
+    const int nc = mbp_nc<R>(m);
     long long xs = 0;
-    for (int c = 0; c < m.n_comp; ++c) xs += (long long)m.xmask[c] * x[c];
+#pragma unroll
+    for (int c = 0; c < R::CMAX; ++c)
+        if (c < nc) xs += (long long)m.xmask[c] * x[c];
     const double d = ysum - (double)xs;
     return m.obs_tmp1 - __ddiv_rn(__dmul_rn(d, d), m.obs_tmp2);
 }
@@ -97,8 +158,8 @@ __device__ __forceinline__ double mbp_obs_ll(const MbpModel& m, double ysum, con
 //             trajectories, no dependent trip to HBM per event).
 constexpr int kMbpWin = 256;
 constexpr int kMbpWarpsPerCta = 4;
-// trajectories per launch up to which the warp-per-trajectory kernels are used (B200, SIS / pooley.csv, propose call:
-// 16 trajectories 3.3 vs 4.1 ms, 1024: 4.3 vs 5.7 ms, 4096: 7.6 vs 6.4 ms, 16384: 19 vs 7 ms)
+// trajectories per launch up to which the warp-per-trajectory kernels are used (B200, SIS / pooley.csv, propose call,
+// warp vs thread per trajectory: 16 trajectories 1.04 vs 1.43 ms, 1024: 1.37 vs 1.96 ms, 4096: 2.53 vs 2.21 ms, 16384: 7.1 vs 2.9 ms)
 constexpr int kMbpWarpThreshold = 2048;
 struct ThreadIO {
     const double* it; const unsigned char* iy; int ilen;   // old trajectory (unused by the simulator)
@@ -142,51 +203,59 @@ struct WarpShared {  // per warp
 };
 
 // iterate_particle! (src/hmm_sim.jl:6-25) of particle p; `writer`: this thread stores the particle's scalars
-template <class IO>
+template <class IO, class R>
 __device__ __forceinline__ void mbp_iterate_body(const MbpModel& m, MbpStore& st, IO& io, int p, bool writer, const double* theta,
                                                  const double* obs_time, const double* obs_ysum, int cap, int t, int fresh, int has_lik,
                                                  uint64_t key, uint32_t id0, double* out_logg) {
-    const double* th = theta + (size_t)p * m.n_params;
-    int x[DPOMP_MAX_COMPARTMENTS];
-    for (int c = 0; c < m.n_comp; ++c) x[c] = st.fc[(size_t)p * m.n_comp + c];
+    const int nc = mbp_nc<R>(m), ne = mbp_ne<R>(m);
+    const double* thp = theta + (size_t)p * m.n_params;
+    double th[R::PMAX];
+    R::load_params(m, thp, th);
+    int x[R::CMAX];
+#pragma unroll
+    for (int c = 0; c < R::CMAX; ++c) x[c] = (c < nc) ? st.fc[(size_t)p * nc + c] : 0;
     int len = st.len[p];
-    double time = fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : obs_time[t - 1];
+    double time = fresh ? (m.t0_index > 0 ? thp[m.t0_index - 1] : 0.0) : obs_time[t - 1];
     const double t_obs = obs_time[t];
     MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, (uint32_t)t, 0u);
-    double cum[DPOMP_MAX_EVENTS];
+    double cum[R::EMAX];
     bool overflow = false;
     for (;;) {
-        mbp_rates(m, th, x, cum);
-        mbp_cumsum(cum, m.n_events);
-        const double tot = cum[m.n_events - 1];
+        R::rates(m, th, x, cum);
+        mbp_cumsum<R>(m, cum);
+        const double tot = R::pick(cum, ne - 1);
         if (!(tot > 0.0)) break;
         const uint2 w = mbp_draw(rs);
         time = time - log(u32_open_f64(w.x)) / tot;
         if (time > t_obs) break;
-        const int e = mbp_choose(cum, m.n_events, u32_open_f64(w.y));
-        for (int c = 0; c < m.n_comp; ++c) x[c] += m.trans[e][c];
+        const int e = mbp_choose<R>(m, cum, u32_open_f64(w.y));
+        R::apply(m, e, x);
         if (len >= cap) { overflow = true; break; }
         io.push(len, time, e + 1);
         ++len;
     }
     io.finish(len);
-    const double out = overflow ? -INFINITY : mbp_obs_ll(m, obs_ysum[t], x);
+    const double out = overflow ? -INFINITY : mbp_obs_ll<R>(m, obs_ysum[t], x);
     if (!writer) return;
-    for (int c = 0; c < m.n_comp; ++c) st.fc[(size_t)p * m.n_comp + c] = x[c];
+#pragma unroll
+    for (int c = 0; c < R::CMAX; ++c)
+        if (c < nc) st.fc[(size_t)p * nc + c] = x[c];
     st.len[p] = len;
     if (overflow) st.ll[2 * (size_t)p] = -INFINITY;
     else if (has_lik) st.ll[2 * (size_t)p] += out;
     out_logg[p] = out;
 }
 
+template <int MODEL>
 __global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant__ MbpModel m, MbpStore st, const double* theta,
                                                            const double* obs_time, const double* obs_ysum, int n, int cap, int t,
                                                            int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     ThreadIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap};
-    mbp_iterate_body(m, st, io, p, true, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
+    mbp_iterate_body<ThreadIO, MbpRates<MODEL>>(m, st, io, p, true, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
 }
+template <int MODEL>
 __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_iterate_warp_kernel(const __grid_constant__ MbpModel m, MbpStore st,
                                                            const double* theta, const double* obs_time, const double* obs_ysum, int n,
                                                            int cap, int t, int fresh, int has_lik, uint64_t key, uint32_t id0,
@@ -197,51 +266,54 @@ __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_iterate_warp_kernel(
     WarpShared& w = sh[warp];
     const int len0 = st.len[p];
     WarpIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, len0};
-    mbp_iterate_body(m, st, io, p, (threadIdx.x & 31) == 0, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
+    mbp_iterate_body<WarpIO, MbpRates<MODEL>>(m, st, io, p, (threadIdx.x & 31) == 0, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key,
+                                              id0, out_logg);
 }
 
 // partial_model_based_proposal (src/hmm_mbp.jl:83-108): xi = current store (through io), xf = proposal store
-template <class IO>
+template <class IO, class R>
 __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf, IO& io, int p, bool writer, bool is_valid,
                                                  const double* theta_i, const double* theta_f, const double* obs_time,
                                                  const double* obs_ysum, const int* obs_haslik, int cap, int ymax, uint64_t key,
                                                  uint32_t id0, double* out_ll) {
+    const int nc = mbp_nc<R>(m), ne = mbp_ne<R>(m);
     double ll0 = 0.0, ll1 = 0.0;
     int flen = 0;
-    int xfc[DPOMP_MAX_COMPARTMENTS], pop_i[DPOMP_MAX_COMPARTMENTS];
-    for (int c = 0; c < m.n_comp; ++c) xfc[c] = pop_i[c] = m.ic[c];
+    int xfc[R::CMAX], pop_i[R::CMAX];
+#pragma unroll
+    for (int c = 0; c < R::CMAX; ++c) xfc[c] = pop_i[c] = (c < nc) ? m.ic[c] : 0;
     if (!is_valid) {
         ll0 = ll1 = -INFINITY;
     } else {
-        const double* thi = theta_i + (size_t)p * m.n_params;
-        const double* thf = theta_f + (size_t)p * m.n_params;
+        double thi[R::PMAX], thf[R::PMAX];
+        R::load_params(m, theta_i + (size_t)p * m.n_params, thi);
+        R::load_params(m, theta_f + (size_t)p * m.n_params, thf);
         const int ilen = io.ilen;
         MbpStream rs = mbp_stream_init(key, id0 + (uint32_t)p, 0u, 1u);
-        double lf[DPOMP_MAX_EVENTS], li[DPOMP_MAX_EVENTS], ld[DPOMP_MAX_EVENTS];
-        const int E = m.n_events;
+        double lf[R::EMAX], li[R::EMAX], ld[R::EMAX];
         int evt = 0;
         double time = 0.0;
         bool overflow = false;
         if (m.t0_index > 0) {  // initialise_trajectory! (:47-80)
-            const double t0f = thf[m.t0_index - 1], t0i = thi[m.t0_index - 1];
+            const double t0f = theta_f[(size_t)p * m.n_params + m.t0_index - 1], t0i = theta_i[(size_t)p * m.n_params + m.t0_index - 1];
             if (t0f < t0i) {
                 double t = t0f;
                 for (;;) {
-                    mbp_rates(m, thf, xfc, lf);
-                    mbp_cumsum(lf, E);
-                    if (!(lf[E - 1] > 0.0)) break;
+                    R::rates(m, thf, xfc, lf);
+                    mbp_cumsum<R>(m, lf);
+                    const double tot = R::pick(lf, ne - 1);
+                    if (!(tot > 0.0)) break;
                     const uint2 w = mbp_draw(rs);
-                    t = t - log(u32_open_f64(w.x)) / lf[E - 1];
+                    t = t - log(u32_open_f64(w.x)) / tot;
                     if (t > t0i) break;
-                    const int e = mbp_choose(lf, E, u32_open_f64(w.y));
+                    const int e = mbp_choose<R>(m, lf, u32_open_f64(w.y));
                     if (flen >= cap) { overflow = true; break; }
                     io.push(flen, t, e + 1); ++flen;
-                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                    R::apply(m, e, xfc);
                 }
             } else {
                 while (evt < ilen && !(io.in_time(evt) > t0f)) {
-                    const int e = io.in_type(evt) - 1;
-                    for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
+                    R::apply(m, io.in_type(evt) - 1, pop_i);
                     ++evt;
                 }
             }
@@ -252,20 +324,24 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
             for (;;) {  // iterate_mbp! (:14-42)
                 const double t_next = (evt >= ilen) ? INFINITY : io.in_time(evt);
                 const double tmax = (evt >= ilen) ? t_obs : (t_obs < t_next ? t_obs : t_next);
-                mbp_rates(m, thi, pop_i, li);
+                R::rates(m, thi, pop_i, li);
                 for (;;) {
-                    mbp_rates(m, thf, xfc, lf);
-                    for (int e = 0; e < E; ++e) {
-                        const double dlt = __dsub_rn(lf[e], li[e]);
-                        ld[e] = dlt > 0.0 ? dlt : 0.0;
+                    R::rates(m, thf, xfc, lf);
+#pragma unroll
+                    for (int e = 0; e < R::EMAX; ++e) {
+                        if (e < ne) {
+                            const double dlt = __dsub_rn(lf[e], li[e]);
+                            ld[e] = dlt > 0.0 ? dlt : 0.0;
+                        }
                     }
-                    mbp_cumsum(ld, E);
-                    if (!(ld[E - 1] > 0.0)) break;
+                    mbp_cumsum<R>(m, ld);
+                    const double tot = R::pick(ld, ne - 1);
+                    if (!(tot > 0.0)) break;
                     const uint2 w = mbp_draw(rs);
-                    time = time - log(u32_open_f64(w.x)) / ld[E - 1];
+                    time = time - log(u32_open_f64(w.x)) / tot;
                     if (time > tmax) break;
-                    const int e = mbp_choose(ld, E, u32_open_f64(w.y));
-                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                    const int e = mbp_choose<R>(m, ld, u32_open_f64(w.y));
+                    R::apply(m, e, xfc);
                     if (flen >= cap) { overflow = true; break; }
                     io.push(flen, time, e + 1); ++flen;
                 }
@@ -274,7 +350,7 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
                 if (t_next > t_obs) break;
                 const int e = io.in_type(evt) - 1;
                 time = t_next;
-                const double prob_keep = __ddiv_rn(lf[e], li[e]);
+                const double prob_keep = __ddiv_rn(R::pick(lf, e), R::pick(li, e));
                 bool keep = prob_keep > 1.0;
                 if (!keep) {
                     const uint2 w = mbp_draw(rs);
@@ -283,21 +359,23 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
                 if (keep) {
                     if (flen >= cap) { overflow = true; break; }
                     io.push(flen, time, e + 1); ++flen;
-                    for (int c = 0; c < m.n_comp; ++c) xfc[c] += m.trans[e][c];
+                    R::apply(m, e, xfc);
                 }
-                for (int c = 0; c < m.n_comp; ++c) pop_i[c] += m.trans[e][c];
+                R::apply(m, e, pop_i);
                 ++evt;
             }
             if (overflow) break;
             time = t_obs;
-            ll1 = mbp_obs_ll(m, obs_ysum[oi], xfc);
+            ll1 = mbp_obs_ll<R>(m, obs_ysum[oi], xfc);
             if (obs_haslik[oi]) ll0 += ll1;
         }
         if (overflow) ll0 = -INFINITY;
     }
     io.finish(flen);
     if (!writer) return;
-    for (int c = 0; c < m.n_comp; ++c) xf.fc[(size_t)p * m.n_comp + c] = xfc[c];
+#pragma unroll
+    for (int c = 0; c < R::CMAX; ++c)
+        if (c < nc) xf.fc[(size_t)p * nc + c] = xfc[c];
     xf.len[p] = flen;
     xf.ll[2 * (size_t)p] = ll0;
     xf.ll[2 * (size_t)p + 1] = ll1;
@@ -305,6 +383,7 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
     out_ll[2 * (size_t)p + 1] = ll1;
 }
 
+template <int MODEL>
 __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant__ MbpModel m, MbpStore xi, MbpStore xf,
                                                            const double* theta_i, const double* theta_f, const unsigned char* valid,
                                                            const double* obs_time, const double* obs_ysum, const int* obs_haslik,
@@ -313,8 +392,10 @@ __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant_
     if (p >= n) return;
     ThreadIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
                 xf.ev_type + (size_t)p * cap};
-    mbp_propose_body(m, xf, io, p, true, valid[p] != 0, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap, ymax, key, id0, out_ll);
+    mbp_propose_body<ThreadIO, MbpRates<MODEL>>(m, xf, io, p, true, valid[p] != 0, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap,
+                                                ymax, key, id0, out_ll);
 }
+template <int MODEL>
 __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_propose_warp_kernel(const __grid_constant__ MbpModel m, MbpStore xi,
                                                            MbpStore xf, const double* theta_i, const double* theta_f,
                                                            const unsigned char* valid, const double* obs_time, const double* obs_ysum,
@@ -328,8 +409,8 @@ __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_propose_warp_kernel(
               xf.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, 0};
     const bool is_valid = valid[p] != 0;
     if (is_valid) io.load(0);
-    mbp_propose_body(m, xf, io, p, (threadIdx.x & 31) == 0, is_valid, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap, ymax, key,
-                     id0, out_ll);
+    mbp_propose_body<WarpIO, MbpRates<MODEL>>(m, xf, io, p, (threadIdx.x & 31) == 0, is_valid, theta_i, theta_f, obs_time, obs_ysum,
+                                              obs_haslik, cap, ymax, key, id0, out_ll);
 }
 
 // dst[dst_slot[k]] <- src[src_slot[k]] : one CTA per particle, only the live part of the trajectory moves
@@ -411,6 +492,7 @@ struct dpomp_mbp {
     MbpStore store[3]{};   // [cur], [cur ^ 1] (resample workspace), [2] proposal
     int cur = 0;
     int mode = 0;          // 0 automatic, 1 one thread per trajectory, 2 one warp per trajectory
+    int model_id = 0;      // predefined model with compile-time structure (dpomp_models.cuh), 0 = generic rate table
     uint64_t seed = 0, call_index = 0, forced_key = 0;
     bool key_forced = false;
     long long batch_offset = 0;
@@ -432,6 +514,8 @@ static uint64_t mbp_next_key(dpomp_mbp* h) {
     h->call_index += 1;
     return k;
 }
+// the kernels are instantiated for the generic rate table and for every predefined model
+#define DPOMP_MBP_MODELS(X) X(kModelGeneric) X(kModelSI) X(kModelSIR) X(kModelSIS) X(kModelSEI) X(kModelSEIR) X(kModelSEIS) X(kModelLOTKA)
 // one warp per trajectory while the warps of a launch fit on the device a few times over, else one thread per trajectory
 static bool mbp_use_warps(const dpomp_mbp* h, int n) { return h->mode == 2 || (h->mode == 0 && n <= kMbpWarpThreshold); }
 static void mbp_free(dpomp_mbp* h) {
@@ -466,6 +550,7 @@ int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_
     h->model = model; h->device = device; h->n = n_particles; h->cap = max_traj; h->seed = seed;
     MbpModel& m = h->dm;
     m.n_comp = d.n_compartments; m.n_events = d.n_events; m.n_params = d.n_params; m.t0_index = d.t0_index;
+    h->model_id = builtin_model_id(d);
     for (int ev = 0; ev < DPOMP_MAX_EVENTS; ++ev) {
         m.par[ev] = d.rate_par[ev]; m.k1[ev] = d.rate_k1[ev]; m.k2[ev] = d.rate_k2[ev]; m.kd[ev] = d.rate_kd[ev];
         m.has_den[ev] = d.rate_has_den[ev];
@@ -543,15 +628,21 @@ int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_
     MCK(cudaSetDevice(h->device));
     const uint64_t key = mbp_next_key(h);
     MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (mbp_use_warps(h, n))
-        mbp_iterate_warp_kernel<<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(
-            h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0,
-            h->model->h.obs_id[obs_i - 1] > 0, key, (uint32_t)h->batch_offset, h->out);
-    else
-        mbp_iterate_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n,
-                                                                   h->cap, obs_i - 1, fresh ? 1 : 0,
-                                                                   h->model->h.obs_id[obs_i - 1] > 0, key,
-                                                                   (uint32_t)h->batch_offset, h->out);
+    const bool warps = mbp_use_warps(h, n);
+    const int has_lik = h->model->h.obs_id[obs_i - 1] > 0;
+#define DPOMP_MBP_ITERATE(ID)                                                                                                  \
+    if (h->model_id == ID) {                                                                                                   \
+        if (warps)                                                                                                             \
+            mbp_iterate_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
+                h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0, has_lik,   \
+                key, (uint32_t)h->batch_offset, h->out);                                                                       \
+        else                                                                                                                   \
+            mbp_iterate_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time,   \
+                                                                           h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0,   \
+                                                                           has_lik, key, (uint32_t)h->batch_offset, h->out);   \
+    }
+    DPOMP_MBP_MODELS(DPOMP_MBP_ITERATE)
+#undef DPOMP_MBP_ITERATE
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));
@@ -569,14 +660,21 @@ int dpomp_mbp_propose(dpomp_mbp* h, const double* theta_i, const double* theta_f
     MCK(cudaMemcpyAsync(h->theta_i, theta_i, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->theta_f, theta_f, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->valid, valid, (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    if (mbp_use_warps(h, n))
-        mbp_propose_warp_kernel<<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(
-            h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid, h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap,
-            ymax, key, (uint32_t)h->batch_offset, h->out);
-    else
-        mbp_propose_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f,
-                                                                   h->valid, h->obs_time, h->obs_ysum, h->obs_haslik, n, h->cap, ymax,
-                                                                   key, (uint32_t)h->batch_offset, h->out);
+    const bool warps = mbp_use_warps(h, n);
+#define DPOMP_MBP_PROPOSE(ID)                                                                                                  \
+    if (h->model_id == ID) {                                                                                                   \
+        if (warps)                                                                                                             \
+            mbp_propose_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
+                h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid, h->obs_time, h->obs_ysum,              \
+                h->obs_haslik, n, h->cap, ymax, key, (uint32_t)h->batch_offset, h->out);                                       \
+        else                                                                                                                   \
+            mbp_propose_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i,   \
+                                                                           h->theta_f, h->valid, h->obs_time, h->obs_ysum,     \
+                                                                           h->obs_haslik, n, h->cap, ymax, key,                \
+                                                                           (uint32_t)h->batch_offset, h->out);                 \
+    }
+    DPOMP_MBP_MODELS(DPOMP_MBP_PROPOSE)
+#undef DPOMP_MBP_PROPOSE
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));

@@ -19,9 +19,19 @@ def _setup(dp, case="sis_pooley", t0=False):
     return model, y, hmm, theta
 
 
-@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False)])
+def _setup_any(dp, case, t0):
+    """_setup plus "sis_freq": the frequency-dependent SIS model (src/hmm_examples.jl:126-131), whose rate table has
+    denominators and therefore runs the generic (run-time table) trajectory kernels instead of a predefined-model instantiation."""
+    if case != "sis_freq":
+        return _setup(dp, case, t0)
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    model = dp.generate_model("SIS", [100, 1], freq_dep=True)
+    return model, y, dp.get_private_model(model, y), np.array([0.3, 0.1])
+
+
+@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False), ("sis_freq", False)])
 def test_iterate_and_propose_match_oracle(dp, orc, case, t0):
-    model, y, hmm, theta = _setup(dp, case, t0)
+    model, y, hmm, theta = _setup_any(dp, case, t0)
     dm = dp.device_model(hmm)
     desc = dm.compiled.desc
     n, cap = 64, 4096
@@ -241,12 +251,12 @@ def test_run_mcmc_analysis_default_algorithm_posterior(dp):
         dp.run_mcmc_analysis(model, y, mbp=False)
 
 
-@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False)])
+@pytest.mark.parametrize("case,t0", [("sis_pooley", False), ("sis_pooley", True), ("seir_c3", False), ("sis_freq", False)])
 def test_warp_and_thread_per_trajectory_kernels_are_identical(dp, case, t0):
     """dpomp_mbp_set_mode: the warp-per-trajectory kernels (shared-memory windows of the event lists) and the
     thread-per-trajectory kernels execute the same walk -- trajectories, states and log-likelihoods bit for bit, including a
     tiny event capacity (overflow) and event lists longer than one window."""
-    model, y, hmm, theta = _setup(dp, case, t0)
+    model, y, hmm, theta = _setup_any(dp, case, t0)
     dm = dp.device_model(hmm)
     rng = np.random.default_rng(4)
     for n, cap in ((70, 4096), (33, 40)):
