@@ -301,3 +301,40 @@ def test_fused_step_kernel_equals_two_kernel_path(dp, case, n, nb, f64, rs_type)
     assert np.array_equal(ll_a, ll_b) and np.array_equal(anc_a, anc_b)
     assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
     assert launches_a < launches_b  # one launch per resampling observation instead of two
+
+
+@pytest.mark.parametrize("variant", ["wide_spread", "huge_observation", "tiny_sigma"])
+def test_weight_pass_paths_are_bit_exact_against_oracle(dp, orc, variant):
+    """The integer-domain weight pass of the simulate kernel (tile maximum by integer min, per-CTA exp table indexed by
+    |y - x| - d_min) against the oracle's direct f64 evaluation, on the paths beside the table: offsets beyond its 128
+    entries (population 1000: |y - x| spreads over hundreds), observations >= 2^30 (the direct f64 path), and a sigma for
+    which 2 sigma^2 is not a power of two (the f64 division instead of the multiplication)."""
+    if variant == "wide_spread":
+        model, y, hmm, theta = load_case(dp, "sir_dense")
+        # one long interval without resampling up to the epidemic peak: infectives range from 0 (early extinction) to hundreds
+        y = [dp.Observation(40.0, 1, 1.0, [0, 300, 0]), dp.Observation(41.0, 1, 1.0, [0, 300, 0])]
+        hmm = dp.get_private_model(model, y)
+    elif variant == "huge_observation":
+        model, y, hmm, theta = load_case(dp, "sis_pooley")
+        y = [dp.Observation(20.0, 1, 1.0, [0, 18]), dp.Observation(40.0, 1, 1.0, [0, (1 << 31) + 5]), dp.Observation(60.0, 1, 1.0, [0, 70])]
+        hmm = dp.get_private_model(model, y)
+    else:
+        model, y, hmm, theta = load_case(dp, "sis_pooley")
+        model = dp.generate_model("SIS", [100, 1], obs_error=1.7)
+        hmm = dp.get_private_model(model, y)
+    for n in (1500, 5000):
+        pf = _pf(dp, hmm, n, f64=True)
+        tile, items = pf.geometry()
+        key = 0x5EED + n
+        pf.set_stream_key(key)
+        ymax = len(y) - 1  # the last evaluated step is followed by a resampling step (obs_i < length(obs_data))
+        ll = pf.partial(theta, 1, ymax)[0]
+        o_ll, o_lw, o_anc, o_ev, o_ovf, o_pop = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, ymax, 1, key, 0,
+                                                               orc.MODE_DEVICE, tile, items)
+        assert np.array_equal(pf.last_logw(), o_lw) and np.array_equal(pf.last_ancestors(), o_anc)
+        assert np.array_equal(pf.get_pop(1), o_pop)
+        assert (np.isnan(ll) and np.isnan(o_ll)) or ll == o_ll or abs(ll - o_ll) <= 1e-12 * max(1.0, abs(o_ll))
+        if variant == "wide_spread":
+            lw = pf.last_logw()
+            d = np.sqrt(np.maximum(0.0, (lw.max() - lw[np.isfinite(lw)]) * 8.0))  # sigma = 2: logw = c - d^2 / 8
+            assert d.max() > 160  # offsets well beyond the 128-entry table
