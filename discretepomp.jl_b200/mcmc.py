@@ -66,11 +66,9 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
     pf = make(max(n_loc, 1), seed)
     adapt_interval = max(adapt_period // 10, 1)  # ADAPT_INTERVAL = adapt_period / 10 (:168)
     chains = np.zeros((n_loc, steps, d))
-    rngs = [np.random.default_rng([seed, lo + k]) for k in range(n_loc)]  # per-chain streams: sharding independent
     chol = np.zeros((n_loc, d, d))
-    for k in range(n_loc):
-        t0 = theta_init[:, lo + k]
-        chol[k] = np.diag(np.sqrt(0.1 * np.where(t0 == 0.0, 1.0, t0 * t0)))  # covar[i,i] = 0.1 * theta0[i]^2 (:171-174)
+    t0s = theta_init[:, lo:hi].T
+    chol[:, np.arange(d), np.arange(d)] = np.sqrt(0.1 * np.where(t0s == 0.0, 1.0, t0s * t0s))  # covar[i,i] = 0.1 * theta0[i]^2 (:171-174)
     c = np.full(n_loc, C_INITIAL)
     accepted_total = np.zeros(n_loc, dtype=np.int64)
 
@@ -87,33 +85,40 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
             out[valid] = lp[valid] + pf.loglik(np.ascontiguousarray(thetas[valid].T))
         return out
 
-    chains[:, 0, :] = theta_init[:, lo:hi].T
+    chains[:, 0, :] = t0s
     ll_i = target(chains[:, 0, :], 0)
+    sum_x = chains[:, 0, :].copy()                               # running sums of every chain's samples: the covariance
+    sum_xx = np.einsum("ki,kj->kij", sum_x, sum_x)               # of the adaptation step without a pass over the history
     for i in range(1, steps):
-        # get_mv_param(propd, c, theta[mc, i-1, :]) (:181) for every chain (each chain keeps its own random stream)
-        z = np.stack([rngs[k].standard_normal(d) for k in range(n_loc)]) if n_loc else np.zeros((0, d))
+        # host draws of step i for ALL chains from one stream keyed by (seed, i); a rank uses the rows of its chains, so the
+        # chains do not depend on the number of ranks.  get_mv_param(propd, c, theta[mc, i-1, :]) (:181)
+        g = np.random.default_rng([seed & 0xFFFFFFFF, 0x504D, i])
+        z = g.standard_normal((n_chains, d))[lo:hi]
+        u = g.random(n_chains)[lo:hi]
         prop = chains[:, i - 1, :] + c[:, None] * np.einsum("kij,kj->ki", chol, z)
         ll_f = target(prop, i)
-        u = np.array([rngs[k].random() for k in range(n_loc)])
         with np.errstate(over="ignore", invalid="ignore"):
             mh = np.exp(np.minimum(ll_f - ll_i, 700.0))
         ok = (ll_f != -np.inf) & ((mh > 1) | (mh > u))  # :189-190
         ll_i = np.where(ok, ll_f, ll_i)
         chains[:, i, :] = np.where(ok[:, None], prop, chains[:, i - 1, :])
         accepted_total += ok
+        sum_x += chains[:, i, :]
+        sum_xx += np.einsum("ki,kj->kij", chains[:, i, :], chains[:, i, :])
         if i + 1 < adapt_period:  # Julia's 1-based step index is i + 1 (:198)
             c *= np.where(ok, 1.002, 0.999)
             if (i + 1) % adapt_interval == 0:
-                for k in range(n_loc):
-                    covar = np.atleast_2d(np.cov(chains[k, : i + 1].T))
-                    if covar.sum() == 0:
-                        if verbose:
-                            print("warning: low acceptance rate detected in adaptation period")
-                    else:
-                        try:
-                            chol[k] = np.linalg.cholesky(covar)
-                        except np.linalg.LinAlgError:
-                            pass
+                n_s = i + 1
+                mean = sum_x / n_s
+                covar = (sum_xx - n_s * np.einsum("ki,kj->kij", mean, mean)) / (n_s - 1)
+                flat_chain = covar.reshape(n_loc, -1).sum(axis=1) == 0
+                if verbose and flat_chain.any():
+                    print("warning: low acceptance rate detected in adaptation period")
+                for k in np.nonzero(~flat_chain)[0]:
+                    try:
+                        chol[k] = np.linalg.cholesky(covar[k])
+                    except np.linalg.LinAlgError:
+                        pass
     flat = comm.allgather_f64(chains.reshape(n_loc, steps * d), n_chains)
     theta = np.ascontiguousarray(flat.reshape(n_chains, steps, d).transpose(2, 1, 0))
     rs = handle_rej_samples(theta, adapt_period)
