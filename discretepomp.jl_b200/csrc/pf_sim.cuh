@@ -345,13 +345,14 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
         for (int kk = 0; kk < ITEMS; ++kk) excluded[kk] = !(base_n + tid * ITEMS + kk < a.n) || of.v[kk] != 0;
 
-        // event statistics: one atomic per warp
+        // event statistics: one RED per warp, issued by lane 1 -- thread 0 takes the tickets below, and its __threadfence
+        // would wait for its own RED, queued behind those of every other warp on the same address
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
             ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
         }
-        if ((tid & 31) == 0) {
+        if ((tid & 31) == 1) {
             if (ev_local) atomicAdd(a.ev_count, ev_local);
             if (ovf_local) atomicAdd(a.ovf_count, ovf_local);
         }
@@ -412,17 +413,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     DPOMP_STAMP(0, 4);
     // tile partials (m_b, s_b) in the blocked item order of the scan tree
     const double s_b = tile_scan<ITEMS, false>(av, incl, excl, warp_scratch);
-    if (!resample_here) {  // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs
-        double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
-        if constexpr (ITEMS % 2 == 0) {
-#pragma unroll
-            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(wt_b + kk) = make_double2(incl[kk], incl[kk + 1]);
-        } else {
-#pragma unroll
-            for (int kk = 0; kk < ITEMS; ++kk) wt_b[kk] = incl[kk];
-        }
-    }
-
     // ---- two-level combine of the tile partials, each level done by whoever finishes last (tickets) -----------------
     // level 1: the kGroupTiles tiles of a group, level 2: the groups of the filter.  Both levels are one warp with the
     // same tree (one value per lane, Kogge-Stone over the lanes, chunks of 32 chained sequentially): no block barriers on
@@ -438,6 +428,18 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         __threadfence();
         const unsigned int ticket = atomicAdd(&a.grp_counter[(size_t)b * a.ngroups + grp], 1u);
         grp_last = (ticket == (unsigned int)(grp_tiles - 1));
+    }
+    // the scan goes out AFTER thread 0 took its ticket: its consumer is the next kernel, and the fence above then has no
+    // bulk stores of this thread to wait for
+    if (!resample_here) {  // the tile-local inclusive scan of exp(logw - m_b) is all the resample kernel needs
+        double* wt_b = a.wtile + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
+        if constexpr (ITEMS % 2 == 0) {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; kk += 2) *reinterpret_cast<double2*>(wt_b + kk) = make_double2(incl[kk], incl[kk + 1]);
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < ITEMS; ++kk) wt_b[kk] = incl[kk];
+        }
     }
     if (tid < 32) grp_last = __shfl_sync(0xffffffffu, grp_last, 0);
     if (grp_last && tid < 32) {
