@@ -5,13 +5,14 @@
 // closures (src/hmm_examples.jl:103-168) and the Gaussian observation model (src/hmm_examples.jl:59-67) of the
 // reference, plus the `log(cum_weight[end]/N)` accumulation of partial_log_likelihood! (src/hmm_particle_filter.jl:60).
 //
-// Mapping: one CTA of 256 threads per (filter, tile of 256*ITEMS particles).  The tile's int32 states are staged in
-// shared memory; each warp then drains its chunk of 32*ITEMS particles through a ballot-based work queue: one loop
-// iteration is ONE event attempt for every lane, and a lane whose particle reached the observation time parks it and
-// pulls the next unassigned particle of the chunk, so all lanes stay busy until the chunk is empty (no atomics: the
-// queue head is warp-uniform).  Compartment counts live in registers as Real during the loop.  One Philox2x32-10 call
-// per attempt yields the waiting-time and event-type uniforms.  The observation log-weight (one f64 divide per
-// particle) is computed afterwards in a convergent pass together with the coalesced write-back.
+// Mapping: one CTA of kBlockThreads (128) threads per (filter, tile of kBlockThreads * ITEMS particles).  The tile's int32
+// states are staged in shared memory; each warp then drains its chunk of 32 * ITEMS particles through a ballot-based work
+// queue: one loop iteration is ONE event attempt for every lane (branch free in the f32 loop), and a lane whose particle
+// reached the observation time parks it and pulls the next unassigned particle of the chunk, so all lanes stay busy until
+// the chunk is empty (no atomics: the queue head is warp-uniform).  Compartment counts live in registers as Real during the
+// loop.  One Philox2x32-10 call per attempt yields the waiting-time and event-type uniforms.  The observation log-weights
+// are formed afterwards in a convergent pass in the integer domain (tile maximum by integer min, exp from a per-CTA table)
+// together with the coalesced write-back, the tile scan and the two-level ticket combine.
 #pragma once
 #include <type_traits>
 
