@@ -43,6 +43,32 @@ def test_get_grid_points_cache_semantics(dp):
     assert e.process_run and e.result.visited == 3 and not f.process_run and f.result.sampled == 4 and pdf.calls == 3
 
 
+def test_get_grid_points_batched_density(dp):
+    """A density closure that accepts (n_theta, B) matrices (like get_log_pdf_fn's, attribute `batched`) receives the
+    evaluations of a round in chunks of at most n_batch columns, and yields the same cache as the scalar closure."""
+    rng = np.random.default_rng(0)
+    mu, sd = np.array([0.4, 0.9]), np.array([0.2, 0.3])
+    calls = []
+
+    def pdf(theta):
+        th = np.asarray(theta, dtype=float)
+        calls.append(th.shape)
+        z = (th - (mu[:, None] if th.ndim == 2 else mu)) / (sd[:, None] if th.ndim == 2 else sd)
+        return -0.5 * np.sum(z * z, axis=0)
+    pdf.batched, pdf.n_batch = True, 2
+    prior = lambda th: 0.0
+    mdl = dp.LikelihoodModel(pdf, np.array([0.1, 0.1]), np.array([0.05, 0.05]), 1, 50, 0.0, prior)
+    grid = {}
+    pts = [np.array([i, 2 * i]) for i in range(5)] + [np.array([1, 2])]  # five distinct points and one repeat
+    res = dp.get_grid_points(grid, pts, mdl, [False] * 6, rng)
+    assert calls == [(2, 2), (2, 2), (2, 1)] and len(grid) == 5  # 5 evaluations in chunks of n_batch = 2; the repeat is cached
+    assert [r.process_run for r in res] == [True] * 5 + [False]
+    for r, p in zip(res, pts):
+        val = mdl.sample_offset + p * mdl.sample_interval
+        assert np.allclose(r.result.sample, val) and np.isclose(r.result.log_likelihood, float(pdf(val)))
+    assert res[5].result.sampled == 2 and res[1].result.sampled == 1
+
+
 def test_theta_f_and_adapt_jw(dp):
     rng = np.random.default_rng(1)
     th = np.array([10, 20, 30])
