@@ -106,6 +106,9 @@ def ncu_traffic():
                 r = rows[metric]
                 tot += sum(float(r[2 + i].replace(",", "")) for i in cols) / max(len(cols), 1) * scale.get(r[1], 1.0)
             out[key] = tot if cols else None
+            r = rows.get("smsp__inst_executed.sum")
+            if r and cols:  # executed warp instructions per launch, for the issue-rate view of the same kernels
+                out[key + ":warp_inst"] = sum(float(r[2 + i].replace(",", "")) for i in cols) / len(cols)
         return out
     except Exception:
         return {}
@@ -355,6 +358,12 @@ def main():
                 kernels[nm] = {"ncu_dram_bytes_per_launch": traffic.get(nm), "avg_launch_us": 1e3 * avg_ms, "launches_per_step": int(k_n[i] // roof_steps),
                                "share_of_kernel_time": float(k_ms[i] / k_ms.sum()), "alg_bytes_per_particle": alg[nm],
                                "achieved_gbs": ach, "frac_of_hbm_peak": ach / hbm_peak}
+                wi = traffic.get(nm + ":warp_inst")
+                if wi:  # issue-rate view: executed warp instructions (ncu) / measured launch time vs SMs x 4 schedulers x clock
+                    sm_clock = float((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6
+                    issue_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_clock
+                    kernels[nm].update({"ncu_warp_inst_per_launch": wi, "warp_inst_per_s": wi / (avg_ms * 1e-3),
+                                        "frac_of_issue_peak": wi / (avg_ms * 1e-3) / issue_peak})
         dom = max(kernels, key=lambda k: kernels[k]["share_of_kernel_time"])
         value = world * units_per_step * args.steps / wall
         line = {
@@ -375,7 +384,7 @@ def main():
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic.get(dom), "peak_source": peak_src,
                          "traffic_source": "profiles/r1_ncu_full_metrics.csv (ncu --set full of this command; bytes per launch; the 33 MB working set is L2 resident)",
-                         "note": "the simulate kernel is instruction-issue bound, not HBM bound (DESIGN.md); frac is its HBM-roofline fraction"},
+                         "note": "the simulate kernel is instruction-issue / latency bound, not HBM bound (DESIGN.md 4.1); frac is its HBM-roofline fraction, roofline_kernels[*].frac_of_issue_peak the issue-rate view (ncu warp instructions / measured launch time)"},
             "roofline_kernels": kernels,
             "roofline_pipeline": {"alg_bytes_per_step": 16 * C + 48, "achieved_gbs": (16 * C + 48) * value / world / 1e9,
                                   "frac_of_hbm_peak": (16 * C + 48) * value / world / 1e9 / hbm_peak},
