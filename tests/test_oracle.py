@@ -114,3 +114,49 @@ def test_t0_index_shifts_start(dp, orc):
     cm = dp.compile_model(model, y)
     ll, lw, anc, ev, ovf, pop = orc.pf_partial(cm.desc, [0.003, 0.1, 20.0], 64, None, 1, 1)
     assert ev == 0 and np.all(pop == np.array([100, 1]))
+
+
+def test_gillespie_law_against_closed_forms(dp, orc):
+    """Pins the simulation semantics of the oracle (src/hmm_particle_filter.jl:17-28, src/hmm_cmn.jl:4-10) independently of
+    the reference's seeded statistics, on processes with closed-form laws:
+      * pure death (SIS with theta_1 = 0): I(t) ~ Binomial(I0, exp(-theta_2 t));
+      * pure birth (LOTKA with only prey reproduction, theta = (a, 0, 0)): prey(t) - prey0 ~ NegBinomial(prey0, exp(-a t)),
+        mean prey0 exp(a t), variance prey0 exp(a t)(exp(a t) - 1);
+      * two competing exits from one state (SEIS with E -> I and I -> S, no infection): event choice by cumulative rates."""
+    from scipy import stats
+    reps = 4000
+    # pure death
+    model = dp.generate_model("SIS", [40, 60])
+    y = [dp.Observation(20.0, 1, 1.0, [0, 0])]
+    cm = dp.compile_model(model, y)
+    gam = 0.05
+    fin = np.array([orc.gillespie_sim(cm.desc, [0.0, gam], key=100 + i)[0][0, 1] for i in range(reps)])
+    p = np.exp(-gam * 20.0)
+    assert abs(fin.mean() - 60 * p) < 4.5 * np.sqrt(60 * p * (1 - p) / reps)
+    edges = np.arange(10, 36)
+    obs = np.array([(fin <= edges[0]).sum()] + [(fin == k).sum() for k in edges[1:-1]] + [(fin >= edges[-1]).sum()])
+    pmf = stats.binom.pmf(np.arange(0, 61), 60, p)
+    exp = reps * np.array([pmf[: edges[0] + 1].sum()] + [pmf[k] for k in edges[1:-1]] + [pmf[edges[-1]:].sum()])
+    chi2 = ((obs - exp) ** 2 / exp).sum()
+    assert chi2 < stats.chi2.ppf(0.9999, len(obs) - 1), chi2
+    # pure birth: LOTKA state = (predator, prey), rates (theta_1 prey, theta_2 pred prey, theta_3 pred), births first
+    model = dp.generate_model("LOTKA", [0, 10])
+    y = [dp.Observation(4.0, 1, 1.0, [0, 0])]
+    cm = dp.compile_model(model, y)
+    a = 0.3
+    fin = np.array([orc.gillespie_sim(cm.desc, [a, 0.0, 0.0], key=7000 + i)[0][0, 1] for i in range(reps)], dtype=float)
+    g = np.exp(a * 4.0)
+    mean, var = 10 * g, 10 * g * (g - 1)
+    assert abs(fin.mean() - mean) < 4.5 * np.sqrt(var / reps)
+    assert abs(fin.var(ddof=1) - var) < 0.2 * var
+    # competing exits: SEIS [S, E, I] with theta = (0, b, c): the single exposed individual becomes infectious (rate b), the
+    # infectious one recovers (rate c); P(still exposed at t) = exp(-b t), P(infectious at t) = b/(c-b) (exp(-b t) - exp(-c t))
+    model = dp.generate_model("SEIS", [10, 1, 0])
+    y = [dp.Observation(3.0, 1, 1.0, [0, 0, 0])]
+    cm = dp.compile_model(model, y)
+    bb, cc = 0.6, 0.25
+    st = np.array([orc.gillespie_sim(cm.desc, [0.0, bb, cc], key=9000 + i)[0][0] for i in range(reps)])
+    p_e = np.exp(-bb * 3.0)
+    p_i = bb / (cc - bb) * (np.exp(-bb * 3.0) - np.exp(-cc * 3.0))
+    for got, want in (((st[:, 1] == 1).mean(), p_e), ((st[:, 2] == 1).mean(), p_i)):
+        assert abs(got - want) < 4.5 * np.sqrt(want * (1 - want) / reps), (got, want)
