@@ -54,3 +54,27 @@ def load_case(dp, name):
     model = dp.generate_model(mname, ic)
     y = dp.get_observations(os.path.join(GOLDEN, csv))
     return model, y, dp.get_private_model(model, y), np.asarray(theta, dtype=np.float64)
+
+
+def pure_death_case(dp):
+    """Pure-death process (SIS with theta_1 = 0) with five Gaussian observations and its EXACT log-likelihood by the forward
+    recursion over the 61 hidden states (binomial thinning between observations).  Returns (hmm, theta, exact log-lik)."""
+    import numpy as np
+    from scipy import stats
+
+    model = dp.generate_model("SIS", [40, 60])
+    ys = [47, 36, 29, 22, 18]
+    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
+    gam, sigma, i0 = 0.05, 2.0, 60
+    p = np.exp(-gam * 5.0)
+    states = np.arange(i0 + 1)
+    trans = np.array([stats.binom.pmf(states, k, p) for k in states])  # trans[k, j] = P(j survivors | k)
+    alpha = np.zeros(i0 + 1)
+    alpha[i0] = 1.0
+    ll = 0.0
+    for v in ys:
+        alpha = alpha @ trans
+        alpha = alpha * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
+        ll += np.log(alpha.sum())
+        alpha /= alpha.sum()
+    return model, y, dp.get_private_model(model, y), np.array([0.0, gam]), float(ll)

@@ -9,7 +9,7 @@ Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from conftest import load_case
+from conftest import load_case, pure_death_case
 
 pytestmark = pytest.mark.gpu
 
@@ -338,3 +338,17 @@ def test_weight_pass_paths_are_bit_exact_against_oracle(dp, orc, variant):
             lw = pf.last_logw()
             d = np.sqrt(np.maximum(0.0, (lw.max() - lw[np.isfinite(lw)]) * 8.0))  # sigma = 2: logw = c - d^2 / 8
             assert d.max() > 160  # offsets well beyond the 128-entry table
+
+
+@pytest.mark.parametrize("f64", [False, True])
+@pytest.mark.parametrize("rs_type", [1, 2, 3])
+def test_pf_loglik_against_exact_forward_algorithm(dp, f64, rs_type):
+    """The CUDA filter against an EXACT likelihood (no oracle, no reference statistic): pure-death process, p(y_1..y_5) by
+    the forward recursion over its 61 hidden states; the PF likelihood estimate is unbiased, 2^18 particles x 8 filters."""
+    model, y, hmm, theta, ll_exact = pure_death_case(dp)
+    nb = 8
+    pf = dp.ParticleFilter(dp.device_model(hmm), 1 << 18, nb, rs_type, seed=17 + rs_type,
+                           sim_precision=dp._capi.SIM_F64 if f64 else dp._capi.SIM_F32)
+    lls = pf.loglik(np.tile(theta[:, None], (1, nb)))
+    assert abs(np.log(np.mean(np.exp(lls - ll_exact)))) < 0.004, (lls, ll_exact)
+    assert np.all(np.abs(lls - ll_exact) < 0.02)
