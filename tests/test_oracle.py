@@ -180,3 +180,51 @@ def test_particle_filter_loglik_against_exact_forward_algorithm(dp, orc):
     ll0 = orc.pf_loglik(cm.desc, [0.0, 0.0], 300, 1, key=5)[0]
     want = sum(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - i0) ** 2 / (2 * sigma * sigma) for v in ys)
     assert abs(ll0 - want) < 1e-9 * abs(want)
+
+
+def test_smc2_evidence_against_exact_quadrature(dp, orc):
+    """run_pibis (src/hmm_ibis.jl:12-135) on an exactly solvable case: one-parameter pure-death model, prior U(0, 0.2);
+    p(y) = (1/0.2) * integral of the forward-algorithm likelihood over the death rate (trapezoid over 2001 nodes).
+      * without resample-move steps (ess_rs_crit = 0) bme[1] is plain importance sampling from the prior: matches exactly;
+      * with random-walk mutations (ind_prop = false, a symmetric proposal) it matches as well;
+      * with the reference's DEFAULT independent proposals (ind_prop = true) the acceptance ratio `exp(aw_f - aw[p])`
+        (src/hmm_ibis.jl:104) has no proposal-density ratio, so the move step is not invariant and -log p(y) comes out
+        ~0.16 too low here -- the same offset as between the reference's seeded 19.98 and the prior-IS 20.18 on pooley.csv
+        (SURVEY.md 8c).  It is the reference's behaviour; both restatements (oracle and CUDA host driver) keep it."""
+    from scipy import stats
+
+    def rf(out, p, x):
+        out[0] = p[0] * x[1]
+    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
+    ys = [47, 36, 29, 22, 18]
+    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
+    cm = dp.compile_model(model, y)
+    states, sigma = np.arange(61), 2.0
+
+    def exact_ll(gam):
+        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
+        alpha = np.zeros(61); alpha[60] = 1.0
+        ll = 0.0
+        for v in ys:
+            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
+            ll += np.log(alpha.sum())
+            alpha /= alpha.sum()
+        return ll
+    g = np.linspace(0.0, 0.2, 2001)
+    lik = np.exp(np.array([exact_ll(v) for v in g]))
+    bme_exact = -np.log(np.trapezoid(lik, g) / 0.2)
+    mu_exact = np.trapezoid(lik * g, g) / np.trapezoid(lik, g)
+    th = orc.max_threads()
+
+    def runs(n, outer_p, **kw):
+        out = [orc.run_pibis(cm.desc, model.prior.rand(outer_p, np.random.default_rng(40 + s)), model.prior.lower,
+                             model.prior.upper, npf=400, seed=70 + s, threads=th, **kw) for s in range(n)]
+        return np.array([o["bme"][0] for o in out]), np.array([o["mu"][0] for o in out]), out
+    b_is, _, o_is = runs(4, 20000, ess_rs_crit=0.0)
+    assert all(o["k_log"][0] == 0 for o in o_is) and abs(-np.log(np.mean(np.exp(-b_is))) - bme_exact) < 0.06, (b_is, bme_exact)
+    b_rw, m_rw, _ = runs(5, 4000, ind_prop=False)
+    assert abs(-np.log(np.mean(np.exp(-b_rw))) - bme_exact) < 0.08 and abs(m_rw.mean() - mu_exact) < 0.002, (b_rw, bme_exact)
+    b_ind, m_ind, _ = runs(5, 4000)  # the reference's default
+    assert abs(m_ind.mean() - mu_exact) < 0.002
+    off = -np.log(np.mean(np.exp(-b_ind))) - bme_exact
+    assert -0.35 < off < -0.03, (b_ind, bme_exact)  # biased low by the missing proposal ratio (see the docstring)
