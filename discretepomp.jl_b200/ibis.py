@@ -194,9 +194,13 @@ class FilterBank:
 
 def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, ind_prop: bool, alpha: float, np_: int,
               n_props: int = 1, rng: Optional[np.random.Generator] = None, seed: int = 1, comm: Optional[Comm] = None,
-              pf_factory: Optional[Callable] = None, outer_rs: Callable = rs_systematic, verbose: bool = True) -> ImportanceSample:
+              pf_factory: Optional[Callable] = None, outer_rs: Callable = rs_systematic, verbose: bool = True,
+              hastings_correction: bool = False) -> ImportanceSample:
     """run_pibis(model, theta, ess_rs_crit, ind_prop, alpha, np; n_props = 1) (src/hmm_ibis.jl:12-135).
-    `theta` is (n_theta, outer_p); `np_` is the number of state particles per filter."""
+    `theta` is (n_theta, outer_p); `np_` is the number of state particles per filter.
+    `hastings_correction` (not in the reference, default off): with independent proposals the reference accepts with
+    exp(aw_f - aw) (src/hmm_ibis.jl:104), which leaves out the proposal-density ratio q(theta) / q(theta_f) and biases the
+    evidence; True adds it."""
     comm = comm or Comm(None)
     rng = rng or np.random.default_rng(seed)
     theta = np.array(theta, dtype=np.float64, order="C")
@@ -242,8 +246,13 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
                     aw_f, gx_f = bank.propose(theta_f, valid, obs_i)
                     aw_f = aw_f + np.where(valid, prtf, 0.0)
                     u = rng.random(outer_p)
+                    log_ratio = aw_f - aw
+                    if ind_prop and hastings_correction:  # + log q(theta) - log q(theta_f) for q = N(mu, cov)
+                        zc = np.linalg.solve(propd.chol, theta - mu[:, None])
+                        zf = np.linalg.solve(propd.chol, theta_f - mu[:, None])
+                        log_ratio = log_ratio + 0.5 * ((zf * zf).sum(axis=0) - (zc * zc).sum(axis=0))
                     with np.errstate(over="ignore", invalid="ignore"):
-                        accepted = valid & (np.exp(aw_f - aw) > u)
+                        accepted = valid & (np.exp(log_ratio) > u)
                     bank.accept(accepted)
                     mtd_gx[accepted] = np.exp(gx_f[accepted])
                     theta[:, accepted] = theta_f[:, accepted]
