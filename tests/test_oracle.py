@@ -228,3 +228,8 @@ def test_smc2_evidence_against_exact_quadrature(dp, orc):
     assert abs(m_ind.mean() - mu_exact) < 0.002
     off = -np.log(np.mean(np.exp(-b_ind))) - bme_exact
     assert -0.35 < off < -0.03, (b_ind, bme_exact)  # biased low by the missing proposal ratio (see the docstring)
+    # run_mbp_ibis (src/hmm_ibis.jl:140-244) with its defaults (random-walk theta proposals, model-based trajectory proposals):
+    # one trajectory per theta-particle, evidence from the trajectories' observation likelihoods -- matches the exact value too
+    b_mbp = np.array([orc.run_mbp_ibis(cm.desc, model.prior.rand(10000, np.random.default_rng(40 + s)), model.prior.lower,
+                                       model.prior.upper, seed=70 + s, threads=th, cap=4096)["bme"][0] for s in range(4)])
+    assert abs(-np.log(np.mean(np.exp(-b_mbp))) - bme_exact) < 0.06, (b_mbp, bme_exact)
