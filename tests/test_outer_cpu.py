@@ -206,3 +206,40 @@ def test_smc2_hastings_correction_removes_the_evidence_bias(dp, orc):
         res[corr] = -np.log(np.mean(np.exp(-np.array(b))))
     assert abs(res[True] - bme_exact) < 0.07, (res, bme_exact)
     assert res[False] < res[True] - 0.05, (res, bme_exact)
+
+
+def test_mbp_mcmc_posterior_against_exact_quadrature(dp, orc):
+    """run_mbp_mcmc on the exactly solvable pure-death case: posterior mean and standard deviation of the death rate against
+    quadrature of the forward-algorithm likelihood (prior U(0, 0.2)).  Host driver on the oracle-backed trajectory store."""
+    from fake_mbp import OracleMbp
+    from scipy import stats
+
+    def rf(out, p, x):
+        out[0] = p[0] * x[1]
+    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
+    ys = [47, 36, 29, 22, 18]
+    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
+    hmm = dp.get_private_model(model, y)
+    cm = dp.compile_model(model, y)
+    states, sigma = np.arange(61), 2.0
+
+    def exact_ll(gam):
+        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
+        alpha = np.zeros(61); alpha[60] = 1.0
+        ll = 0.0
+        for v in ys:
+            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
+            ll += np.log(alpha.sum())
+            alpha /= alpha.sum()
+        return ll
+    g = np.linspace(0.0, 0.2, 801)
+    lik = np.exp(np.array([exact_ll(v) for v in g]))
+    z = np.trapezoid(lik, g)
+    mean = np.trapezoid(lik * g, g) / z
+    sd = np.sqrt(np.trapezoid(lik * (g - mean) ** 2, g) / z)
+    mk = lambda n, sd_: OracleMbp(cm.desc, [o.time for o in y], 0, n, 4096, sd_)
+    r = dp.run_mbp_mcmc(hmm, model.prior.rand(4, np.random.default_rng(1)), 20000, 4000, False, seed=3, particles_factory=mk,
+                        verbose=False)
+    assert abs(r.samples.mu[0] - mean) < 0.03 * mean, (r.samples.mu, mean)
+    assert abs(np.sqrt(r.samples.cv[0, 0]) - sd) < 0.12 * sd, (r.samples.cv, sd)
+    assert r.sre[0, 1] < 1.05
