@@ -78,3 +78,36 @@ def pure_death_case(dp):
         ll += np.log(alpha.sum())
         alpha /= alpha.sum()
     return model, y, dp.get_private_model(model, y), np.array([0.0, gam]), float(ll)
+
+
+def death_rate_case(dp, nodes: int = 2001):
+    """One-parameter pure-death model (rate theta * I, prior U(0, 0.2)) with the observations of pure_death_case, and the
+    EXACT likelihood on a grid of death rates (forward recursion over the 61 hidden states).  Returns a dict with the model,
+    the observations, the grid `g`, the likelihood `lik` on it, and by trapezoid quadrature the exact -ln p(y) (`bme`),
+    posterior mean (`mean`) and standard deviation (`sd`)."""
+    import numpy as np
+    from scipy import stats
+
+    def rf(out, p, x):
+        out[0] = p[0] * x[1]
+    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
+    ys = [47, 36, 29, 22, 18]
+    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
+    states, sigma = np.arange(61), 2.0
+
+    def exact_ll(gam):
+        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
+        alpha = np.zeros(61)
+        alpha[60] = 1.0
+        ll = 0.0
+        for v in ys:
+            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
+            ll += np.log(alpha.sum())
+            alpha /= alpha.sum()
+        return ll
+    g = np.linspace(0.0, 0.2, nodes)
+    lik = np.exp(np.array([exact_ll(v) for v in g]))
+    z = np.trapezoid(lik, g)
+    mean = np.trapezoid(lik * g, g) / z
+    return dict(model=model, y=y, hmm=dp.get_private_model(model, y), cm=dp.compile_model(model, y), g=g, lik=lik,
+                bme=float(-np.log(z / 0.2)), mean=float(mean), sd=float(np.sqrt(np.trapezoid(lik * (g - mean) ** 2, g) / z)))

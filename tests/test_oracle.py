@@ -191,29 +191,9 @@ def test_smc2_evidence_against_exact_quadrature(dp, orc):
         (src/hmm_ibis.jl:104) has no proposal-density ratio, so the move step is not invariant and -log p(y) comes out
         ~0.16 too low here -- the same offset as between the reference's seeded 19.98 and the prior-IS 20.18 on pooley.csv
         (SURVEY.md 8c).  It is the reference's behaviour; both restatements (oracle and CUDA host driver) keep it."""
-    from scipy import stats
-
-    def rf(out, p, x):
-        out[0] = p[0] * x[1]
-    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
-    ys = [47, 36, 29, 22, 18]
-    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
-    cm = dp.compile_model(model, y)
-    states, sigma = np.arange(61), 2.0
-
-    def exact_ll(gam):
-        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
-        alpha = np.zeros(61); alpha[60] = 1.0
-        ll = 0.0
-        for v in ys:
-            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
-            ll += np.log(alpha.sum())
-            alpha /= alpha.sum()
-        return ll
-    g = np.linspace(0.0, 0.2, 2001)
-    lik = np.exp(np.array([exact_ll(v) for v in g]))
-    bme_exact = -np.log(np.trapezoid(lik, g) / 0.2)
-    mu_exact = np.trapezoid(lik * g, g) / np.trapezoid(lik, g)
+    from conftest import death_rate_case
+    case = death_rate_case(dp)
+    model, cm, bme_exact, mu_exact = case["model"], case["cm"], case["bme"], case["mean"]
     th = orc.max_threads()
 
     def runs(n, outer_p, **kw):

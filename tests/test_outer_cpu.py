@@ -170,29 +170,10 @@ def test_smc2_hastings_correction_removes_the_evidence_bias(dp, orc):
     the acceptance step of the independent proposals, the evidence of the exactly solvable pure-death case
     (tests/test_oracle.py::test_smc2_evidence_against_exact_quadrature, -ln p(y) = 13.147) is recovered; the default
     (reference behaviour) stays ~0.16 lower.  Host driver on the oracle-backed filter bank."""
+    from conftest import death_rate_case
     from fake_pf import OraclePF
-    from scipy import stats
-
-    def rf(out, p, x):
-        out[0] = p[0] * x[1]
-    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
-    ys = [47, 36, 29, 22, 18]
-    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
-    hmm = dp.get_private_model(model, y)
-    cm = dp.compile_model(model, y)
-    states, sigma = np.arange(61), 2.0
-
-    def exact_ll(gam):
-        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
-        alpha = np.zeros(61); alpha[60] = 1.0
-        ll = 0.0
-        for v in ys:
-            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
-            ll += np.log(alpha.sum())
-            alpha /= alpha.sum()
-        return ll
-    g = np.linspace(0.0, 0.2, 801)
-    bme_exact = -np.log(np.trapezoid(np.exp(np.array([exact_ll(v) for v in g])), g) / 0.2)
+    case = death_rate_case(dp, 801)
+    model, hmm, cm, bme_exact = case["model"], case["hmm"], case["cm"], case["bme"]
     factory = lambda nb, sd: OraclePF(cm.desc, 200, nb, 1, sd)
     res = {}
     for corr in (True, False):
@@ -211,32 +192,10 @@ def test_smc2_hastings_correction_removes_the_evidence_bias(dp, orc):
 def test_mbp_mcmc_posterior_against_exact_quadrature(dp, orc):
     """run_mbp_mcmc on the exactly solvable pure-death case: posterior mean and standard deviation of the death rate against
     quadrature of the forward-algorithm likelihood (prior U(0, 0.2)).  Host driver on the oracle-backed trajectory store."""
+    from conftest import death_rate_case
     from fake_mbp import OracleMbp
-    from scipy import stats
-
-    def rf(out, p, x):
-        out[0] = p[0] * x[1]
-    model = dp.generate_custom_model("DEATH", rf, [40, 60], [[1, -1]], prior=dp.UniformProduct([0.0], [0.2]))
-    ys = [47, 36, 29, 22, 18]
-    y = [dp.Observation(5.0 * (k + 1), 1, 1.0, [0, v]) for k, v in enumerate(ys)]
-    hmm = dp.get_private_model(model, y)
-    cm = dp.compile_model(model, y)
-    states, sigma = np.arange(61), 2.0
-
-    def exact_ll(gam):
-        trans = stats.binom.pmf(states[None, :], states[:, None], np.exp(-gam * 5.0))
-        alpha = np.zeros(61); alpha[60] = 1.0
-        ll = 0.0
-        for v in ys:
-            alpha = (alpha @ trans) * np.exp(np.log(1.0 / (np.sqrt(2 * np.pi) * sigma)) - (v - states) ** 2 / (2 * sigma * sigma))
-            ll += np.log(alpha.sum())
-            alpha /= alpha.sum()
-        return ll
-    g = np.linspace(0.0, 0.2, 801)
-    lik = np.exp(np.array([exact_ll(v) for v in g]))
-    z = np.trapezoid(lik, g)
-    mean = np.trapezoid(lik * g, g) / z
-    sd = np.sqrt(np.trapezoid(lik * (g - mean) ** 2, g) / z)
+    case = death_rate_case(dp, 801)
+    model, y, hmm, cm, mean, sd = case["model"], case["y"], case["hmm"], case["cm"], case["mean"], case["sd"]
     mk = lambda n, sd_: OracleMbp(cm.desc, [o.time for o in y], 0, n, 4096, sd_)
     r = dp.run_mbp_mcmc(hmm, model.prior.rand(4, np.random.default_rng(1)), 20000, 4000, False, seed=3, particles_factory=mk,
                         verbose=False)
