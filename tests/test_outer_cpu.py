@@ -202,3 +202,19 @@ def test_mbp_mcmc_posterior_against_exact_quadrature(dp, orc):
     assert abs(r.samples.mu[0] - mean) < 0.03 * mean, (r.samples.mu, mean)
     assert abs(np.sqrt(r.samples.cv[0, 0]) - sd) < 0.12 * sd, (r.samples.cv, sd)
     assert r.sre[0, 1] < 1.05
+
+
+def test_pmcmc_posterior_against_exact_quadrature(dp, orc):
+    """run_pmcmc (src/hmm_mcmc.jl:349-365, 166-211) on the exactly solvable pure-death case: the pseudo-marginal chain
+    targets the exact posterior whatever the particle count; mean and sd against quadrature.  Host driver on the
+    oracle-backed particle filter."""
+    from conftest import death_rate_case
+    from fake_pf import OraclePF
+    case = death_rate_case(dp, 801)
+    factory = lambda nb, sd: OraclePF(case["cm"].desc, 300, nb, 1, sd)
+    th0 = np.array([[0.03, 0.05, 0.07, 0.09]])
+    r = dp.run_pmcmc(case["hmm"], th0, steps=6000, adapt_period=1500, p=300, seed=4, pf_factory=factory, verbose=False)
+    assert r.samples.theta.shape == (1, 6000, 4)
+    assert abs(r.samples.mu[0] - case["mean"]) < 0.04 * case["mean"], (r.samples.mu, case["mean"])
+    assert abs(np.sqrt(r.samples.cv[0, 0]) - case["sd"]) < 0.15 * case["sd"], (r.samples.cv, case["sd"])
+    assert np.all(r.accepted > 300)
