@@ -4,10 +4,12 @@
  * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load it.  The product (libdpomp.so) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned" at function level -- the reference (pure Julia; no Julia toolchain in this
- * image) ships no known-answer vectors for this path.  The restatement is pinned only to
- * Monte-Carlo accuracy by the reference's seeded end-to-end numbers (test/runtests.jl:35,51) and the surveyor's
- * anchors (PF log-lik -15.69 +- 0.01 on data/pooley.csv); tests/test_oracle_anchors.py checks those.
+ * PARITY STATUS: "parity unpinned" by the reference at function level -- the reference (pure Julia; no Julia toolchain
+ * in this image) cannot be run here and ships no known-answer vectors for this path.  What pins the
+ * restatement instead (tests/test_oracle.py): the reference's seeded end-to-end numbers (test/runtests.jl:35,43,51) and
+ * the surveyor's anchors (PF log-lik -15.69 +- 0.01 on data/pooley.csv), to Monte-Carlo accuracy; closed-form laws of the
+ * simulated process; and an exactly solvable case (pure-death process: likelihood by the forward recursion over its
+ * hidden states, evidence and posterior by quadrature) for the filter and for the outer layers.
  *
  * Each function cites the reference file:line it follows (paths relative to the reference repository).
  * Uniform random numbers come from Philox4x32-10 with the counter layout of DESIGN.md ("random streams") so
