@@ -226,8 +226,10 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
             lml = np.log(np.sum(w * gx) / np.sum(w))
             bme[0] += lml
             w = w * gx
-            mu, cv = compute_is_mu_covar(theta, w)
             if compute_ess(w) < ess_crit:
+                # compute_is_mu_covar! (:62): the reference evaluates it at every observation, its values are only used here
+                # (and after the last observation), so it is evaluated where it is consumed
+                mu, cv = compute_is_mu_covar(theta, w)
                 propd = get_prop_density(cv, propd)
                 nidx = outer_rs(w.copy(), rng)  # 1-based
                 theta = theta[:, nidx - 1]

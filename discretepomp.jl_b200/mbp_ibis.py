@@ -207,8 +207,8 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
             lml = np.log(np.sum(w * gx) / np.sum(w))
             bme[0] += lml
             w = w * gx
-            mu, cv = compute_is_mu_covar(theta, w)
             if compute_ess(w) < ess_crit:
+                mu, cv = compute_is_mu_covar(theta, w)  # evaluated where it is consumed (the reference: at every observation)
                 propd = get_prop_density(cv, propd)
                 nidx = outer_rs(w.copy(), rng)
                 mtd_gx = gx[nidx - 1].copy()
