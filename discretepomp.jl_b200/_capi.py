@@ -110,6 +110,7 @@ _SIGS = {
     "dpomp_mbp_import": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
     "dpomp_mbp_get_states": (C.c_int, [_P, C.c_int32, _P]),
     "dpomp_mbp_get_particle": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
+    "dpomp_debug_uniforms_f32": (C.c_int, [_P, C.c_int32, _P, _P]),
     "dpomp_resample_indices": (
         C.c_int,
         [C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, C.c_int32],

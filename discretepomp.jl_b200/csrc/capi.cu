@@ -410,14 +410,17 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             a.work_counter = pf->work_counter;
             a.work_base = pf->work_base;
             a.filt_gen = pf->filt_gen;
-            a.gen = ++pf->gen;
-            pf->work_base += (unsigned long long)nb * pf->ntiles;
+            a.gen = pf->gen + 1;
         }
         if (pf->kernel_timing) CK(kernel_event(pf, 0, st));
         CK(launch_sim_weight(mh, pf->sim_precision, pf->items, fused ? 1 : 0, a, st));
         if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
         ++launches;
         if (fused) {
+            // the host mirrors of the device ticket counter / generation advance only once the launch is enqueued: a failed
+            // launch leaves the handle consistent (the device counter has not moved either)
+            pf->gen += 1;
+            pf->work_base += (unsigned long long)nb * pf->ntiles;
             pf->cur ^= 1;
         } else if (do_rs) {
             ResampleLaunch r{};

@@ -166,9 +166,16 @@ __device__ __forceinline__ SimStream sim_stream_init(uint64_t key, uint32_t filt
     return SimStream{p.w0, p.w1, p.w2};
 }
 
-// (0,1) with 32-bit resolution; f64 value is exact, f32 value is the rounding of it
+// (0,1) with 32-bit resolution; the f64 value is exact
 __device__ __forceinline__ double u32_open_f64(uint32_t w) { return ((double)w + 0.5) * 0x1.0p-32; }
-__device__ __forceinline__ float u32_open_f32(uint32_t w) { return fmaf(__uint2float_rn(w), 0x1.0p-32f, 0x1.0p-33f); }
+// f32 uniforms of the event loop (24-bit resolution after rounding):
+//   waiting time: (0, 1] -- never 0 (log stays finite); the top 128 words round to exactly 1.0f, i.e. a zero waiting time
+//                 with probability 3e-8 per draw (harmless: the reference's rand() is [0,1), -log(1-u) has the same law)
+//   event choice: [0, 1) like the reference's rand() (src/hmm_cmn.jl:5) -- round toward zero, so the largest value is
+//                 1 - 2^-24 and fl(u * R) < R for every R > 0: `cum[i] > etc` always holds for some event with a positive
+//                 rate and choose_event can never fall through to a zero-rate last event
+__device__ __forceinline__ float u32_wait_f32(uint32_t w) { return fmaf(__uint2float_rn(w), 0x1.0p-32f, 0x1.0p-33f); }
+__device__ __forceinline__ float u32_event_f32(uint32_t w) { return __uint2float_rz(w) * 0x1.0p-32f; }
 // [0,1) with 53-bit resolution (Julia's rand() range) for the resampling draws
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)(((uint64_t)hi << 21) | (uint64_t)(lo >> 11)) * 0x1.0p-53;

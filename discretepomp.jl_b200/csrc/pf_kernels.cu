@@ -170,8 +170,15 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
             const int mid = (lq + hq) >> 1;
             if (chs < cw[mid]) hq = mid; else lq = mid + 1;
         }
-        if (lq >= nvalid) lq = nvalid - 1;
+        // cw of the tile's last particle and tile_end(lt) are rounded differently: a draw with cw_last <= chs < tile_end(lt)
+        // belongs to the first particle of the following tile whose cw exceeds it (src/hmm_resample.jl:9-16), not to this tile
         res = base + lq;
+        if (lq >= nvalid) {
+            res = a.n - 1;
+            for (long long q2 = base + nvalid; q2 < a.n; ++q2) {  // cw is non-decreasing: ends after a step or two
+                if (chs < a.cw[(size_t)b * a.n_pad + q2]) { res = q2; break; }
+            }
+        }
     }
     const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad;
     int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad;
@@ -274,7 +281,33 @@ cudaError_t launch_search_hook(int rs_type, const double* cw_dev, long long n, c
     return cudaGetLastError();
 }
 
+__global__ void debug_uniforms_kernel(const uint32_t* w, int n, float* wait, float* evt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        wait[i] = u32_wait_f32(w[i]);
+        evt[i] = u32_event_f32(w[i]);
+    }
+}
+
 }  // namespace dpomp
+
+// diagnostics: the two f32 uniform conversions of the event loop evaluated on the device for the given Philox words
+extern "C" int dpomp_debug_uniforms_f32(const uint32_t* words, int32_t n, float* out_wait, float* out_event) {
+    if (!words || !out_wait || !out_event || n < 1) return DPOMP_ERR_ARG;
+    uint32_t* w = nullptr;
+    float* o = nullptr;
+    if (cudaMalloc((void**)&w, (size_t)n * 4) != cudaSuccess || cudaMalloc((void**)&o, (size_t)n * 8) != cudaSuccess) {
+        cudaFree(w);
+        return DPOMP_ERR_CUDA;
+    }
+    cudaMemcpy(w, words, (size_t)n * 4, cudaMemcpyHostToDevice);
+    dpomp::debug_uniforms_kernel<<<(n + 127) / 128, 128>>>(w, n, o, o + n);
+    cudaError_t e = cudaMemcpy(out_wait, o, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_event, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(w);
+    cudaFree(o);
+    return e == cudaSuccess ? DPOMP_OK : DPOMP_ERR_CUDA;
+}
 
 #ifdef DPOMP_PHASE_TIMERS
 extern "C" int dpomp_debug_phases_rs(unsigned long long* out /* [2][4096][8] */) {

@@ -236,11 +236,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                 const Real rtot = cum[E - 1];
                 const uint2 w = philox2x32_10(pc[s], k[s] ^ ss.b, ss.k);
                 // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
-                const Real tmn = fmaf(__log2f(u32_open_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm[s]);
+                const Real tmn = fmaf(__log2f(u32_wait_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm[s]);
                 const bool capped = k[s] >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
                 const bool go = (rtot > (Real)0) && !capped && (tmn >= (Real)0);  // `time > tmax && break` (:24)
                 Real dx[C];
-                chosen_transition<Real, C, E, MODEL>(m, cum, u32_open_f32(w.y) * rtot, dx);  // choose_event + fn_transition (:25-26)
+                chosen_transition<Real, C, E, MODEL>(m, cum, u32_event_f32(w.y) * rtot, dx);  // choose_event + fn_transition (:25-26)
                 if (go) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) x[s][c] += dx[c];

@@ -9,6 +9,7 @@ the final gather of the samples.
 """
 from __future__ import annotations
 
+import math
 import time
 from typing import Callable, Optional
 
@@ -64,7 +65,7 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
         print(f"Running PMCMC analysis: {n_chains} x {steps} samples")
     make = pf_factory or (lambda nb, sd: ParticleFilter(device_model(model), p, nb, 1, seed=sd))
     pf = make(max(n_loc, 1), seed)
-    adapt_interval = max(adapt_period // 10, 1)  # ADAPT_INTERVAL = adapt_period / 10 (:168)
+    adapt_interval = adapt_period / 10  # ADAPT_INTERVAL = adapt_period / 10 is a Float64 in the reference (:168)
     chains = np.zeros((n_loc, steps, d))
     chol = np.zeros((n_loc, d, d))
     t0s = theta_init[:, lo:hi].T
@@ -87,8 +88,11 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
 
     chains[:, 0, :] = t0s
     ll_i = target(chains[:, 0, :], 0)
-    sum_x = chains[:, 0, :].copy()                               # running sums of every chain's samples: the covariance
-    sum_xx = np.einsum("ki,kj->kij", sum_x, sum_x)               # of the adaptation step without a pass over the history
+    # running sums of every chain's samples, SHIFTED by the chain's starting point (no cancellation for tightly
+    # concentrated chains): the covariance of the adaptation step without a pass over the history
+    shift = chains[:, 0, :].copy()
+    sum_x = np.zeros((n_loc, d))
+    sum_xx = np.zeros((n_loc, d, d))
     for i in range(1, steps):
         # host draws of step i for ALL chains from one stream keyed by (seed, i); a rank uses the rows of its chains, so the
         # chains do not depend on the number of ranks.  get_mv_param(propd, c, theta[mc, i-1, :]) (:181)
@@ -103,11 +107,12 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
         ll_i = np.where(ok, ll_f, ll_i)
         chains[:, i, :] = np.where(ok[:, None], prop, chains[:, i - 1, :])
         accepted_total += ok
-        sum_x += chains[:, i, :]
-        sum_xx += np.einsum("ki,kj->kij", chains[:, i, :], chains[:, i, :])
+        dx = chains[:, i, :] - shift
+        sum_x += dx
+        sum_xx += np.einsum("ki,kj->kij", dx, dx)
         if i + 1 < adapt_period:  # Julia's 1-based step index is i + 1 (:198)
             c *= np.where(ok, 1.002, 0.999)
-            if (i + 1) % adapt_interval == 0:
+            if adapt_interval > 0 and math.fmod(i + 1, adapt_interval) == 0:  # i % ADAPT_INTERVAL == 0 (:200)
                 n_s = i + 1
                 mean = sum_x / n_s
                 covar = (sum_xx - n_s * np.einsum("ki,kj->kij", mean, mean)) / (n_s - 1)

@@ -119,7 +119,10 @@ int dpomp_pf_set_max_events(dpomp_pf* pf, int64_t max_events);        /* per par
 int dpomp_pf_set_batch_offset(dpomp_pf* pf, int64_t batch_offset);    /* global id of local filter 0 (0): makes the
                                                                          random streams independent of the sharding  */
 int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on);                     /* fused simulate+resample launch per observation: 0 never, (1) for
-                                                                         filters of one tile, 2 whenever all tiles of a filter are co-resident */
+                                                                         filters of one tile, 2 whenever all tiles of a filter are co-resident.
+                                                                         Mode 2 spin-waits inside the kernel for the other tiles of the filter and
+                                                                         therefore REQUIRES AN EXCLUSIVE DEVICE: with another handle, stream or
+                                                                         process (MPS) holding SM slots the wait can hang; modes 0 and 1 never wait */
 int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n); /* explicit 0-based GLOBAL ids of the first n
                                                                          filters for the random streams; NULL = batch_offset + b */
 int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key);              /* force the Philox key of the NEXT call (tests) */
@@ -227,6 +230,10 @@ int dpomp_mbp_get_particle(dpomp_mbp* mbp, int32_t p, int32_t which, int64_t* fc
  */
 int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double* w, int64_t n, const double* u,
                            int64_t n_u, int64_t n_out, int64_t* out_idx, int32_t device);
+
+/* diagnostics: the f32 uniform conversions of the event loop evaluated on the device for the given 32-bit Philox words:
+ * out_wait in (0, 1] (waiting time), out_event in [0, 1) (choose_event, src/hmm_cmn.jl:5) */
+int dpomp_debug_uniforms_f32(const uint32_t* words, int32_t n, float* out_wait, float* out_event);
 
 #ifdef __cplusplus
 }

@@ -258,7 +258,7 @@ int orc_run_pmcmc(const dpomp_model_desc* m, const double* theta_init, int n_cha
                   int64_t npf, const double* prior_lo, const double* prior_hi, double c_initial, uint64_t seed,
                   int threads, int64_t max_events, double* samples, int64_t* accepted) {
     const int d = m->n_params, T = m->n_obs;
-    const int adapt_interval = adapt_period / 10 > 0 ? adapt_period / 10 : 1;
+    const double adapt_interval = (double)adapt_period / 10.0;   /* ADAPT_INTERVAL = adapt_period / 10, Float64 (:168) */
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
     for (int mc = 0; mc < n_chains; ++mc) {
         orc_rng rng; rng_seed(&rng, seed + 0x9E37ull * (uint64_t)(mc + 1));
@@ -299,7 +299,7 @@ int orc_run_pmcmc(const dpomp_model_desc* m, const double* theta_init, int n_cha
             if (ok) { ll_i = ll_f; ++acc; } else memcpy(cur, prv, sizeof(double) * d);
             if (i + 1 < adapt_period) {   /* 1-based step index i+1 < adapt_period */
                 c *= ok ? 1.002 : 0.999;
-                if ((i + 1) % adapt_interval == 0) {
+                if (fmod((double)(i + 1), adapt_interval) == 0.0) {   /* i % ADAPT_INTERVAL == 0 (:200) */
                     /* covar = cov(theta[:, 1:i, mc]) (sample covariance, n-1 denominator) */
                     const int n = i + 1;
                     double mean[DPOMP_MAX_PARAMS] = {0};

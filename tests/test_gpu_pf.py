@@ -352,3 +352,43 @@ def test_pf_loglik_against_exact_forward_algorithm(dp, f64, rs_type):
     lls = pf.loglik(np.tile(theta[:, None], (1, nb)))
     assert abs(np.log(np.mean(np.exp(lls - ll_exact)))) < 0.004, (lls, ll_exact)
     assert np.all(np.abs(lls - ll_exact) < 0.02)
+
+
+def test_f32_event_uniform_is_strictly_below_one(dp):
+    """the f32 event-choice uniform must stay below 1 so that choose_event (src/hmm_cmn.jl:4-10) never falls
+    through to a zero-rate last event; the waiting-time uniform must stay above 0 (finite log)."""
+    import ctypes as C
+    words = np.array([0, 1, 127, 128, 0x7FFFFFFF, 0x80000000, 0xFFFFFF00, 0xFFFFFF7F, 0xFFFFFF80, 0xFFFFFFFE, 0xFFFFFFFF],
+                     dtype=np.uint32)
+    wait, evt = np.zeros(len(words), dtype=np.float32), np.zeros(len(words), dtype=np.float32)
+    dp._capi.check(dp._capi.lib().dpomp_debug_uniforms_f32(dp._capi.ptr(words), len(words), dp._capi.ptr(wait), dp._capi.ptr(evt)))
+    assert np.all(wait > 0) and np.all(wait <= 1)
+    assert np.all(evt >= 0) and np.all(evt < 1) and evt.max() == np.float32(1 - 2.0 ** -24)
+    # fl(u * R) < R for every positive total rate R: some event with a positive rate is always chosen
+    rates = np.float32(np.random.default_rng(0).uniform(1e-6, 1e6, 4096))
+    rates = np.concatenate([rates, np.float32([1.0, 2.0, 3.0, 0.1, 1e-30, 1.5e38])])
+    assert np.all(evt.max() * rates < rates)
+
+
+def test_f32_loop_never_produces_negative_compartments(dp):
+    """SEIR (last event I->R has rate 0 while I == 0 and E > 0): 2^22 particle-steps, no compartment may go negative and
+    the population size is conserved."""
+    model, y, hmm, theta = load_case(dp, "seir_c3")
+    pf = _pf(dp, hmm, 1 << 18, seed=5)
+    pf.partial(theta, 1, 16)
+    pop = pf.get_pop(1)
+    assert pop.min() >= 0 and np.all(pop.sum(axis=1) == 101)
+
+
+def test_multinomial_seam_matches_flat_search(dp, orc):
+    """a multinomial draw between the last cw of a tile and the tile's end belongs to the NEXT tile's first
+    particle with cw > chs (src/hmm_resample.jl:9-16); ancestors equal the oracle's on many multi-tile steps."""
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    n = 5000
+    for key in range(900, 906):
+        pf = _pf(dp, hmm, n, rs=3, f64=True)
+        tile, items = pf.geometry()
+        pf.set_stream_key(key)
+        pf.partial(theta, 1, 6)
+        o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 6, 3, key, 0, orc.MODE_DEVICE, tile, items)
+        assert np.array_equal(pf.last_ancestors(), o[2]) and np.array_equal(pf.get_pop(1), o[5])

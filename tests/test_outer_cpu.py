@@ -218,3 +218,33 @@ def test_pmcmc_posterior_against_exact_quadrature(dp, orc):
     assert abs(r.samples.mu[0] - case["mean"]) < 0.04 * case["mean"], (r.samples.mu, case["mean"])
     assert abs(np.sqrt(r.samples.cv[0, 0]) - case["sd"]) < 0.15 * case["sd"], (r.samples.cv, case["sd"])
     assert np.all(r.accepted > 300)
+
+
+def test_pmcmc_adapt_interval_is_float_like_the_reference(dp, orc):
+    """ADAPT_INTERVAL = adapt_period / 10 is a Float64 (src/hmm_mcmc.jl:168,200): with adapt_period = 25 no
+    step index is a multiple of 2.5 except 5, 10, 15, 20; with adapt_period = 27 the proposal covariance never adapts."""
+    from conftest import death_rate_case
+    from fake_pf import OraclePF
+    import dpomp_b200 as dpm
+    import math
+    case = death_rate_case(dp, 201)
+    factory = lambda nb, sd: OraclePF(case["cm"].desc, 64, nb, 1, sd)
+    th0 = np.array([[0.05, 0.07]])
+    calls = []
+    real = np.linalg.cholesky
+
+    def spy(a):
+        calls.append(1)
+        return real(a)
+    np.linalg.cholesky = spy
+    try:
+        dp.run_pmcmc(case["hmm"], th0, steps=40, adapt_period=27, p=64, seed=4, pf_factory=factory, verbose=False)
+        n27 = len(calls)
+        calls.clear()
+        dp.run_pmcmc(case["hmm"], th0, steps=40, adapt_period=25, p=64, seed=4, pf_factory=factory, verbose=False)
+        n25 = len(calls)
+    finally:
+        np.linalg.cholesky = real
+    assert n27 == 0
+    expected = sum(1 for i in range(2, 25) if math.fmod(i, 2.5) == 0)  # Julia steps 2..24 with i % 2.5 == 0: 5, 10, 15, 20
+    assert expected == 4 and n25 <= expected * th0.shape[1] and n25 > 0
