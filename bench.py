@@ -184,6 +184,106 @@ def run_smc2(dp, world, rank, barrier):
     return out
 
 
+def _max_over_ranks(dt, world):
+    import torch
+
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+def _sha16(*arrays):
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def _seir_c3(dp):
+    model = dp.generate_model("SEIR", [100, 0, 1, 0])
+    model.prior = dp.UniformProduct([0, 0, 0], [0.02, 1.0, 0.5])
+    y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "seir_c3.csv"))
+    return model, y
+
+
+PMCMC_CHAINS, PMCMC_NPF, PMCMC_STEPS = 64, 65536, 41
+
+
+def run_pmcmc_c3(dp, world, rank, barrier):
+    """BASELINE config C3: SEIR [100,0,1,0], pMCMC (src/hmm_mcmc.jl:349-365, 166-211) with 64 independent chains x 65536
+    particles, T = 100 observations (tests/golden/seir_c3.csv), prior U(0,(0.02,1,0.5)).  Chains are sharded over the
+    ranks (strong scaling: the total work is fixed); no communication until the final gather of the samples.  The timed
+    region is PMCMC_STEPS - 1 Metropolis-Hastings steps of every chain (plus the initial evaluation) on a pre-allocated
+    filter bank."""
+    import gc
+
+    model, y = _seir_c3(dp)
+    hmm = dp.get_private_model(model, y)
+    comm = dp.Comm() if world > 1 else None
+    lo, hi = (comm.bounds(PMCMC_CHAINS) if comm is not None else (0, PMCMC_CHAINS))
+    th0 = np.tile(np.array([[0.005], [0.2], [0.1]]), (1, PMCMC_CHAINS)) * np.random.default_rng(1).uniform(0.8, 1.25, (3, PMCMC_CHAINS))
+    pf = dp.ParticleFilter(dp.device_model(hmm), PMCMC_NPF, max(hi - lo, 1), 1, seed=2)
+    factory = lambda nb, sd: pf
+    dp.run_pmcmc(hmm, th0, steps=4, adapt_period=2, p=PMCMC_NPF, seed=1, comm=comm, pf_factory=factory, verbose=False)
+    gc.collect()
+    barrier()
+    t0 = time.perf_counter()
+    res = dp.run_pmcmc(hmm, th0, steps=PMCMC_STEPS, adapt_period=PMCMC_STEPS // 2, p=PMCMC_NPF, seed=2, comm=comm,
+                       pf_factory=factory, verbose=False)
+    barrier()
+    dt = _max_over_ranks(time.perf_counter() - t0, world)
+    evals = PMCMC_CHAINS * PMCMC_STEPS  # one PF evaluation per chain and step (the first one is the initial point)
+    return {"metric": "pMCMC chain-steps/s", "value": evals / dt, "unit": "PF evaluations (chain x MH step)/s", "wall_s": dt,
+            "n_gpus": world, "scaling": "strong", "particle_obs_steps_per_s": evals * PMCMC_NPF * len(y) / dt,
+            "config": {"workload": f"C3: SEIR [100,0,1,0], {PMCMC_CHAINS} chains x {PMCMC_NPF} particles, T={len(y)}, {PMCMC_STEPS} "
+                                   "MH steps per chain, prior U(0,(0.02,1,0.5)); filter bank allocated before the timed region"},
+            "ms_per_mh_step": 1e3 * dt / PMCMC_STEPS,
+            "mean_acceptance": float(res.accepted.mean() / (PMCMC_STEPS - 1)),
+            "samples_sha16": _sha16(res.samples.theta), "posterior_mean": [float(v) for v in res.samples.mu],
+            "rank0_phase_seconds": {k: round(float(v) * (1e-3 if k.endswith("_ms") else 1.0), 4) for k, v in sorted(res.timers.items())}}
+
+
+MBPI_OUTER = 16384
+
+
+def run_mbp_ibis_c5(dp, world, rank, barrier):
+    """BASELINE config C5: SEIR data of C3, MBP-IBIS (src/hmm_ibis.jl:140-244) with 16384 theta-particles, n_props 3,
+    ess_rs_crit 0.5, ind_prop false, STRATIFIED outer resampling; theta-particles and their trajectories are sharded over
+    the ranks, trajectories migrate after every outer resample (two-phase all-to-all-v over NCCL)."""
+    import gc
+
+    model, y = _seir_c3(dp)
+    hmm = dp.get_private_model(model, y)
+    comm = dp.Comm() if world > 1 else None
+    lo, hi = (comm.bounds(MBPI_OUTER) if comm is not None else (0, MBPI_OUTER))
+    th0 = model.prior.rand(MBPI_OUTER, np.random.default_rng(3))
+    # warm-up on the first observations (reaches a resample-mutate step: NCCL sets up all-to-all connections lazily)
+    hmm_w = dp.get_private_model(model, y[:12])
+    dp.run_mbp_ibis(hmm_w, th0[:, : max(MBPI_OUTER // 8, 8 * world)], 0.5, 3, False, 1.002, seed=5, comm=comm, outer_rs=dp.rs_stratified, verbose=False)
+    gc.collect()
+    ptcls = dp.MbpParticles(dp.device_model(hmm), max(hi - lo, 1), 8192, 4)
+    barrier()
+    t0 = time.perf_counter()
+    r = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=4, comm=comm, outer_rs=dp.rs_stratified, verbose=False,
+                        particles_factory=lambda n, sd: ptcls)
+    barrier()
+    dt = _max_over_ranks(time.perf_counter() - t0, world)
+    return {"metric": "MBP-IBIS theta-particle-observation updates/s", "value": MBPI_OUTER * len(y) / dt, "unit": "theta-particle-obs/s",
+            "wall_s": dt, "n_gpus": world, "scaling": "strong",
+            "config": {"workload": f"C5: SEIR [100,0,1,0], {MBPI_OUTER} theta-particles (one trajectory each), T={len(y)}, n_props 3, "
+                                   "ess_rs_crit 0.5, ind_prop false, stratified outer resampling; trajectory store allocated before the timed region",
+                       "resample_mutate_steps": int(r.k_log[0] // (3 * MBPI_OUTER))},
+            "minus_log_evidence": [float(v) for v in r.bme], "posterior_mean": [float(v) for v in r.mu],
+            "acceptance_rate": float(r.k_log[1] / max(r.k_log[0], 1)),
+            "result_sha16": _sha16(r.theta, r.weight, r.bme),
+            "rank0_phase_seconds": {k: round(float(v), 4) for k, v in sorted(getattr(r, "timers", {}).items())}}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same config and metric."""
     rank = int(os.environ.get("RANK", "0"))
@@ -192,17 +292,25 @@ def run_reference(args):
     dp, model, y, theta = load_c2()
     from oracle import oracle as orc
 
-    threads = orc.max_threads()
-    n_sample = 1 << 17  # bounded sample of the 2^20-particle workload per step
+    # torchrun exports OMP_NUM_THREADS=1: take the cores this process may run on and pass the count explicitly (the oracle's
+    # num_threads clause overrides the environment), so the arm uses the same threads at every --gpus N
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rate = 0.0
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_baseline(dp, model, y, theta, 1 << 14, threads)
+        rate = max(rate, cpu_baseline(dp, model, y, theta, 1 << 15, threads)[0])
+    # one step = the full 2^20-particle workload when it fits the per-step budget, else a power-of-two sample of it
+    budget_s = min(4.0, 150.0 / max(args.steps, 1))
+    n_sample = N_PARTICLES
+    while n_sample > (1 << 14) and n_sample * len(y) / rate > budget_s:
+        n_sample >>= 1
     t_total, units = 0.0, 0
     for _ in range(args.steps):
         v, dt, _, _ = cpu_baseline(dp, model, y, theta, n_sample, threads)
         t_total += dt
         units += n_sample * len(y)
     value = units / t_total
-    sample = f"{n_sample} of {N_PARTICLES} particles x {len(y)} observations per step, OpenMP over particles"
+    sample = (f"{n_sample} of {N_PARTICLES} particles x {len(y)} observations per step, OpenMP over particles on {threads} threads "
+              f"(thread count passed explicitly: independent of OMP_NUM_THREADS / torchrun)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -235,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smc2", action="store_true", help="skip the SMC^2 (config C4) secondary measurement")
+    ap.add_argument("--no-outer", action="store_true", help="skip the pMCMC (C3) and MBP-IBIS (C5) secondary measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -326,15 +435,35 @@ def main():
     pf.set_kernel_timing(False)
 
     # ---- secondary metric of BASELINE.json: SMC^2 theta-particles/s on config C4, sharded over the ranks ------------
-    smc2 = None
+    # ---- reference-precision throughput: the same C2 step with the f64 event loop (DPOMP_SIM_F64) ----------------------
+    pf64 = dp.ParticleFilter(dm, N_PARTICLES, 1, 1, seed=3000 + rank, device=local_rank, sim_precision=dp._capi.SIM_F64)
+    for _ in range(2):
+        pf64.loglik_device(theta_dev.data_ptr(), 1, out_dev.data_ptr())
+    f64_steps = max(3, min(args.steps, 10))
+    barrier()
+    wall_f64 = 0.0
+    for _ in range(f64_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pf64.loglik_device(theta_dev.data_ptr(), 1, out_dev.data_ptr())
+        wall_f64 += time.perf_counter() - t0
+    barrier()
+    ll_f64 = float(out_dev.item())
+    del pf64
+
+    smc2 = pmcmc = mbpi = None
     if not args.no_smc2:
         smc2 = run_smc2(dp, world, rank, barrier)
+    if not args.no_outer:
+        pmcmc = run_pmcmc_c3(dp, world, rank, barrier)
+        mbpi = run_mbp_ibis_c5(dp, world, rank, barrier)
 
     # max over ranks
-    t = torch.tensor([wall, dev_ms, wall_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, dev_ms, wall_e2e, wall_f64], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, dev_ms, wall_e2e = (float(v) for v in t.tolist())
+    wall, dev_ms, wall_e2e, wall_f64 = (float(v) for v in t.tolist())
 
     if rank == 0:
         peaks = {}
@@ -386,11 +515,22 @@ def main():
                          "traffic_source": "profiles/r1_ncu_full_metrics.csv (ncu --set full of this command; bytes per launch; the 33 MB working set is L2 resident)",
                          "note": "the simulate kernel is instruction-issue / latency bound, not HBM bound (DESIGN.md 4.1); frac is its HBM-roofline fraction, roofline_kernels[*].frac_of_issue_peak the issue-rate view (ncu warp instructions / measured launch time)"},
             "roofline_kernels": kernels,
+            "roofline_kernels_note": "avg_launch_us / share_of_kernel_time come from a separate pass with CUDA events around EVERY launch, "
+                                     "which serialises the programmatic-dependent-launch chain: they are upper bounds (their sum exceeds ms_per_step); "
+                                     "value / ms_per_step are measured without per-launch events",
+            "value_f64_loop": {"value": world * units_per_step * f64_steps / wall_f64, "unit": UNIT, "ms_per_step": 1e3 * wall_f64 / f64_steps,
+                               "steps": f64_steps, "loglik_last": ll_f64,
+                               "note": "same C2 step with DPOMP_SIM_F64: rates, waiting times and event choice in f64 with the reference's "
+                                       "expressions (the draw-for-draw parity loop)"},
             "roofline_pipeline": {"alg_bytes_per_step": 16 * C + 48, "achieved_gbs": (16 * C + 48) * value / world / 1e9,
                                   "frac_of_hbm_peak": (16 * C + 48) * value / world / 1e9 / hbm_peak},
         }
         if smc2 is not None:
             line["smc2"] = smc2
+        if pmcmc is not None:
+            line["pmcmc_c3"] = pmcmc
+        if mbpi is not None:
+            line["mbp_ibis_c5"] = mbpi
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
 

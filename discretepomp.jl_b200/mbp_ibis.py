@@ -156,10 +156,22 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
     ess_crit = ess_rs_crit * outer_p
     make = particles_factory or (lambda n, sd: MbpParticles(device_model(model), n, max_traj, sd))
     ptcls = make(max(n_loc, 1), seed)
+    if particles_factory is not None and hasattr(ptcls, "reset"):
+        ptcls.reset()  # a caller-provided (pre-allocated, possibly used) store starts from the initial condition
     ptcls.set_batch_offset(lo)
 
+    timers = {}  # seconds per phase on this rank
+
+    def tick(name: str, t0: float) -> float:
+        t1 = time.perf_counter()
+        timers[name] = timers.get(name, 0.0) + (t1 - t0)
+        return t1
+
     def gather(local: np.ndarray) -> np.ndarray:
-        return comm.allgather_f64(local, outer_p)
+        t0 = time.perf_counter()
+        out = comm.allgather_f64(local, outer_p)
+        tick("allgather", t0)
+        return out
 
     def migrate(nidx: np.ndarray) -> None:
         """ptcls2[p] = deepcopy(ptcls[nidx[p]]) (:196-199) across ranks."""
@@ -200,7 +212,10 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
     mu, cv = compute_is_mu_covar(theta, w)
     for obs_i in range(1, len(model.obs_data) + 1):
         ptcls.set_stream_key(next_key())
-        lg = gather(ptcls.iterate(theta[:, lo:hi], obs_i, fresh=(obs_i == 1)) if n_loc else np.zeros(0))  # :176-179
+        t_ph = time.perf_counter()
+        lg_loc = ptcls.iterate(theta[:, lo:hi], obs_i, fresh=(obs_i == 1)) if n_loc else np.zeros(0)  # :176-179
+        tick("iterate", t_ph)
+        lg = gather(lg_loc)
         if model.obs_data[obs_i - 1].obs_id > 0:
             log_like = log_like + lg  # -Inf propagates for overflowed trajectories (src/hmm_sim.jl:17-20)
             gx = np.exp(lg)
@@ -212,7 +227,9 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                 propd = get_prop_density(cv, propd)
                 nidx = outer_rs(w.copy(), rng)
                 mtd_gx = gx[nidx - 1].copy()
+                t_ph = time.perf_counter()
                 migrate(nidx)
+                tick("resample_migrate", t_ph)
                 theta, prior, log_like = theta[:, nidx - 1], prior[nidx - 1], log_like[nidx - 1]
                 mlr = np.mean(gx[nidx - 1]) * np.exp(lml)
                 k_log[0] += outer_p * n_props
@@ -221,13 +238,18 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
                     prior_f = prior_logpdf_columns(model.prior, theta_f)
                     valid = prior_f != -np.inf
                     ptcls.set_stream_key(next_key())
-                    ll_f = gather(ptcls.propose(theta[:, lo:hi], theta_f[:, lo:hi], valid[lo:hi], obs_i)
-                                  if n_loc else np.zeros((0, 2)))  # (outer_p, 2)
+                    t_ph = time.perf_counter()
+                    ll_loc = (ptcls.propose(theta[:, lo:hi], theta_f[:, lo:hi], valid[lo:hi], obs_i)
+                              if n_loc else np.zeros((0, 2)))
+                    tick("propose", t_ph)
+                    ll_f = gather(ll_loc)  # (outer_p, 2)
                     u = rng.random(outer_p)
                     with np.errstate(over="ignore", invalid="ignore"):
                         ratio = np.exp(prior_f - prior) * np.exp(ll_f[:, 0] - log_like)  # :212
                     accepted = ratio > u  # NaN compares false, as in the reference
+                    t_ph = time.perf_counter()
                     ptcls.accept(np.nonzero(accepted[lo:hi])[0] + 1)
+                    tick("accept_copy", t_ph)
                     mtd_gx[accepted] = np.exp(ll_f[accepted, 1])
                     theta[:, accepted] = theta_f[:, accepted]
                     prior[accepted] = prior_f[accepted]
@@ -245,5 +267,6 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
         ar = 100.0 * k_log[1] / k_log[0] if k_log[0] else float("nan")
         print(f"- finished in {output.run_time / 1e9:.1f} seconds (AR := {ar:.3g}%)")
     output.k_log = k_log
+    output.timers = timers
     output.particles = ptcls
     return output

@@ -75,15 +75,24 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
 
     from .ibis import prior_logpdf_columns
 
+    timers = {"filter_calls_wall": 0.0, "filter_device_ms": 0.0}  # seconds in the batched C-ABI call / its CUDA-event time
+    last_ids = [None]
+
     def target(thetas: np.ndarray, step: int) -> np.ndarray:
         """model prior + estimate_likelihood(model, theta, p, ps, rsp_systematic) for each local chain (:356-358)."""
         lp = prior_logpdf_columns(model.prior, thetas.T)
         valid = np.nonzero(lp != -np.inf)[0]
         out = np.full(n_loc, -np.inf)
         if len(valid):
-            pf.set_filter_ids(lo + valid)
+            if last_ids[0] is None or not np.array_equal(last_ids[0], valid):  # filter slot j simulates chain lo + valid[j]
+                pf.set_filter_ids(lo + valid)
+                last_ids[0] = valid
             pf.set_stream_key(splitmix64((seed & _M64) ^ splitmix64(step + 1)))
+            t0 = time.perf_counter()
             out[valid] = lp[valid] + pf.loglik(np.ascontiguousarray(thetas[valid].T))
+            timers["filter_calls_wall"] += time.perf_counter() - t0
+            if hasattr(pf, "last_timing"):
+                timers["filter_device_ms"] += pf.last_timing()[0]
         return out
 
     chains[:, 0, :] = t0s
@@ -129,6 +138,8 @@ def run_pmcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int = 500
     rs = handle_rej_samples(theta, adapt_period)
     out = MCMCSample(rs, adapt_period, gelman_diagnostic_sre(theta, adapt_period), time.time_ns() - start_time)
     out.accepted = comm.allgather_f64(accepted_total.astype(np.float64), n_chains).astype(np.int64)
+    timers["total_wall"] = (time.time_ns() - start_time) * 1e-9
+    out.timers = timers
     return out
 
 

@@ -124,3 +124,56 @@ def test_smc2_two_ranks_equal_one_rank_bitwise(tmp_path):
     a, b = np.load(one), np.load(two)
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
+
+
+def _z(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return (a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b) + 1e-300)
+
+
+def test_smc2_lotka_c4_shape_against_oracle(dp, orc):
+    """BASELINE config C4 at reduced scale (LOTKA [70,70], lotka_c4.csv, prior U(0,(1,0.01,1)), ess 0.3, independent
+    proposals): 512 theta x 256 state particles over the first 20 observations, 5 replicates each side; both evidence
+    estimators (src/hmm_ibis.jl:58-60, :118-122) and the posterior mean are z-tested against the oracle's literal run_pibis."""
+    model, y, hmm, theta = load_case(dp, "lotka_c4")
+    model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
+    y = y[:20]
+    cm = dp.compile_model(model, y)
+    reps, n_o, n_x = 5, 512, 256
+    ours, ref, mus, rmus = [], [], [], []
+    for s in range(reps):
+        r = dp.run_ibis_analysis(model, y, np=n_o, npf=n_x, seed=140 + s, verbose=False)
+        ours.append(r.bme.copy()); mus.append(r.mu.copy())
+        assert r.k_log[0] > 0  # resample-move steps happened
+        th0 = model.prior.rand(n_o, np.random.default_rng(170 + s))
+        o = orc.run_pibis(cm.desc, th0, model.prior.lower, model.prior.upper, npf=n_x, seed=190 + s, threads=orc.max_threads())
+        ref.append(o["bme"].copy()); rmus.append(o["mu"].copy())
+    ours, ref, mus, rmus = map(np.array, (ours, ref, mus, rmus))
+    for k in range(2):
+        assert abs(_z(ours[:, k], ref[:, k])) < 4.5, (k, ours[:, k], ref[:, k])
+    for j in range(3):
+        assert abs(_z(mus[:, j], rmus[:, j])) < 4.5, (j, mus[:, j], rmus[:, j])
+    # the data were simulated at theta* = (0.5, 0.0025, 0.3): the posterior mean sits near it
+    assert np.all(np.abs(mus.mean(axis=0) - [0.5, 0.0025, 0.3]) < [0.15, 0.0008, 0.1]), mus.mean(axis=0)
+
+
+def test_pmcmc_seir_c3_shape_against_oracle(dp, orc):
+    """BASELINE config C3 at reduced scale (SEIR [100,0,1,0], seir_c3.csv, prior U(0,(0.02,1,0.5))): 8 chains x 1024
+    particles over the first 40 observations.  Chains are independent, so the post-adaptation chain means are the
+    replicates of a z-test (batch means) of ours against the oracle's literal pMCMC (src/hmm_mcmc.jl:349-365, 166-211)."""
+    model, y, hmm, theta = load_case(dp, "seir_c3")
+    model.prior = dp.UniformProduct([0, 0, 0], [0.02, 1.0, 0.5])
+    y = y[:40]
+    hmm = dp.get_private_model(model, y)
+    cm = dp.compile_model(model, y)
+    chains, steps, adapt, npf = 8, 2500, 800, 1024
+    th0 = np.tile(theta[:, None], (1, chains)) * np.random.default_rng(3).uniform(0.8, 1.25, (3, chains))
+    res = dp.run_pmcmc(hmm, th0, steps=steps, adapt_period=adapt, p=npf, seed=21, verbose=False)
+    ref, acc = orc.run_pmcmc(cm.desc, th0, steps, adapt, npf, model.prior.lower, model.prior.upper, seed=22, threads=orc.max_threads())
+    ours_means = res.samples.theta[:, adapt:, :].mean(axis=1)  # (3, chains)
+    ref_means = ref[:, adapt:, :].mean(axis=1)
+    for j in range(3):
+        assert abs(_z(ours_means[j], ref_means[j])) < 4.5, (j, ours_means[j], ref_means[j])
+    # acceptance behaviour of the same sampler on both sides
+    assert abs(_z(res.accepted / steps, acc / steps)) < 4.5, (res.accepted, acc)
+    assert np.all(res.accepted > 50)
