@@ -18,6 +18,7 @@ MAX_OBS_VALS = 8
 
 RS_SYSTEMATIC, RS_STRATIFIED, RS_MULTINOMIAL = 1, 2, 3
 SIM_F32, SIM_F64 = 0, 1
+SCATTER_REFERENCE, SCATTER_INTERLEAVED = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DPOMP_LIB_PATH selects another build of the same library (kernel A/B measurements); there is still no fallback
@@ -74,6 +75,7 @@ _SIGS = {
     "dpomp_pf_set_max_events": (C.c_int, [_P, C.c_int64]),
     "dpomp_pf_set_batch_offset": (C.c_int, [_P, C.c_int64]),
     "dpomp_pf_set_fused": (C.c_int, [_P, C.c_int32]),
+    "dpomp_pf_set_scatter": (C.c_int, [_P, C.c_int32]),
     "dpomp_pf_set_filter_ids": (C.c_int, [_P, _P, C.c_int32]),
     "dpomp_pf_set_stream_key": (C.c_int, [_P, C.c_uint64]),
     "dpomp_pf_get_stream_key": (C.c_int, [_P, C.POINTER(C.c_uint64)]),

@@ -63,6 +63,7 @@ struct dpomp_pf {
     unsigned long long work_base = 0;
     unsigned int* filt_gen = nullptr;            // [n_batch] generation of the last finished combine
     unsigned int gen = 0;
+    int scatter_mode = DPOMP_SCATTER_DEFAULT;    // offspring placement: 0 reference order, 1 chunk-interleaved over the tiles
     bool fused_enabled = true;
     int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
     int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
@@ -288,6 +289,11 @@ int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on) {
     pf->fused_mode = on >= 2 ? 2 : 1;
     return DPOMP_OK;
 }
+int dpomp_pf_set_scatter(dpomp_pf* pf, int32_t mode) {
+    if (!pf || (mode != DPOMP_SCATTER_REFERENCE && mode != DPOMP_SCATTER_INTERLEAVED)) return fail(DPOMP_ERR_ARG, "bad scatter mode");
+    pf->scatter_mode = mode;
+    return DPOMP_OK;
+}
 int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n) {
     if (!pf) return fail(DPOMP_ERR_ARG, "null handle");
     if (!ids) { pf->use_filter_ids = false; return DPOMP_OK; }
@@ -407,6 +413,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             a.rs_type = pf->rs_type;
             a.pop_dst = pf->pop[pf->cur ^ 1];
             a.anc = pf->record_anc ? pf->anc : nullptr;
+            a.perm = make_chunk_perm(pf->scatter_mode, pf->n, pf->ntiles);
             a.work_counter = pf->work_counter;
             a.work_base = pf->work_base;
             a.filt_gen = pf->filt_gen;
@@ -431,6 +438,7 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;
             r.t = t; r.rs_type = pf->rs_type; r.key = key; r.filter0 = (uint32_t)pf->batch_offset;
+            r.perm = make_chunk_perm(pf->scatter_mode, pf->n, pf->ntiles);
             r.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
             if (pf->kernel_timing) CK(kernel_event(pf, 1, st));
             CK(launch_resample(pf->items, r, st));

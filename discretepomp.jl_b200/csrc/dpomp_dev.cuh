@@ -116,6 +116,37 @@ __device__ __forceinline__ Level2 combine_level2(const double* gm_b, const doubl
     }
     return Level2{big_m, carry};
 }
+// ------------------------------------------------------------------------------------------------------------
+// Offspring placement (dpomp_pf_set_scatter).  The reference writes offspring i to row i (src/hmm_pf_resample.jl:38), so
+// after systematic resampling neighbouring rows share their lineage and the work of the next simulation step clusters
+// in a few tiles.  With the interleaved placement the 32-offspring chunk k goes to chunk position sigma(k), where sigma
+// orders the full chunks by (k mod M, k div M) with M = number of tiles: consecutive chunks land in consecutive tiles and
+// every tile receives a uniform sample of the lineages.  sigma is a bijection on the ncf = floor(N / 32) full chunks
+// (ncf = q * M + r); the trailing partial chunk stays in place; ncf = 0 means identity (the reference's order).
+// Particle order is arbitrary in a bootstrap filter; ancestors given (cw, u) are unchanged, only their rows move.
+// ------------------------------------------------------------------------------------------------------------
+struct ChunkPerm {
+    int ncf, m, q, r;
+};
+__host__ __device__ __forceinline__ int chunk_sigma(const ChunkPerm& p, int rr, int qq) {
+    return rr * p.q + (rr < p.r ? rr : p.r) + qq;
+}
+__host__ __device__ __forceinline__ long long perm_pos(const ChunkPerm& p, long long i) {
+    const int k = (int)(i >> 5);
+    if (k >= p.ncf) return i;
+    return ((long long)chunk_sigma(p, k % p.m, k / p.m) << 5) | (i & 31);
+}
+inline ChunkPerm make_chunk_perm(int scatter_mode, long long n, int ntiles) {
+    ChunkPerm p{0, 1, 0, 0};
+    if (scatter_mode != 0 && ntiles > 1) {
+        p.ncf = (int)(n >> 5);
+        p.m = ntiles;
+        p.q = p.ncf / ntiles;
+        p.r = p.ncf % ntiles;
+    }
+    return p;
+}
+
 constexpr uint32_t kTagSim = 0u;
 constexpr uint32_t kTagResample = 1u;
 
@@ -262,21 +293,30 @@ __device__ __forceinline__ double div_by_n(const ResampleCtx& c, double v) {
     return c.pow2 ? v * c.inv_n : __ddiv_rn(v, c.dn);
 }
 
+// RS: compile-time resampler (DPOMP_RS_SYSTEMATIC / DPOMP_RS_STRATIFIED) or 0 = take c.rs_type at run time.  The
+// systematic instantiation contains no Philox code: the stand-alone resample kernel shrinks from 5176 to a fraction of
+// the SASS instructions (round 1: stalled_no_instruction 1.84 per issue from instruction-cache misses).
+template <int RS = 0>
 __device__ __forceinline__ double resample_u(const ResampleCtx& c, int i /*1-based, n < 2^31*/) {
     const double q = div_by_n(c, (double)(i - 1));
     double r = c.r1_over_n;
-    if (c.rs_type == DPOMP_RS_STRATIFIED) {
+    if ((RS ? RS : c.rs_type) == DPOMP_RS_STRATIFIED) {
         const Philox4 p = stream_draw(c.key, (uint32_t)(i - 1), c.filter, c.obs, kTagResample, 1u);
         r = div_by_n(c, u53(p.w0, p.w1));
     }
     return __dmul_rn(__dadd_rn(r, q), c.s);
 }
 
-__device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, double v) {
+// The count in two steps: a closed-form guess (`exact` = it needs no verification) and the exact correction by
+// comparisons with u_i.  Callers with many values per thread take the guess for all of them first and run ONE copy of
+// the correction code for the few that need it (resample_tile), instead of one inlined copy per value.
+template <int RS = 0>
+__device__ __forceinline__ int resample_ecount_guess(const ResampleCtx& c, double v, bool& exact) {
     const int n = (int)c.n;
+    exact = true;
     if (!(c.s > 0.0)) return n;
     double g;
-    if (c.rs_type == DPOMP_RS_STRATIFIED) {
+    if ((RS ? RS : c.rs_type) == DPOMP_RS_STRATIFIED) {
         g = floor(v * c.inv_s * c.dn);
     } else {
         // u_i <= v  <=>  i <= t + 1 with t = v N / S - r in exact arithmetic.  The f64 evaluation of t and the rounding of
@@ -286,15 +326,25 @@ __device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, doubl
         const double fl = floor(t);
         const double frac = t - fl;
 #ifndef DPOMP_NO_ECOUNT_FAST
-        if (frac > 0x1.0p-12 && frac < 1.0 - 0x1.0p-12 && t > 0.0 && t < c.dn - 1.0) return (long long)fl + 1;
+        if (frac > 0x1.0p-12 && frac < 1.0 - 0x1.0p-12 && t > 0.0 && t < c.dn - 1.0) return (int)fl + 1;
 #endif
         g = fl + 1.0;
     }
-    g = fmin(fmax(g, 0.0), c.dn);
-    int e = (int)g;
-    while (e < n && resample_u(c, e + 1) <= v) ++e;
-    while (e > 0 && resample_u(c, e) > v) --e;
+    exact = false;
+    return (int)fmin(fmax(g, 0.0), c.dn);
+}
+template <int RS = 0>
+__device__ __forceinline__ int resample_ecount_correct(const ResampleCtx& c, double v, int e) {
+    const int n = (int)c.n;
+    while (e < n && resample_u<RS>(c, e + 1) <= v) ++e;
+    while (e > 0 && resample_u<RS>(c, e) > v) --e;
     return e;
+}
+template <int RS = 0>
+__device__ __forceinline__ long long resample_ecount(const ResampleCtx& c, double v) {
+    bool exact;
+    const int e = resample_ecount_guess<RS>(c, v, exact);
+    return exact ? e : resample_ecount_correct<RS>(c, v, e);
 }
 
 __device__ __forceinline__ ResampleCtx make_resample_ctx(int rs_type, long long n, double s, uint64_t key,

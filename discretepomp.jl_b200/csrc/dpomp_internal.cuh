@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/dpomp.h"
+#include "dpomp_dev.cuh"
 
 namespace dpomp {
 
@@ -68,6 +69,7 @@ struct SimLaunch {
     int rs_type;
     int32_t* pop_dst;        // [B][C][n_pad] offspring populations
     int32_t* anc;            // [B][n_pad] 0-based ancestors or nullptr
+    ChunkPerm perm;          // offspring placement (identity or chunk-interleaved)
     unsigned long long* work_counter;  // dynamic logical CTA index (arrival order) = atomicAdd(work_counter) - work_base
     unsigned long long work_base;
     unsigned int* filt_gen;  // [B] set to `gen` by the CTA that finished the filter's combine
@@ -94,6 +96,7 @@ struct ResampleLaunch {
     long long n, n_pad;
     int ntiles, n_filters, n_comp;
     int t, rs_type;
+    ChunkPerm perm;          // offspring placement (identity or chunk-interleaved)
     uint64_t key;
     uint32_t filter0;
     const uint32_t* filter_ids;

@@ -68,7 +68,7 @@ int sim_kernel_supported(int n_comp, int n_events) {
 #ifndef DPOMP_RS_MINB
 #define DPOMP_RS_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
-template <int ITEMS>
+template <int ITEMS, int RS>
 __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
     constexpr int CHUNK = 32 * ITEMS;
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
         return;
     }
     const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
-                    a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
+                    a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
     DPOMP_STAMP(1, 2);
-    resample_tile<ITEMS, int, false>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
+    resample_tile<ITEMS, int, false, RS>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
     DPOMP_STAMP(1, 4);
 }
 
@@ -182,15 +182,24 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
     }
     const int32_t* src_b = a.pop_src + (size_t)b * a.n_comp * a.n_pad;
     int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad;
-    for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + i] = src_b[(size_t)c * a.n_pad + res];
-    if (a.anc) a.anc[(size_t)b * a.n_pad + i] = (int32_t)res;
+    const long long row = perm_pos(a.perm, i);
+    for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + row] = src_b[(size_t)c * a.n_pad + res];
+    if (a.anc) a.anc[(size_t)b * a.n_pad + row] = (int32_t)res;
 }
 
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
     const size_t smem = (size_t)kBlockThreads * items * a.n_comp * sizeof(int);  // staged ancestor states
-    cudaError_t err = items == kItemsSmall ? launch_pdl(pf_resample_kernel<kItemsSmall>, grid, kBlockThreads, smem, stream, a)
-                                           : launch_pdl(pf_resample_kernel<kItemsLarge>, grid, kBlockThreads, smem, stream, a);
+    // one instantiation per resampler: the systematic one carries no stratified (Philox) code (multinomial only uses the
+    // cw materialisation at the top of the kernel)
+    const bool strat = a.rs_type == DPOMP_RS_STRATIFIED;
+    cudaError_t err;
+    if (items == kItemsSmall)
+        err = strat ? launch_pdl(pf_resample_kernel<kItemsSmall, DPOMP_RS_STRATIFIED>, grid, kBlockThreads, smem, stream, a)
+                    : launch_pdl(pf_resample_kernel<kItemsSmall, DPOMP_RS_SYSTEMATIC>, grid, kBlockThreads, smem, stream, a);
+    else
+        err = strat ? launch_pdl(pf_resample_kernel<kItemsLarge, DPOMP_RS_STRATIFIED>, grid, kBlockThreads, smem, stream, a)
+                    : launch_pdl(pf_resample_kernel<kItemsLarge, DPOMP_RS_SYSTEMATIC>, grid, kBlockThreads, smem, stream, a);
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {
         const long long total = (long long)a.n_filters * a.n_pad;

@@ -19,6 +19,7 @@ struct RsArgs {              // what the phase needs besides the tile's own data
     long long n, n_pad;
     int ntiles, ngroups, n_comp, t, rs_type;
     uint64_t key;
+    ChunkPerm perm;          // offspring i is stored at row perm_pos(perm, i)
 };
 
 //   cw_q = O_g + F_g * (o_{b|g} + f_{b|g} * incl_q)   (incl_q: tile-local scan, deterministic tree)
@@ -35,7 +36,7 @@ __device__ __forceinline__ T ld_combine(const T* p) {  // CG: the value was writ
     if constexpr (CG) return __ldcg(p); else return *p;
 }
 
-template <int ITEMS, typename SrcT, bool CG>
+template <int ITEMS, typename SrcT, bool CG, int RS = 0>
 __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, uint32_t gfilter, const double (&incl)[ITEMS],
                                               const SrcT* st_tile, int stride, int* am_all, int* warp_max_s, long long* lohi_s) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -54,12 +55,12 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     const ResampleCtx ctx = make_resample_ctx(a.rs_type, a.n, big_s, a.key, gfilter, (uint32_t)a.t, u53(p.w0, p.w1));
 
     // tile seams: the offset of a tile is its cw at incl = 0
-    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
+    if (tid == 0) lohi_s[0] = (tile == 0) ? 0 : resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, 0.0));
     if (tid == kBlockThreads / 2) {
         long long hi_b = a.n;
         if (tile != a.ntiles - 1) {
             const int g2 = (tile + 1) / kGroupTiles;
-            hi_b = resample_ecount(ctx, tile_cw(ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + g2), ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + g2),
+            hi_b = resample_ecount<RS>(ctx, tile_cw(ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + g2), ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + g2),
                                                 ld_combine<double, CG>(a.tile_off + (size_t)b * a.ntiles + tile + 1), 1.0, 0.0));
         }
         lohi_s[1] = hi_b;
@@ -68,11 +69,33 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     const int nvalid = rem < TILE ? (int)rem : TILE;
     // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
     int er[ITEMS];
+    unsigned todo = 0;  // items whose closed-form guess needs the exact correction
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        er[k] = (int)resample_ecount(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
-        if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
+        bool exact;
+        er[k] = resample_ecount_guess<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]), exact);
+        if (!exact) todo |= 1u << k;
     }
+    // one copy of the correction code (not ITEMS inlined ones: instruction-cache footprint); the arrays stay in registers
+    // (select chains instead of dynamic indexing).  Systematic: rare (|t - round(t)| < 2^-12); stratified: every item.
+#pragma unroll 1
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        double inc_k = incl[0];
+        int e_k = er[0];
+#pragma unroll
+        for (int j = 1; j < ITEMS; ++j) {
+            inc_k = (k == j) ? incl[j] : inc_k;
+            e_k = (k == j) ? er[j] : e_k;
+        }
+        e_k = resample_ecount_correct<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, inc_k), e_k);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) er[j] = (k == j) ? e_k : er[j];
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+        if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
     // running maximum in item order: lane-serial, then Kogge-Stone over the lanes; the warp maximum goes to shared memory
 #pragma unroll
     for (int k = 1; k < ITEMS; ++k) er[k] = max(er[k], er[k - 1]);
@@ -113,7 +136,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     const int wfirst = clamp_off(wprev_raw);                    // the warp owns offspring offsets (wfirst, wlast]
     const int wlast = __shfl_sync(FULL, emax[ITEMS - 1], 31);
 
-    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad + lo;
+    int32_t* dst_b = a.pop_dst + (size_t)b * a.n_comp * a.n_pad;  // row of offspring i: perm_pos(a.perm, i)
     // Heavy tile (weight collapse: this tile feeds far more offspring than it has ancestors): per-warp windows would leave
     // the warp that owns the heavy ancestors looping alone, so the whole CTA walks the tile's offspring range instead and
     // finds each ancestor by binary search over the running maxima (block-uniform decision: lo and hi are shared).
@@ -128,8 +151,9 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
                 const int mid = (lq + hq) >> 1;
                 if (am_all[mid] >= o) hq = mid; else lq = mid + 1;
             }
-            for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + o - 1] = (int)st_tile[(size_t)c * stride + lq];
-            if (a.anc) a.anc[(size_t)b * a.n_pad + lo + o - 1] = (int32_t)(base_n + lq);
+            const long long row = perm_pos(a.perm, lo + o - 1);
+            for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + row] = (int)st_tile[(size_t)c * stride + lq];
+            if (a.anc) a.anc[(size_t)b * a.n_pad + row] = (int32_t)(base_n + lq);
         }
         return;
     }
@@ -160,29 +184,39 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
         __syncwarp();
-        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
+        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores.
+        // Row of offspring i = lo + wlo + j * 32 + lane: consecutive j advance the chunk index by one, so (k mod M, k div M)
+        // is kept incrementally (one division per window).
         int srcq[ITEMS];
+        long long row[ITEMS];
+        {
+            const long long i0 = lo + wlo + lane;
+            int k = (int)(i0 >> 5);
+            int rr = k % a.perm.m, qq = k / a.perm.m;
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const int pidx = j * 32 + lane;
-            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+            for (int j = 0; j < ITEMS; ++j) {
+                const int pidx = j * 32 + lane;
+                srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+                row[j] = (k < a.perm.ncf) ? (((long long)chunk_sigma(a.perm, rr, qq) << 5) | (i0 & 31)) : i0 + j * 32;
+                ++k;
+                if (++rr == a.perm.m) { rr = 0; ++qq; }
+            }
         }
         for (int c = 0; c < a.n_comp; ++c) {
             const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
-            int32_t* dc = dst_b + (size_t)c * a.n_pad + wlo + lane;
+            int32_t* dc = dst_b + (size_t)c * a.n_pad;
             int vals[ITEMS];
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
                 if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) dc[j * 32] = vals[j];
+                if (srcq[j] >= 0) dc[row[j]] = vals[j];
         }
         if (a.anc) {
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0)
-                    a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+                if (srcq[j] >= 0) a.anc[(size_t)b * a.n_pad + row[j]] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
         }
         __syncwarp();
     }

@@ -508,7 +508,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         __shared__ int warp_max_s[kBlockThreads / 32];
         __shared__ long long lohi_s[2];
         const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
-                        a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key};
+                        a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
         // ovf_s (TILE ints) is free after the weight pass: it becomes the per-warp offspring windows
         resample_tile<ITEMS, SState, true>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s, warp_max_s, lohi_s);
     }

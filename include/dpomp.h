@@ -123,6 +123,19 @@ int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on);                     /* fused s
                                                                          Mode 2 spin-waits inside the kernel for the other tiles of the filter and
                                                                          therefore REQUIRES AN EXCLUSIVE DEVICE: with another handle, stream or
                                                                          process (MPS) holding SM slots the wait can hang; modes 0 and 1 never wait */
+/* Row order of the offspring after a resampling step.  The ancestors chosen for offspring i = 1..N are always those of the
+ * reference's walk (src/hmm_pf_resample.jl:34-40); the mode only says where offspring i is stored:
+ *   DPOMP_SCATTER_REFERENCE    row i, as `pop[i,:] = old_p[j,:]` (src/hmm_pf_resample.jl:38)
+ *   DPOMP_SCATTER_INTERLEAVED  32-row chunk k goes to chunk sigma(k), sigma = rank of k ordered by (k mod tiles, k div tiles)
+ *                              over the floor(N/32) full chunks, the trailing partial chunk stays: every tile of the next
+ *                              simulation step holds a uniform sample of the lineages (load balance).  Particle order is
+ *                              arbitrary in a bootstrap filter; the estimate has the same law. */
+#define DPOMP_SCATTER_REFERENCE 0
+#define DPOMP_SCATTER_INTERLEAVED 1
+#ifndef DPOMP_SCATTER_DEFAULT
+#define DPOMP_SCATTER_DEFAULT DPOMP_SCATTER_REFERENCE
+#endif
+int dpomp_pf_set_scatter(dpomp_pf* pf, int32_t mode);
 int dpomp_pf_set_filter_ids(dpomp_pf* pf, const int64_t* ids, int32_t n); /* explicit 0-based GLOBAL ids of the first n
                                                                          filters for the random streams; NULL = batch_offset + b */
 int dpomp_pf_set_stream_key(dpomp_pf* pf, uint64_t key);              /* force the Philox key of the NEXT call (tests) */

@@ -35,6 +35,7 @@
 
 #define ORC_MODE_LITERAL 0
 #define ORC_MODE_DEVICE 1
+#define ORC_MODE_DEVICE_INTERLEAVED 2 /* device order + dpomp_pf_set_scatter(DPOMP_SCATTER_INTERLEAVED) */
 #define ORC_GROUP_TILES 32 /* tiles per group of the two-level combine (kGroupTiles of the device code) */
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -460,8 +461,13 @@ static double device_normalise_resample(const double* logw, int64_t n, int tile,
                 int64_t nvalid = (n - base < tile) ? (n - base) : tile;
                 int64_t lo_q = 0, hi_q = nvalid;
                 while (lo_q < hi_q) { int64_t mid = (lo_q + hi_q) / 2; if (chs < cw[base + mid]) hi_q = mid; else lo_q = mid + 1; }
-                if (lo_q >= nvalid) lo_q = nvalid - 1; /* seam: chs < off[b+1] but not < last cw of the tile */
                 res = base + lo_q + 1;
+                if (lo_q >= nvalid) { /* seam: chs < off[b+1] but not < the last cw of the tile: the walk of
+                                       * src/hmm_resample.jl:9-16 continues into the following tiles */
+                    res = n;
+                    for (int64_t q2 = base + nvalid; q2 < n; ++q2)
+                        if (chs < cw[q2]) { res = q2 + 1; break; }
+                }
             }
             if (res > n) res = n;
             anc[i] = res;
@@ -548,6 +554,24 @@ int orc_pf_partial(const dpomp_model_desc* m, const double* theta, int64_t n, in
             if (do_rs) memcpy(old_p, pop, sizeof(int64_t) * (size_t)(n * C));
         }
         if (do_rs) { /* m_pop[i,:] .= old_p[j,:] (src/hmm_pf_resample.jl:38) */
+            if (mode == ORC_MODE_DEVICE_INTERLEAVED) {
+                /* offspring i goes to row pos(i): 32-row chunk k -> chunk sigma(k) = rank of k by (k mod M, k div M), M = tiles,
+                 * over the floor(n / 32) full chunks; identity for one tile and for the trailing partial chunk (include/dpomp.h) */
+                const int64_t m_t = (n + tile - 1) / tile, ncf = (m_t > 1) ? (n >> 5) : 0;
+                const int64_t pq = ncf / (m_t > 0 ? m_t : 1), pr = ncf % (m_t > 0 ? m_t : 1);
+                int64_t* anc2 = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+                for (int64_t i = 0; i < n; ++i) {
+                    const int64_t k = i >> 5;
+                    int64_t row = i;
+                    if (k < ncf) {
+                        const int64_t rr = k % m_t, qq = k / m_t;
+                        row = ((rr * pq + (rr < pr ? rr : pr) + qq) << 5) | (i & 31);
+                    }
+                    anc2[row] = anc[i];
+                }
+                memcpy(anc, anc2, sizeof(int64_t) * (size_t)n);
+                free(anc2);
+            }
             for (int c = 0; c < C; ++c)
                 for (int64_t i = 0; i < n; ++i) pop[c * n + i] = old_p[c * n + (anc[i] - 1)];
         }

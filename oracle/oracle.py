@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
-MODE_LITERAL, MODE_DEVICE = 0, 1
+MODE_LITERAL, MODE_DEVICE, MODE_DEVICE_INTERLEAVED = 0, 1, 2
 _lib = None
 
 

@@ -23,20 +23,25 @@ def _pf(dp, hmm, n, nb=1, rs=1, seed=1, f64=False, **kw):
 
 @pytest.mark.parametrize("case", ["sis_pooley", "sir_c2", "seir_c3", "lotka_c4"])
 @pytest.mark.parametrize("rs_type", [1, 2, 3])
-def test_f64_loop_is_bit_exact_against_oracle(dp, orc, case, rs_type):
+@pytest.mark.parametrize("scatter", [0, 1])  # offspring rows: the reference's order / chunk-interleaved over the tiles
+def test_f64_loop_is_bit_exact_against_oracle(dp, orc, case, rs_type, scatter):
     model, y, hmm, theta = load_case(dp, case)
     ymax = min(len(y), 4)
-    for n in (200, 1024, 3000):  # 256-particle tile, exactly one 1024 tile, ragged multi-tile
+    for n in (200, 1024, 3000, 4133):  # 256-particle tile, exactly one 1024 tile, ragged multi-tile (93 / 129 full chunks)
         if case == "lotka_c4" and n > 1024:
+            continue
+        if scatter and n <= 1024:  # one tile: the interleaved placement is the identity (covered by scatter = 0)
             continue
         pf = _pf(dp, hmm, n, rs=rs_type, f64=True)
         pf.set_record_ancestors(True)
+        pf.set_scatter(scatter)
         tile, items = pf.geometry()
         key = 0xABCDEF00 + n + rs_type
         pf.set_stream_key(key)
         ll = pf.partial(theta, 1, ymax)[0]
         o_ll, o_lw, o_anc, o_ev, o_ovf, o_pop = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, ymax, rs_type,
-                                                               key, 0, orc.MODE_DEVICE, tile, items)
+                                                               key, 0, orc.MODE_DEVICE_INTERLEAVED if scatter else orc.MODE_DEVICE,
+                                                               tile, items)
         assert pf.last_event_count() == o_ev
         assert np.array_equal(pf.last_logw(), o_lw)
         assert np.array_equal(pf.last_ancestors(), o_anc)
@@ -50,6 +55,7 @@ def test_literal_reference_arithmetic_gives_same_ancestors(dp, orc):
     model, y, hmm, theta = load_case(dp, "sis_pooley")
     n = 2000
     pf = _pf(dp, hmm, n, f64=True)
+    pf.set_scatter(0)  # the reference's row order (offspring i in row i)
     key = 424242
     pf.set_stream_key(key)
     ll = pf.loglik(theta)[0]
@@ -392,3 +398,39 @@ def test_multinomial_seam_matches_flat_search(dp, orc):
         pf.partial(theta, 1, 6)
         o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 6, 3, key, 0, orc.MODE_DEVICE, tile, items)
         assert np.array_equal(pf.last_ancestors(), o[2]) and np.array_equal(pf.get_pop(1), o[5])
+
+
+def test_interleaved_scatter_is_a_row_permutation_of_the_reference_order(dp):
+    """One resampling step from identical inputs: the interleaved placement holds exactly the reference-order offspring,
+    32-row chunk k moved to chunk sigma(k) (include/dpomp.h), the trailing partial chunk in place; ancestors move with
+    their rows.  Also at 2^17 particles x 2 filters (multi-group combine)."""
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    for n, nb in ((4133, 1), (1 << 17, 2)):
+        pops, ancs = [], []
+        for mode in (0, 1):
+            pf = _pf(dp, hmm, n, nb=nb, f64=False, seed=9)
+            pf.set_scatter(mode)
+            pf.set_stream_key(77)
+            pf.partial(np.tile(theta[:, None], (1, nb)), 1, 1)  # observation 1 resamples (obs_id > 0, not the last)
+            pops.append(pf.get_pop(nb)); ancs.append(pf.last_ancestors(nb))
+        tile, _ = pf.geometry()
+        m = -(-n // tile)
+        ncf = n >> 5
+        q, r = divmod(ncf, m)
+        k = np.arange(n) >> 5
+        rr, qq = k % m, k // m
+        row = np.where(k < ncf, ((rr * q + np.minimum(rr, r) + qq) << 5) | (np.arange(n) & 31), np.arange(n))
+        assert np.array_equal(np.sort(row), np.arange(n))  # a bijection
+        assert np.array_equal(pops[1][row], pops[0]) and np.array_equal(ancs[1][row], ancs[0])
+
+
+def test_interleaved_scatter_estimate_has_the_same_law(dp):
+    """z-test of the PF log-likelihood estimate between the two row orders (f32 loop, 64 replicate filters each)."""
+    model, y, hmm, theta = load_case(dp, "seir_c3")
+    lls = []
+    for mode in (0, 1):
+        pf = _pf(dp, hmm, 8192, nb=64, seed=31 + mode)
+        pf.set_scatter(mode)
+        lls.append(pf.loglik(np.tile(theta[:, None], (1, 64))))
+    z = (lls[0].mean() - lls[1].mean()) / np.sqrt(lls[0].var(ddof=1) / 64 + lls[1].var(ddof=1) / 64)
+    assert abs(z) < 4.5, (lls[0].mean(), lls[1].mean(), z)

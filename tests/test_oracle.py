@@ -213,3 +213,26 @@ def test_smc2_evidence_against_exact_quadrature(dp, orc):
     b_mbp = np.array([orc.run_mbp_ibis(cm.desc, model.prior.rand(10000, np.random.default_rng(40 + s)), model.prior.lower,
                                        model.prior.upper, seed=70 + s, threads=th, cap=4096)["bme"][0] for s in range(4)])
     assert abs(-np.log(np.mean(np.exp(-b_mbp))) - bme_exact) < 0.06, (b_mbp, bme_exact)
+
+
+def test_interleaved_device_mode_is_a_row_permutation(dp, orc):
+    """ORC_MODE_DEVICE_INTERLEAVED (mirror of dpomp_pf_set_scatter(1)): after ONE resampling step the population is the
+    device-order one with 32-row chunk k moved to chunk sigma(k); the log-likelihood increment is identical."""
+    from conftest import load_case
+    model, y, hmm, theta = load_case(dp, "sir_c2")
+    cm = dp.compile_model(model, y)
+    n, tile = 4133, 1024
+    a = orc.pf_partial(cm.desc, theta, n, None, 1, 1, 1, 5, 0, orc.MODE_DEVICE, tile, 8)
+    b = orc.pf_partial(cm.desc, theta, n, None, 1, 1, 1, 5, 0, orc.MODE_DEVICE_INTERLEAVED, tile, 8)
+    m, ncf = -(-n // tile), n >> 5
+    q, r = divmod(ncf, m)
+    i = np.arange(n)
+    k = i >> 5
+    rr, qq = k % m, k // m
+    row = np.where(k < ncf, ((rr * q + np.minimum(rr, r) + qq) << 5) | (i & 31), i)
+    assert np.array_equal(np.sort(row), i)
+    assert a[0] == b[0] and np.array_equal(b[5][row], a[5]) and np.array_equal(b[2][row], a[2])
+    # a single tile: identity
+    c = orc.pf_partial(cm.desc, theta, 1000, None, 1, 3, 1, 5, 0, orc.MODE_DEVICE, tile, 8)
+    d = orc.pf_partial(cm.desc, theta, 1000, None, 1, 3, 1, 5, 0, orc.MODE_DEVICE_INTERLEAVED, tile, 8)
+    assert np.array_equal(c[5], d[5])
