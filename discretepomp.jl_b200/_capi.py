@@ -112,6 +112,16 @@ _SIGS = {
     "dpomp_mbp_import": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
     "dpomp_mbp_get_states": (C.c_int, [_P, C.c_int32, _P]),
     "dpomp_mbp_get_particle": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
+    "dpomp_comm_unique_id": (C.c_int, [_P, C.c_int32]),
+    "dpomp_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "dpomp_comm_destroy": (C.c_int, [_P]),
+    "dpomp_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dpomp_comm_barrier": (C.c_int, [_P]),
+    "dpomp_partition_bounds": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dpomp_comm_allgather_f64": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
+    "dpomp_pf_partial_allgather": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "dpomp_pf_resample_migrate": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "dpomp_mbp_resample_migrate": (C.c_int, [_P, _P, _P, C.c_int64]),
     "dpomp_debug_uniforms_f32": (C.c_int, [_P, C.c_int32, _P, _P]),
     "dpomp_resample_indices": (
         C.c_int,

@@ -26,63 +26,6 @@ int dpomp_set_error(int code, const std::string& msg) { return fail(code, msg); 
             return fail(DPOMP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
     } while (0)
 
-struct dpomp_model {
-    ModelHost h;
-};
-
-struct dpomp_pf {
-    const dpomp_model* model = nullptr;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    long long n = 0, n_pad = 0;
-    int n_batch = 0, ntiles = 0, items = 4, tile = 1024;
-    int rs_type = DPOMP_RS_SYSTEMATIC, sim_precision = DPOMP_SIM_F32;
-    long long max_events = 1ll << 20;
-    uint64_t seed = 0, call_index = 0, forced_key = 0;
-    bool key_forced = false;
-    long long batch_offset = 0;
-    int n_comp = 0, n_params = 0, n_obs = 0;
-    int32_t* pop[2] = {nullptr, nullptr};
-    int cur = 0;
-    double* logw = nullptr;
-    double* wtile = nullptr;
-    double* cw = nullptr;
-    int32_t* anc = nullptr;
-    bool record_anc = false, initialised = false, last_resampled = false;
-    double *theta_dev = nullptr, *tile_m = nullptr, *tile_s = nullptr, *tile_f = nullptr, *tile_off = nullptr;
-    double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
-    double *grp_m = nullptr, *grp_s = nullptr, *grp_f = nullptr, *grp_off = nullptr;
-    unsigned int* grp_counter = nullptr;
-    int ngroups = 0;
-    unsigned int* tile_counter = nullptr;
-    unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
-    double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
-    int64_t* slots_dev = nullptr;            // 2 * n_batch
-    unsigned long long* work_counter = nullptr;  // fused step kernel: arrival-order CTA tickets (monotone)
-    unsigned long long work_base = 0;
-    unsigned int* filt_gen = nullptr;            // [n_batch] generation of the last finished combine
-    unsigned int gen = 0;
-    int scatter_mode = DPOMP_SCATTER_DEFAULT;    // offspring placement: 0 reference order, 1 chunk-interleaved over the tiles
-    bool fused_enabled = true;
-    int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
-    int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
-    uint32_t* filter_ids_dev = nullptr;      // n_batch, valid when use_filter_ids
-    bool use_filter_ids = false;
-    double* h_theta = nullptr;               // pinned staging
-    double* h_ll = nullptr;
-    int64_t* h_slots = nullptr;
-    float last_ms = 0.f;
-    int last_launches = 0;
-    long long last_events = 0;
-    // optional per-kernel timing (bench.py roofline): events around every launch of the last call
-    bool kernel_timing = false;
-    std::vector<cudaEvent_t> kev;      // 2 events per launch slot
-    std::vector<int> kev_kind;         // 0 = simulate+weight, 1 = resample
-    float kernel_ms[2] = {0.f, 0.f};
-    int kernel_launches[2] = {0, 0};
-};
-
 static uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -158,7 +101,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev); cudaFree(pf->work_counter); cudaFree(pf->filt_gen);
-    cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots);
+    cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots); cudaFreeHost(pf->h_cnt);
     for (cudaEvent_t e : pf->kev) cudaEventDestroy(e);
     if (pf->ev0) cudaEventDestroy(pf->ev0);
     if (pf->ev1) cudaEventDestroy(pf->ev1);
@@ -240,6 +183,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     bool ok = cudaMallocHost((void**)&pf->h_theta, B * pf->n_params * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void**)&pf->h_ll, B * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void**)&pf->h_slots, 2 * B * sizeof(int64_t)) == cudaSuccess &&
+              cudaMallocHost((void**)&pf->h_cnt, sizeof(unsigned long long)) == cudaSuccess &&
               cudaStreamCreateWithFlags(&pf->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&pf->ev0) == cudaSuccess && cudaEventCreate(&pf->ev1) == cudaSuccess &&
               cudaMemsetAsync(pf->pop[0], 0, B * pf->n_comp * NP * sizeof(int32_t), pf->stream) == cudaSuccess &&
@@ -351,9 +295,9 @@ static cudaError_t kernel_event(dpomp_pf* pf, int kind, cudaStream_t st) {
 }
 
 // the launch sequence of partial_log_likelihood! (src/hmm_particle_filter.jl:39-76), batched over filters
-static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax, double* out,
-                       bool out_on_device) {
-    if (!pf || !theta || !out) return fail(DPOMP_ERR_ARG, "null argument");
+int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax, double* out,
+                              int out_mode) {
+    if (!pf || !theta || (!out && out_mode != 2)) return fail(DPOMP_ERR_ARG, "null argument");
     if (nb < 1 || nb > pf->n_batch) return fail(DPOMP_ERR_ARG, "n_batch_used out of range");
     if (ymin < 1 || ymax < ymin || ymax > pf->n_obs) return fail(DPOMP_ERR_ARG, "observation range out of bounds");
     if (ymin > 1 && !pf->initialised) return fail(DPOMP_ERR_STATE, "ymin > 1 on a filter that has never been run from ymin == 1");
@@ -448,19 +392,22 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
         }
         pf->last_resampled = do_rs != 0;
     }
-    if (out_on_device) {
+    if (out_mode == 1) {
         CK(cudaMemcpyAsync(out, pf->ll_acc, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    } else {
+    } else if (out_mode == 0) {
         CK(cudaMemcpyAsync(pf->h_ll, pf->ll_acc, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    unsigned long long h_cnt = 0;
-    CK(cudaMemcpyAsync(&h_cnt, pf->counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pf->h_cnt, pf->counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(pf->ev1, st));
-    CK(cudaStreamSynchronize(st));
-    if (!out_on_device) memcpy(out, pf->h_ll, (size_t)nb * sizeof(double));
-    CK(cudaEventElapsedTime(&pf->last_ms, pf->ev0, pf->ev1));
     pf->last_launches = launches;
-    pf->last_events = (long long)h_cnt;
+    return DPOMP_OK;
+}
+
+int dpomp_run_partial_finish(dpomp_pf* pf, double* out, int nb, int out_mode) {
+    CK(cudaStreamSynchronize(pf->stream));
+    if (out_mode == 0) memcpy(out, pf->h_ll, (size_t)nb * sizeof(double));
+    CK(cudaEventElapsedTime(&pf->last_ms, pf->ev0, pf->ev1));
+    pf->last_events = (long long)*pf->h_cnt;
     pf->kernel_ms[0] = pf->kernel_ms[1] = 0.f;
     pf->kernel_launches[0] = pf->kernel_launches[1] = 0;
     for (size_t i = 0; i < pf->kev_kind.size(); ++i) {
@@ -471,6 +418,13 @@ static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, 
     }
     pf->initialised = true;
     return DPOMP_OK;
+}
+
+static int run_partial(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax, double* out,
+                       bool out_on_device) {
+    const int mode = out_on_device ? 1 : 0;
+    int rc = dpomp_run_partial_enqueue(pf, theta, theta_on_device, nb, ymin, ymax, out, mode);
+    return rc ? rc : dpomp_run_partial_finish(pf, out, nb, mode);
 }
 
 int dpomp_pf_loglik(dpomp_pf* pf, const double* theta, int32_t nb, double* out_ll) {

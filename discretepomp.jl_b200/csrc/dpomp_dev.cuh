@@ -128,7 +128,7 @@ __device__ __forceinline__ Level2 combine_level2(const double* gm_b, const doubl
 struct ChunkPerm {
     int ncf, m, q, r;
 };
-__host__ __device__ __forceinline__ int chunk_sigma(const ChunkPerm& p, int rr, int qq) {
+__host__ __device__ __forceinline__ int chunk_sigma(const ChunkPerm& p, int rr, int qq) {  // < n_pad / 32
     return rr * p.q + (rr < p.r ? rr : p.r) + qq;
 }
 __host__ __device__ __forceinline__ long long perm_pos(const ChunkPerm& p, long long i) {

@@ -110,6 +110,95 @@ struct ModelHost {
     std::vector<double> obs_ysum;
 };
 
+}  // namespace dpomp
+
+// ---- the opaque handles of include/dpomp.h (host-side state; shared by capi.cu and comm.cu) -------------------------
+struct dpomp_model {
+    dpomp::ModelHost h;
+};
+
+struct dpomp_pf {
+    const dpomp_model* model = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long n = 0, n_pad = 0;
+    int n_batch = 0, ntiles = 0, items = 4, tile = 1024;
+    int rs_type = DPOMP_RS_SYSTEMATIC, sim_precision = DPOMP_SIM_F32;
+    long long max_events = 1ll << 20;
+    uint64_t seed = 0, call_index = 0, forced_key = 0;
+    bool key_forced = false;
+    long long batch_offset = 0;
+    int n_comp = 0, n_params = 0, n_obs = 0;
+    int32_t* pop[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* logw = nullptr;
+    double* wtile = nullptr;
+    double* cw = nullptr;
+    int32_t* anc = nullptr;
+    bool record_anc = false, initialised = false, last_resampled = false;
+    double *theta_dev = nullptr, *tile_m = nullptr, *tile_s = nullptr, *tile_f = nullptr, *tile_off = nullptr;
+    double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
+    double *grp_m = nullptr, *grp_s = nullptr, *grp_f = nullptr, *grp_off = nullptr;
+    unsigned int* grp_counter = nullptr;
+    int ngroups = 0;
+    unsigned int* tile_counter = nullptr;
+    unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
+    double *obs_time_dev = nullptr, *obs_ysum_dev = nullptr;
+    int64_t* slots_dev = nullptr;            // 2 * n_batch
+    unsigned long long* work_counter = nullptr;  // fused step kernel: arrival-order CTA tickets (monotone)
+    unsigned long long work_base = 0;
+    unsigned int* filt_gen = nullptr;            // [n_batch] generation of the last finished combine
+    unsigned int gen = 0;
+    int scatter_mode = DPOMP_SCATTER_DEFAULT;    // offspring placement: 0 reference order, 1 chunk-interleaved over the tiles
+    bool fused_enabled = true;
+    int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
+    int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
+    uint32_t* filter_ids_dev = nullptr;      // n_batch, valid when use_filter_ids
+    bool use_filter_ids = false;
+    double* h_theta = nullptr;               // pinned staging
+    double* h_ll = nullptr;
+    int64_t* h_slots = nullptr;
+    unsigned long long* h_cnt = nullptr;     // pinned: event count of the last call
+    float last_ms = 0.f;
+    int last_launches = 0;
+    long long last_events = 0;
+    // optional per-kernel timing (bench.py roofline): events around every launch of the last call
+    bool kernel_timing = false;
+    std::vector<cudaEvent_t> kev;      // 2 events per launch slot
+    std::vector<int> kev_kind;         // 0 = simulate+weight, 1 = resample
+    float kernel_ms[2] = {0.f, 0.f};
+    int kernel_launches[2] = {0, 0};
+};
+
+
+int dpomp_set_error(int code, const std::string& msg);  // sets the thread-local message of dpomp_last_error()
+// partial_log_likelihood! launch sequence split in two so that callers can append work on the handle's stream before the
+// single synchronisation: enqueue (out_mode 0: host `out`, 1: device `out`, 2: leave the increments in pf->ll_acc) + finish
+extern "C" int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_device, int nb, int ymin, int ymax,
+                                         double* out, int out_mode);
+extern "C" int dpomp_run_partial_finish(dpomp_pf* pf, double* out, int nb, int out_mode);
+
+struct dpomp_comm;
+namespace dpomp {
+
+// ---- multi-GPU helpers implemented in comm.cu (used by the MBP store in mbp.cu) ---------------------------------------
+struct MigrationPlan {  // 1-based LOCAL slots; send / recv lists ordered by peer rank, then by destination index
+    std::vector<int64_t> local_src, send_slots, recv_slots;
+    std::vector<int> send_counts, recv_counts;
+};
+void migration_plan(const int64_t* nidx, int64_t n_total, int world, int rank, MigrationPlan& out);
+int comm_alltoallv_bytes(dpomp_comm* c, const void* send, const size_t* send_bytes, void* recv, const size_t* recv_bytes,
+                         cudaStream_t stream);
+int comm_rank(const dpomp_comm* c);
+int comm_world(const dpomp_comm* c);
+struct CommScratch {
+    int64_t *h_slots, *d_slots;
+    unsigned char *d_send, *d_recv;
+    int *h_int, *d_int;
+};
+int comm_scratch(dpomp_comm* c, size_t slots, size_t send_bytes, size_t recv_bytes, size_t ints, CommScratch* out);
+
 // launchers implemented in the kernel TUs; all asynchronous on `stream`; return cudaGetLastError()
 cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, int fused, const SimLaunch& a, cudaStream_t stream);
 // co-resident CTAs of the fused step kernel for this model / geometry on the current device (0 = unavailable)

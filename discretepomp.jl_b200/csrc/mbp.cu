@@ -472,11 +472,7 @@ __global__ void mbp_reset_kernel(const __grid_constant__ MbpModel m, MbpStore st
 // ------------------------------------------------------------------------------------------------------------
 using namespace dpomp;
 
-struct dpomp_model {  // same layout as in capi.cu
-    ModelHost h;
-};
-extern "C" const char* dpomp_last_error(void);
-int dpomp_set_error(int code, const std::string& msg);  // defined in capi.cu
+// struct dpomp_model and dpomp_set_error: dpomp_internal.cuh
 
 #define MCK(expr)                                                                                         \
     do {                                                                                                  \
@@ -750,6 +746,94 @@ int dpomp_mbp_export(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets,
 int dpomp_mbp_import(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
                      const void* dev_times, const void* dev_types) {
     return mbp_pack(h, slots, offsets, n, const_cast<void*>(dev_fixed), const_cast<void*>(dev_times), const_cast<void*>(dev_types), 1);
+}
+
+// ptcls2[p] = deepcopy(ptcls[nidx[p]]) (src/hmm_ibis.jl:196-199) across ranks: nidx is the GLOBAL 1-based ancestor vector of
+// all n_total theta-particles.  Two-phase exchange over NCCL on the store's stream: event counts first, then the packed
+// fixed records (64 B per particle), event times (f64) and event types (u8); local ancestors are copied on the device.
+int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx, int64_t n_total) {
+    if (!h || !c || !nidx) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const int world = comm_world(c), rank = comm_rank(c);
+    for (int64_t p = 0; p < n_total; ++p)
+        if (nidx[p] < 1 || nidx[p] > n_total) return dpomp_set_error(DPOMP_ERR_ARG, "ancestor index out of range");
+    if (world == 1) return dpomp_mbp_permute(h, nidx, (int32_t)n_total);
+    MCK(cudaSetDevice(h->device));
+    MigrationPlan pl;
+    migration_plan(nidx, n_total, world, rank, pl);
+    const size_t n_send = pl.send_slots.size(), n_recv = pl.recv_slots.size(), n_loc = pl.local_src.size();
+    if ((int)n_loc > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "this rank's block exceeds the store");
+    cudaStream_t st = h->stream;
+    // phase 1: event counts
+    std::vector<int> all_len((size_t)h->n);
+    MCK(cudaMemcpyAsync(all_len.data(), h->store[h->cur].len, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    CommScratch sc;
+    int rc = comm_scratch(c, 0, 0, 0, n_send + n_recv, &sc);
+    if (rc) return rc;
+    std::vector<size_t> sb((size_t)world), rb((size_t)world);
+    for (size_t k = 0; k < n_send; ++k) sc.h_int[k] = all_len[(size_t)pl.send_slots[k] - 1];
+    for (int r = 0; r < world; ++r) {
+        sb[(size_t)r] = (size_t)pl.send_counts[(size_t)r] * sizeof(int);
+        rb[(size_t)r] = (size_t)pl.recv_counts[(size_t)r] * sizeof(int);
+    }
+    MCK(cudaMemcpyAsync(sc.d_int, sc.h_int, n_send * sizeof(int), cudaMemcpyHostToDevice, st));
+    rc = comm_alltoallv_bytes(c, sc.d_int, sb.data(), sc.d_int + n_send, rb.data(), st);
+    if (rc) return rc;
+    MCK(cudaMemcpyAsync(sc.h_int + n_send, sc.d_int + n_send, n_recv * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    // phase 2: payload.  packed layout per direction: [fixed: n x 64 B][times: events x 8 B][types: events x 1 B]
+    std::vector<int64_t> off_s(n_send + 1, 0), off_r(n_recv + 1, 0);
+    for (size_t k = 0; k < n_send; ++k) off_s[k + 1] = off_s[k] + sc.h_int[k];
+    for (size_t k = 0; k < n_recv; ++k) {
+        if (sc.h_int[n_send + k] < 0 || sc.h_int[n_send + k] > h->cap) return dpomp_set_error(DPOMP_ERR_COMM, "received trajectory length out of range");
+        off_r[k + 1] = off_r[k] + sc.h_int[n_send + k];
+    }
+    const size_t ev_s = (size_t)off_s[n_send], ev_r = (size_t)off_r[n_recv];
+    const size_t fixed_b = (size_t)kMbpFixedWords * sizeof(int);
+    const size_t n_slots = 2 * n_send + n_loc + 2 * n_recv;
+    rc = comm_scratch(c, n_slots, n_send * fixed_b + ev_s * 9 + 64, n_recv * fixed_b + ev_r * 9 + 64, n_send + n_recv, &sc);
+    if (rc) return rc;
+    int64_t* hs = sc.h_slots;
+    for (size_t k = 0; k < n_send; ++k) { hs[k] = pl.send_slots[k]; hs[n_send + k] = off_s[k]; }
+    for (size_t k = 0; k < n_loc; ++k) hs[2 * n_send + k] = pl.local_src[k];
+    for (size_t k = 0; k < n_recv; ++k) { hs[2 * n_send + n_loc + k] = pl.recv_slots[k]; hs[2 * n_send + n_loc + n_recv + k] = off_r[k]; }
+    MCK(cudaMemcpyAsync(sc.d_slots, hs, n_slots * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int* fx_s = (int*)sc.d_send; double* tm_s = (double*)(sc.d_send + n_send * fixed_b); unsigned char* ty_s = sc.d_send + n_send * fixed_b + ev_s * 8;
+    int* fx_r = (int*)sc.d_recv; double* tm_r = (double*)(sc.d_recv + n_recv * fixed_b); unsigned char* ty_r = sc.d_recv + n_recv * fixed_b + ev_r * 8;
+    if (n_send) {
+        mbp_pack_kernel<<<(unsigned)n_send, 128, 0, st>>>(h->store[h->cur], sc.d_slots, sc.d_slots + n_send, fx_s, tm_s, ty_s, h->cap, h->dm.n_comp, 0);
+        MCK(cudaGetLastError());
+    }
+    std::vector<size_t> es((size_t)world, 0), er((size_t)world, 0);  // events per peer
+    {
+        size_t ks = 0, kr = 0;
+        for (int r = 0; r < world; ++r) {
+            for (int j = 0; j < pl.send_counts[(size_t)r]; ++j, ++ks) es[(size_t)r] += (size_t)(off_s[ks + 1] - off_s[ks]);
+            for (int j = 0; j < pl.recv_counts[(size_t)r]; ++j, ++kr) er[(size_t)r] += (size_t)(off_r[kr + 1] - off_r[kr]);
+        }
+    }
+    for (int part = 0; part < 3; ++part) {
+        for (int r = 0; r < world; ++r) {
+            sb[(size_t)r] = part == 0 ? (size_t)pl.send_counts[(size_t)r] * fixed_b : es[(size_t)r] * (part == 1 ? 8 : 1);
+            rb[(size_t)r] = part == 0 ? (size_t)pl.recv_counts[(size_t)r] * fixed_b : er[(size_t)r] * (part == 1 ? 8 : 1);
+        }
+        const void* sp = part == 0 ? (const void*)fx_s : part == 1 ? (const void*)tm_s : (const void*)ty_s;
+        void* rp = part == 0 ? (void*)fx_r : part == 1 ? (void*)tm_r : (void*)ty_r;
+        rc = comm_alltoallv_bytes(c, sp, sb.data(), rp, rb.data(), st);
+        if (rc) return rc;
+    }
+    if (n_loc) {
+        mbp_copy_kernel<<<(unsigned)n_loc, 128, 0, st>>>(h->store[h->cur ^ 1], h->store[h->cur], nullptr, sc.d_slots + 2 * n_send, h->cap, h->dm.n_comp);
+        MCK(cudaGetLastError());
+        h->cur ^= 1;
+    }
+    if (n_recv) {
+        mbp_pack_kernel<<<(unsigned)n_recv, 128, 0, st>>>(h->store[h->cur], sc.d_slots + 2 * n_send + n_loc, sc.d_slots + 2 * n_send + n_loc + n_recv,
+                                                          fx_r, tm_r, ty_r, h->cap, h->dm.n_comp, 1);
+        MCK(cudaGetLastError());
+    }
+    MCK(cudaStreamSynchronize(st));
+    return DPOMP_OK;
 }
 
 int dpomp_mbp_get_states(dpomp_mbp* h, int32_t n, int64_t* out) {

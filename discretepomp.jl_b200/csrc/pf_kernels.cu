@@ -68,7 +68,7 @@ int sim_kernel_supported(int n_comp, int n_events) {
 #ifndef DPOMP_RS_MINB
 #define DPOMP_RS_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
-template <int ITEMS, int RS>
+template <int ITEMS, int RS, bool PERM>
 __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
     constexpr int CHUNK = 32 * ITEMS;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
                     a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
     DPOMP_STAMP(1, 2);
-    resample_tile<ITEMS, int, false, RS>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
+    resample_tile<ITEMS, int, false, RS, PERM>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
     DPOMP_STAMP(1, 4);
 }
 
@@ -192,14 +192,15 @@ cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t str
     const size_t smem = (size_t)kBlockThreads * items * a.n_comp * sizeof(int);  // staged ancestor states
     // one instantiation per resampler: the systematic one carries no stratified (Philox) code (multinomial only uses the
     // cw materialisation at the top of the kernel)
-    const bool strat = a.rs_type == DPOMP_RS_STRATIFIED;
+    const bool strat = a.rs_type == DPOMP_RS_STRATIFIED, perm = a.perm.ncf > 0;
     cudaError_t err;
-    if (items == kItemsSmall)
-        err = strat ? launch_pdl(pf_resample_kernel<kItemsSmall, DPOMP_RS_STRATIFIED>, grid, kBlockThreads, smem, stream, a)
-                    : launch_pdl(pf_resample_kernel<kItemsSmall, DPOMP_RS_SYSTEMATIC>, grid, kBlockThreads, smem, stream, a);
-    else
-        err = strat ? launch_pdl(pf_resample_kernel<kItemsLarge, DPOMP_RS_STRATIFIED>, grid, kBlockThreads, smem, stream, a)
-                    : launch_pdl(pf_resample_kernel<kItemsLarge, DPOMP_RS_SYSTEMATIC>, grid, kBlockThreads, smem, stream, a);
+#define DPOMP_RS_LAUNCH(IT, RS, PM) launch_pdl(pf_resample_kernel<IT, RS, PM>, grid, kBlockThreads, smem, stream, a)
+#define DPOMP_RS_PICK(IT)                                                                                              \
+    (strat ? (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_STRATIFIED, true) : DPOMP_RS_LAUNCH(IT, DPOMP_RS_STRATIFIED, false))   \
+           : (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_SYSTEMATIC, true) : DPOMP_RS_LAUNCH(IT, DPOMP_RS_SYSTEMATIC, false)))
+    err = items == kItemsSmall ? DPOMP_RS_PICK(kItemsSmall) : DPOMP_RS_PICK(kItemsLarge);
+#undef DPOMP_RS_PICK
+#undef DPOMP_RS_LAUNCH
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {
         const long long total = (long long)a.n_filters * a.n_pad;

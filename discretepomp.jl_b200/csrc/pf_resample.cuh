@@ -36,7 +36,7 @@ __device__ __forceinline__ T ld_combine(const T* p) {  // CG: the value was writ
     if constexpr (CG) return __ldcg(p); else return *p;
 }
 
-template <int ITEMS, typename SrcT, bool CG, int RS = 0>
+template <int ITEMS, typename SrcT, bool CG, int RS = 0, bool PERM = true>
 __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, uint32_t gfilter, const double (&incl)[ITEMS],
                                               const SrcT* st_tile, int stride, int* am_all, int* warp_max_s, long long* lohi_s) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -69,6 +69,10 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     const int nvalid = rem < TILE ? (int)rem : TILE;
     // raw counts (n_particles < 2^31); the last valid item and the padding close the tile's range (clamped to hi below)
     int er[ITEMS];
+#ifdef DPOMP_RS_INLINE_CORRECT
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) er[k] = (int)resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
+#else
     unsigned todo = 0;  // items whose closed-form guess needs the exact correction
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -93,6 +97,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) er[j] = (k == j) ? e_k : er[j];
     }
+#endif
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k)
         if (tid * ITEMS + k >= nvalid - 1) er[k] = 0x7fffffff;
@@ -184,39 +189,62 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
         __syncwarp();
-        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores.
-        // Row of offspring i = lo + wlo + j * 32 + lane: consecutive j advance the chunk index by one, so (k mod M, k div M)
-        // is kept incrementally (one division per window).
+        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
         int srcq[ITEMS];
-        long long row[ITEMS];
-        {
-            const long long i0 = lo + wlo + lane;
-            int k = (int)(i0 >> 5);
-            int rr = k % a.perm.m, qq = k / a.perm.m;
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) {
-                const int pidx = j * 32 + lane;
-                srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
-                row[j] = (k < a.perm.ncf) ? (((long long)chunk_sigma(a.perm, rr, qq) << 5) | (i0 & 31)) : i0 + j * 32;
-                ++k;
-                if (++rr == a.perm.m) { rr = 0; ++qq; }
+        for (int j = 0; j < ITEMS; ++j) {
+            const int pidx = j * 32 + lane;
+            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+        }
+        if (!PERM || a.perm.ncf == 0) {  // the reference's row order: offspring i in row i
+            for (int c = 0; c < a.n_comp; ++c) {
+                const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
+                int32_t* dc = dst_b + (size_t)c * a.n_pad + lo + wlo + lane;
+                int vals[ITEMS];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0) dc[j * 32] = vals[j];
             }
-        }
-        for (int c = 0; c < a.n_comp; ++c) {
-            const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
-            int32_t* dc = dst_b + (size_t)c * a.n_pad;
-            int vals[ITEMS];
+            if (a.anc) {
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0)
+                        a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+            }
+        } else {
+            // Row of offspring i = lo + wlo + j * 32 + lane: consecutive j advance the chunk index by one, so
+            // (k mod M, k div M) is kept incrementally (one division per window).  n_pad < 2^31: int rows.
+            int row[ITEMS];
+            {
+                const int i0 = (int)(lo + wlo) + lane;
+                int k = i0 >> 5;
+                int rr = k % a.perm.m, qq = k / a.perm.m;
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) dc[row[j]] = vals[j];
-        }
-        if (a.anc) {
+                for (int j = 0; j < ITEMS; ++j) {
+                    row[j] = (k < a.perm.ncf) ? ((chunk_sigma(a.perm, rr, qq) << 5) | (i0 & 31)) : i0 + j * 32;
+                    ++k;
+                    if (++rr == a.perm.m) { rr = 0; ++qq; }
+                }
+            }
+            for (int c = 0; c < a.n_comp; ++c) {
+                const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
+                int32_t* dc = dst_b + (size_t)c * a.n_pad;
+                int vals[ITEMS];
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (srcq[j] >= 0) a.anc[(size_t)b * a.n_pad + row[j]] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0) dc[row[j]] = vals[j];
+            }
+            if (a.anc) {
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    if (srcq[j] >= 0) a.anc[(size_t)b * a.n_pad + row[j]] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+            }
         }
         __syncwarp();
     }

@@ -1,8 +1,11 @@
-"""Multi-GPU plumbing for the outer layers: one process per GPU, torch.distributed over NCCL / NVLink.
+"""Multi-GPU plumbing for the outer layers: one process per GPU.
 
 theta-particles (SMC^2, MBP-IBIS) and chains (pMCMC) are partitioned contiguously over ranks.  The small per-particle
 scalars (gx, aw) are exchanged with an all-gather; resampled filters move between ranks with one all-to-all of packed
-int32 population blocks (dpomp_pf_export_filters / dpomp_pf_import_filters).  Every rank draws the same host random
+int32 population blocks.  On GPUs every exchange goes through the C ABI (dpomp_comm_*, dpomp_pf_partial_allgather,
+dpomp_pf_resample_migrate, dpomp_mbp_resample_migrate: NCCL inside libdpomp on the handles' own streams) -- the same entry
+points a Julia host binds; torch.distributed only bootstraps the NCCL unique id.  Under the gloo backend (the CPU tests of
+the host logic, world size 2) the exchanges run over torch.distributed instead.  Every rank draws the same host random
 numbers (same seed), so all ranks take identical outer-layer decisions without further communication, and particle-filter
 streams are keyed by the GLOBAL filter index, which makes results independent of the number of ranks.
 """
@@ -27,11 +30,47 @@ class Comm:
                 self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self._ag_bufs = {}  # staging buffers of allgather_f64, by block size
         self.device = None  # torch device of the exchange buffers (cuda:k under NCCL, cpu under gloo)
+        self._h = None      # dpomp_comm handle: NCCL inside libdpomp (set under the nccl backend)
         if self.dist is not None:
             import torch
 
             self.device = (torch.device("cuda", torch.cuda.current_device())
                            if self.dist.get_backend() == "nccl" else torch.device("cpu"))
+            if self.dist.get_backend() == "nccl":
+                self._create_library_comm(torch.cuda.current_device())
+
+    def _create_library_comm(self, device: int) -> None:
+        """rank 0 draws the NCCL unique id through the C ABI, torch.distributed broadcasts the bytes, every rank joins."""
+        import ctypes as C
+
+        from . import _capi
+
+        nbytes = 128  # DPOMP_UNIQUE_ID_BYTES
+        box = [None]
+        if self.rank == 0:
+            buf = (C.c_ubyte * nbytes)()
+            _capi.check(_capi.lib().dpomp_comm_unique_id(buf, nbytes))
+            box[0] = bytes(buf)
+        self.dist.broadcast_object_list(box, src=0)
+        uid = (C.c_ubyte * nbytes).from_buffer_copy(box[0])
+        h = C.c_void_p()
+        _capi.check(_capi.lib().dpomp_comm_create(uid, nbytes, self.rank, self.world, device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if self._h:
+                from . import _capi
+
+                _capi.lib().dpomp_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        """dpomp_comm handle (None when the exchanges run over torch.distributed / gloo or in a single process)."""
+        return self._h
 
     # -- partition -------------------------------------------------------------------------------------------
     def bounds(self, n: int) -> Tuple[int, int]:
@@ -47,6 +86,14 @@ class Comm:
         local = np.ascontiguousarray(local, dtype=np.float64)
         if self.dist is None:
             return local
+        if self._h is not None:  # C ABI: pinned staging + ncclAllGather inside the library
+            from . import _capi
+
+            width = local.shape[1] if local.ndim == 2 else 1
+            out = np.empty((n_total, width) if local.ndim == 2 else n_total, dtype=np.float64)
+            _capi.check(_capi.lib().dpomp_comm_allgather_f64(self._h, _capi.ptr(local) if local.size else None, int(n_total),
+                                                             int(width), _capi.ptr(out)))
+            return out
         import torch
 
         sizes = [partition_bounds(n_total, self.world, r) for r in range(self.world)]

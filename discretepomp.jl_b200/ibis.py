@@ -124,6 +124,13 @@ class FilterBank:
         key = self._next_key()
         loc = np.zeros(0)
         t0 = time.perf_counter()
+        if self.comm.handle is not None and hasattr(self.main, "partial_allgather"):
+            # C ABI: kernels -> ncclAllGather -> one copy to the host on the filters' stream, one synchronisation
+            if self.n_local:
+                self.main.set_stream_key(key)
+            out = self.main.partial_allgather(self.comm, theta[:, self.lo:self.hi], ymin, ymax, self.outer_p)
+            self._tick("filter_step+allgather", t0)
+            return out
         if self.n_local:
             self.main.set_stream_key(key)
             loc = self.main.partial(theta[:, self.lo:self.hi], ymin, ymax)
@@ -139,6 +146,11 @@ class FilterBank:
         if self.comm.world == 1:
             self.main.permute(nidx0 + 1)
             self._tick("resample_local", t0)
+            return
+        if self.comm.handle is not None and hasattr(self.main, "resample_migrate"):
+            # C ABI: plan, pack, grouped ncclSend/ncclRecv, local gather and unpack on the filters' stream
+            self.main.resample_migrate(self.comm, nidx0 + 1, self.outer_p)
+            self._tick("resample_migrate", t0)
             return
         local_src, send_slots, send_counts, recv_slots, recv_counts = migration_plan(
             nidx0, self.outer_p, self.comm.world, self.comm.rank)

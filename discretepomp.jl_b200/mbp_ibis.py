@@ -89,6 +89,11 @@ class MbpParticles:
         s = _capi.as_i64(nidx)
         _capi.check(_capi.lib().dpomp_mbp_permute(self._h, _capi.ptr(s), len(s)))
 
+    def resample_migrate(self, comm, nidx, n_total: int) -> None:
+        """dpomp_mbp_resample_migrate: particle p <- particle nidx[p] (1-based GLOBAL indices) across the ranks of `comm`."""
+        s = _capi.as_i64(nidx)
+        _capi.check(_capi.lib().dpomp_mbp_resample_migrate(self._h, comm.handle, _capi.ptr(s), int(n_total)))
+
     # -- migration between ranks (lengths first, then one packed payload) -------------------------------------
     FIXED_WORDS = 16
 
@@ -177,6 +182,9 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
         """ptcls2[p] = deepcopy(ptcls[nidx[p]]) (:196-199) across ranks."""
         if comm.world == 1:
             ptcls.permute(nidx)
+            return
+        if comm.handle is not None and hasattr(ptcls, "resample_migrate"):  # C ABI: NCCL inside the library
+            ptcls.resample_migrate(comm, nidx, outer_p)
             return
         import torch
         from .distributed import migration_plan

@@ -172,6 +172,20 @@ class ParticleFilter:
                                                  _capi.ptr(out)))
         return out
 
+    def partial_allgather(self, comm, theta_local, ymin: int, ymax: int, n_total: int) -> np.ndarray:
+        """dpomp_pf_partial_allgather: partial() for this rank's block of the n_total filters, then the increments of ALL
+        ranks (one stream-ordered sequence inside the library: kernels -> ncclAllGather -> one copy to the host)."""
+        th = self._theta(theta_local) if np.size(theta_local) else np.zeros((0, self.n_params))
+        out = np.empty(int(n_total), dtype=np.float64)
+        _capi.check(_capi.lib().dpomp_pf_partial_allgather(self._h, comm.handle, _capi.ptr(th) if th.size else None, th.shape[0],
+                                                           int(ymin), int(ymax), int(n_total), _capi.ptr(out)))
+        return out
+
+    def resample_migrate(self, comm, nidx, n_total: int) -> None:
+        """dpomp_pf_resample_migrate: filter p <- filter nidx[p] (1-based GLOBAL indices) across the ranks of `comm`."""
+        idx = _capi.as_i64(nidx)
+        _capi.check(_capi.lib().dpomp_pf_resample_migrate(self._h, comm.handle, _capi.ptr(idx), int(n_total)))
+
     def permute(self, nidx: np.ndarray) -> None:
         idx = _capi.as_i64(nidx)
         _capi.check(_capi.lib().dpomp_pf_permute(self._h, _capi.ptr(idx), len(idx)))

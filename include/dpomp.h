@@ -35,7 +35,8 @@ typedef enum dpomp_status {
     DPOMP_ERR_CUDA = -2,     /* CUDA runtime failure / no device (message has the CUDA error string) */
     DPOMP_ERR_MODEL = -3,    /* model descriptor not representable as a device rate table             */
     DPOMP_ERR_STATE = -4,    /* call sequence error (e.g. partial with ymin>1 on a never-run filter)  */
-    DPOMP_ERR_OVERFLOW = -5  /* reserved; event-cap overflow is reported by dpomp_pf_overflow_count    */
+    DPOMP_ERR_OVERFLOW = -5, /* reserved; event-cap overflow is reported by dpomp_pf_overflow_count    */
+    DPOMP_ERR_COMM = -6      /* NCCL failure or NCCL library not loadable (multi-GPU entry points only) */
 } dpomp_status;
 
 /* rs_type as in get_log_pdf_fn (src/hmm_particle_filter.jl:87-94): 1 systematic, 2 stratified, 3 multinomial */
@@ -243,6 +244,38 @@ int dpomp_mbp_get_particle(dpomp_mbp* mbp, int32_t p, int32_t which, int64_t* fc
  */
 int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double* w, int64_t n, const double* u,
                            int64_t n_u, int64_t n_out, int64_t* out_idx, int32_t device);
+
+/*
+ * Multi-GPU: one process per GPU, theta-particles / chains partitioned contiguously over the ranks
+ * (dpomp_partition_bounds), NCCL over NVLink inside the library, every collective enqueued on the stream of the handle
+ * whose data it moves.  The reference is single-process; these entry points are what a sharded host (Julia with
+ * Distributed / MPI.jl, or the Python host of this repository) calls around run_pibis / run_mbp_ibis:
+ *   rank 0: dpomp_comm_unique_id -> host-side broadcast of the DPOMP_UNIQUE_ID_BYTES bytes -> every rank: dpomp_comm_create.
+ * world == 1 communicators need no id and make every entry point below a local operation.
+ */
+typedef struct dpomp_comm dpomp_comm;
+#define DPOMP_UNIQUE_ID_BYTES 128
+int dpomp_comm_unique_id(void* out_id, int32_t nbytes);
+int dpomp_comm_create(const void* id, int32_t nbytes, int32_t rank, int32_t world, int32_t device, dpomp_comm** out_comm);
+int dpomp_comm_destroy(dpomp_comm* comm);
+int dpomp_comm_info(const dpomp_comm* comm, int32_t* out_rank, int32_t* out_world);
+int dpomp_comm_barrier(dpomp_comm* comm);
+/* rank's contiguous block [lo, hi) (0-based) of n items; block sizes differ by at most one */
+int dpomp_partition_bounds(int64_t n, int32_t world, int32_t rank, int64_t* out_lo, int64_t* out_hi);
+/* all-gather of per-item rows of `width` doubles (host buffers): local = this rank's block of the n_total items,
+ * out = all n_total rows.  The theta-weight exchange of run_pibis (src/hmm_ibis.jl:57-62) for host-computed values. */
+int dpomp_comm_allgather_f64(dpomp_comm* comm, const double* local, int64_t n_total, int32_t width, double* out);
+/* dpomp_pf_partial for this rank's block of the n_total filters (n_batch_used must equal the block size) + all-gather of
+ * the increments of ALL ranks into out_all[n_total] (src/hmm_ibis.jl:53-62): kernels -> ncclAllGather -> one copy to the
+ * host, all on the filter's stream, one synchronisation. */
+int dpomp_pf_partial_allgather(dpomp_pf* pf, dpomp_comm* comm, const double* theta_local, int32_t n_batch_used,
+                               int32_t ymin, int32_t ymax, int64_t n_total, double* out_all);
+/* outer resample across ranks, pop2[p] .= pop[nidx[p]] (src/hmm_ibis.jl:71-79): nidx[n_total] are GLOBAL 1-based ancestors,
+ * identical on every rank; remote ancestors arrive as packed int32 populations over NVLink (grouped ncclSend/ncclRecv) */
+int dpomp_pf_resample_migrate(dpomp_pf* pf, dpomp_comm* comm, const int64_t* nidx, int64_t n_total);
+/* the same for the MBP-IBIS trajectory store, ptcls2[p] = deepcopy(ptcls[nidx[p]]) (src/hmm_ibis.jl:194-201): two-phase
+ * exchange (event counts, then fixed records + event times + event types) */
+int dpomp_mbp_resample_migrate(dpomp_mbp* mbp, dpomp_comm* comm, const int64_t* nidx, int64_t n_total);
 
 /* diagnostics: the f32 uniform conversions of the event loop evaluated on the device for the given 32-bit Philox words:
  * out_wait in (0, 1] (waiting time), out_event in [0, 1) (choose_event, src/hmm_cmn.jl:5) */
