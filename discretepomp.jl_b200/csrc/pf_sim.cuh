@@ -353,10 +353,12 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
             ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
         }
+#ifndef DPOMP_NO_EVCOUNT
         if ((tid & 31) == 1) {
             if (ev_local) atomicAdd(a.ev_count, ev_local);
             if (ovf_local) atomicAdd(a.ovf_count, ovf_local);
         }
+#endif
 
         if (int_obs) {
             const int ys = (int)ysum;

@@ -125,3 +125,20 @@ def test_bad_arguments_are_rejected_by_the_abi(built_lib, dp):
     out = np.zeros(4, dtype=np.int64)
     w = np.ones(4)
     assert built_lib.dpomp_resample_indices(7, 0, w.ctypes.data, 4, w.ctypes.data, 4, 4, out.ctypes.data, -1) == -1
+
+
+def test_c_driver_compiles_and_links_against_the_header(built_lib, tmp_path):
+    """tests/c_driver.c (the no-Python host of the GPU suite) compiles as C11 against include/dpomp.h and links against the
+    in-tree library; without a GPU it stops at the first device query with a clean error, not a crash."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    libdir = os.path.join(ROOT, "discretepomp.jl_b200", "lib")
+    exe = str(tmp_path / "c_driver")
+    subprocess.run([shutil.which("gcc"), "-O1", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_driver.c"), "-o", exe, "-L", libdir, "-ldpomp", "-lm", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True, text=True)
+    import torch
+    if not torch.cuda.is_available():
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 1 and "FAIL" in res.stderr
