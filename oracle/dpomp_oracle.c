@@ -138,6 +138,11 @@ static double obs_model(const dpomp_model_desc* m, int t, const int64_t* x) {
     return tmp1 - ((double)(d * d) / tmp2);
 }
 
+/* function-level probes for the reference known-answer vectors (tests/test_reference_kats.py) */
+void orc_cum_rates(const dpomp_model_desc* m, const double* th, const int64_t* x, double* cum) { cum_rates(m, th, x, cum); }
+int orc_choose_event(const double* cum, int n_events, double u) { return choose_event(cum, n_events, u) + 1; } /* 1-based */
+double orc_obs_model(const dpomp_model_desc* m, int t, const int64_t* x) { return obs_model(m, t, x); }
+
 /* the event loop of iterate_particles! (src/hmm_particle_filter.jl:19-27) for ONE particle over (t, tmax].
  * Attempt k (k = number of events so far) draws Philox2x32 words (waiting time, event type). */
 static int64_t sim_interval(const dpomp_model_desc* m, const double* th, int64_t* x, double time, double tmax,

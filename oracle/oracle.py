@@ -123,6 +123,28 @@ def gillespie_sim(desc, theta, key: int = 0, max_events: int = 1 << 24):
     return out, ev.value
 
 
+def cum_rates(desc, theta, x) -> np.ndarray:
+    """rate_function + cumsum! (src/hmm_particle_filter.jl:20-21) at one state."""
+    th = np.ascontiguousarray(theta, dtype=np.float64); xs = np.ascontiguousarray(x, dtype=np.int64)
+    out = np.zeros(desc.n_events)
+    lib().orc_cum_rates(C.byref(desc), _p(th), _p(xs), _p(out))
+    return out
+
+
+def choose_event(cum, u: float) -> int:
+    """choose_event (src/hmm_cmn.jl:4-10) with the rand() draw given; 1-based event."""
+    c = np.ascontiguousarray(cum, dtype=np.float64)
+    return int(lib().orc_choose_event(_p(c), len(c), C.c_double(u)))
+
+
+def obs_model(desc, t: int, x) -> float:
+    """gom2 (src/hmm_examples.jl:59-67) for observation t (0-based) at state x."""
+    xs = np.ascontiguousarray(x, dtype=np.int64)
+    f = lib().orc_obs_model
+    f.restype = C.c_double
+    return float(f(C.byref(desc), int(t), _p(xs)))
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())
 
