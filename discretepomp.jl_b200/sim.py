@@ -7,6 +7,8 @@ observations filled in by the model's obs_function).
 """
 from __future__ import annotations
 
+import os
+from decimal import Decimal
 from typing import List, Union
 
 import numpy as np
@@ -62,3 +64,50 @@ def gillespie_sim(model: DPOMPModel, parameters, tmax: float = 100.0, num_obs: i
     if verbose:
         print(" - finished.")
     return out[0] if n_sims == 1 else out
+
+
+def _jl_float(x: float) -> str:
+    """Julia's `string(::Float64)`: shortest round-trip digits, positional for 1e-4 <= |x| < 1e6, else d.ddde±n."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Inf" if x > 0 else "-Inf"
+    if x == 0.0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()  # repr: shortest digits that round-trip, like Ryu
+    digits = "".join(map(str, digits)).rstrip("0") or "0"
+    e10 = len("".join(map(str, Decimal(repr(x)).as_tuple().digits))) + exp - 1  # decimal exponent of the first digit
+    neg = "-" if sign else ""
+    if -4 <= e10 < 6:
+        if e10 >= 0:
+            whole = digits[: e10 + 1].ljust(e10 + 1, "0")
+            frac = digits[e10 + 1:] or "0"
+            return f"{neg}{whole}.{frac}"
+        return f"{neg}0.{'0' * (-e10 - 1)}{digits}"
+    return f"{neg}{digits[0]}.{digits[1:] or '0'}e{e10}"
+
+
+def save_to_file(results: SimResults, dpath: str, literal: bool = False) -> None:
+    """save_to_file(results::SimResults, dpath) (src/hmm_utils.jl:35-72): writes `<dpath>sim.csv` (one row per event:
+    time, event type, state after the event) and `<dpath>obs.csv` (time, id, observed values); like the reference, `dpath`
+    is used as a prefix (`string(dpath, "sim.csv")`), so it normally ends with a path separator.
+    The reference's sim.csv header is `time, event,1` and every row carries the whole state as ONE Julia array literal
+    (`population` is a Vector of Vectors, so `size(results.population, 2) == 1`): `literal=True` reproduces those bytes;
+    the default writes one column per compartment, which is what the header suggests and what a CSV reader can parse."""
+    if dpath and not os.path.isdir(dpath):
+        os.makedirs(dpath, exist_ok=True)
+    traj = results.particle.trajectory
+    n_comp = len(results.population[0]) if len(results.population) else len(results.particle.initial_condition)
+    with open(f"{dpath}sim.csv", "w") as f:
+        f.write("time, event")
+        f.write(",1" if literal else "".join(f",{p + 1}" for p in range(n_comp)))
+        for i, ev in enumerate(traj):
+            f.write(f"\n{_jl_float(ev.time)},{int(ev.event_type)}")
+            x = results.population[i]
+            f.write(",[" + ", ".join(str(int(v)) for v in x) + "]" if literal else "".join(f",{int(v)}" for v in x))
+    with open(f"{dpath}obs.csv", "w") as f:
+        f.write("time,id")
+        f.write("".join(f",{p + 1}" for p in range(len(results.observations[0].val))))
+        for o in results.observations:
+            f.write(f"\n{_jl_float(o.time)},{int(o.obs_id)}" + "".join(f",{int(v)}" for v in o.val))

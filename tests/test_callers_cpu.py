@@ -146,3 +146,20 @@ def test_model_comparison_fanout_and_two_ranks(tmp_path):
     assert np.array_equal(a["bme"], [[20, 23], [21, 24], [22, 25]])
     assert np.allclose(a["mu"], -np.log(np.mean(np.exp(-a["bme"]), axis=0))) and np.allclose(a["sigma"], 1.0)
     assert np.array_equal(a["t00"], [0.0, 1.0]) and np.array_equal(a["t21"], [2.5, 3.5, 4.5])
+
+
+def test_save_to_file_writes_the_reference_csv_formats(dp, tmp_path):
+    """save_to_file(results::SimResults, dpath) (src/hmm_utils.jl:35-72): sim.csv + obs.csv; Julia float formatting."""
+    from dpomp_b200.sim import _jl_float
+    assert [_jl_float(v) for v in (20.0, 1e-5, 0.0001, 1234567.8, 100000.0, 0.30000000000000004)] == \
+        ["20.0", "1.0e-5", "0.0001", "1.2345678e6", "100000.0", "0.30000000000000004"]
+    part = dp.Particle(np.array([0.003, 0.1]), np.array([100, 1]), np.array([99, 1]),
+                       [dp.Event(1.25, 1), dp.Event(2.5, 2)], 0.0, np.zeros(2))
+    res = dp.SimResults("SIS", part, [np.array([99, 2]), np.array([100, 1])],
+                        [dp.Observation(20.0, 1, 1.0, np.array([100, 1])), dp.Observation(40.0, 1, 1.0, np.array([90, 11]))])
+    d = str(tmp_path) + os.sep
+    dp.save_to_file(res, d)
+    assert open(d + "sim.csv").read() == "time, event,1,2\n1.25,1,99,2\n2.5,2,100,1"
+    assert open(d + "obs.csv").read() == "time,id,1,2\n20.0,1,100,1\n40.0,1,90,11"
+    dp.save_to_file(res, d, literal=True)  # the reference's literal bytes: the state printed as one Julia array
+    assert open(d + "sim.csv").read() == "time, event,1\n1.25,1,[99, 2]\n2.5,2,[100, 1]"
