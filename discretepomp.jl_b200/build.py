@@ -108,6 +108,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return out
 
 
+def build_bounds_variant() -> str:
+    """lib/variants/libdpomp_bounds.so: the same library with -DDPOMP_BOUNDS_CHECK (every shared / global index of the
+    resample phase, the warp work queue and the MBP windows trapped when out of range).  Used by tests/test_gpu_bounds.py
+    as the stand-in for compute-sanitizer; never loaded by the product path."""
+    out = os.path.join(LIBDIR, "variants", "libdpomp_bounds.so")
+    stamp = out + ".stamp"
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "dpomp.h")]
+    digest = _digest(deps)
+    if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return out
+    build_variant("bounds", ["-DDPOMP_BOUNDS_CHECK"])
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return out
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--variant":
         print(build_variant(sys.argv[2], sys.argv[3:]))

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/dpomp.h"
 
@@ -41,6 +42,20 @@ __device__ __forceinline__ unsigned long long dpomp_gtime() {
     } while (0)
 #else
 #define DPOMP_STAMP(K, P) do { } while (0)
+#endif
+// Debug build only (-DDPOMP_BOUNDS_CHECK, lib/variants/libdpomp_bounds.so, tests/test_gpu_bounds.py): every shared / global
+// index of the resample phase, the warp work queue and the MBP windows is checked against its buffer and traps (the pool's
+// compute-sanitizer is closed).  The release build compiles the checks away.
+#ifdef DPOMP_BOUNDS_CHECK
+#define DPOMP_CHECK_IDX(i, n)                                                                                          \
+    do {                                                                                                               \
+        if (!((long long)(i) >= 0 && (long long)(i) < (long long)(n))) {                                               \
+            printf("dpomp bounds: %s:%d: index %lld outside [0, %lld)\n", __FILE__, __LINE__, (long long)(i), (long long)(n)); \
+            __trap();                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+#else
+#define DPOMP_CHECK_IDX(i, n) do { } while (0)
 #endif
 constexpr int kBlockThreads = DPOMP_BLOCK_THREADS;
 constexpr int kItemsLarge = DPOMP_ITEMS_LARGE, kItemsSmall = DPOMP_ITEMS_SMALL;

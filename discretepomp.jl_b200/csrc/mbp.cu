@@ -175,6 +175,7 @@ struct WarpIO {
     double* s_it; unsigned char* s_iy;   // [kMbpWin] window of the old list: events [ibase, ibase + kMbpWin)
     double* s_ft; unsigned char* s_fy;   // [kMbpWin] staged new events [fbase, fbase + kMbpWin)
     int ibase, fbase;
+    int capc;  // trajectory capacity (bounds-checked debug build)
     __device__ __forceinline__ void load(int start) {
         const int lane = threadIdx.x & 31;
         __syncwarp();
@@ -182,17 +183,34 @@ struct WarpIO {
         for (int i = lane; i < kMbpWin && start + i < ilen; i += 32) { s_it[i] = it[start + i]; s_iy[i] = iy[start + i]; }
         __syncwarp();
     }
-    __device__ __forceinline__ double in_time(int e) { if (e >= ibase + kMbpWin) load(e); return s_it[e - ibase]; }
-    __device__ __forceinline__ int in_type(int e) { if (e >= ibase + kMbpWin) load(e); return s_iy[e - ibase]; }
+    __device__ __forceinline__ double in_time(int e) {
+        if (e >= ibase + kMbpWin) load(e);
+        DPOMP_CHECK_IDX(e - ibase, kMbpWin);
+        DPOMP_CHECK_IDX(e, ilen);
+        return s_it[e - ibase];
+    }
+    __device__ __forceinline__ int in_type(int e) {
+        if (e >= ibase + kMbpWin) load(e);
+        DPOMP_CHECK_IDX(e - ibase, kMbpWin);
+        DPOMP_CHECK_IDX(e, ilen);
+        return s_iy[e - ibase];
+    }
     __device__ __forceinline__ void flush(int upto) {
         const int lane = threadIdx.x & 31;
         __syncwarp();
-        for (int i = lane; fbase + i < upto; i += 32) { ft[fbase + i] = s_ft[i]; fy[fbase + i] = s_fy[i]; }
+        for (int i = lane; fbase + i < upto; i += 32) {
+            DPOMP_CHECK_IDX(i, kMbpWin);
+#ifdef DPOMP_BOUNDS_CHECK
+            DPOMP_CHECK_IDX(fbase + i, capc);
+#endif
+            ft[fbase + i] = s_ft[i]; fy[fbase + i] = s_fy[i];
+        }
         __syncwarp();
         fbase = upto;
     }
     __device__ __forceinline__ void push(int pos, double t, int type1) {
         if (pos - fbase >= kMbpWin) flush(pos);
+        DPOMP_CHECK_IDX(pos - fbase, kMbpWin);
         if ((threadIdx.x & 31) == 0) { s_ft[pos - fbase] = t; s_fy[pos - fbase] = (unsigned char)type1; }
     }
     __device__ __forceinline__ void finish(int flen) { flush(flen); }
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_iterate_warp_kernel(
     if (p >= n) return;
     WarpShared& w = sh[warp];
     const int len0 = st.len[p];
-    WarpIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, len0};
+    WarpIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, len0, cap};
     mbp_iterate_body<WarpIO, MbpRates<MODEL>>(m, st, io, p, (threadIdx.x & 31) == 0, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key,
                                               id0, out_logg);
 }
@@ -406,7 +424,7 @@ __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_propose_warp_kernel(
     if (p >= n) return;
     WarpShared& w = sh[warp];
     WarpIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
-              xf.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, 0};
+              xf.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, 0, cap};
     const bool is_valid = valid[p] != 0;
     if (is_valid) io.load(0);
     mbp_propose_body<WarpIO, MbpRates<MODEL>>(m, xf, io, p, (threadIdx.x & 31) == 0, is_valid, theta_i, theta_f, obs_time, obs_ysum,

@@ -319,6 +319,17 @@ extern "C" int dpomp_debug_uniforms_f32(const uint32_t* words, int32_t n, float*
     return e == cudaSuccess ? DPOMP_OK : DPOMP_ERR_CUDA;
 }
 
+#ifdef DPOMP_BOUNDS_CHECK
+// bounds-checked debug build only: proves that the checker is live (a deliberately out-of-range index must trap)
+namespace dpomp {
+__global__ void bounds_selftest_kernel(int i, int n) { DPOMP_CHECK_IDX(i, n); }
+}  // namespace dpomp
+extern "C" int dpomp_debug_bounds_selftest(int i, int n) {
+    dpomp::bounds_selftest_kernel<<<1, 1>>>(i, n);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+#endif
+
 #ifdef DPOMP_PHASE_TIMERS
 extern "C" int dpomp_debug_phases_rs(unsigned long long* out /* [2][4096][8] */) {
     return (int)cudaMemcpyFromSymbol(out, dpomp::g_dpomp_phase, sizeof(unsigned long long) * 2 * 4096 * 8);

@@ -124,6 +124,9 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #endif
 
     const long long lo = lohi_s[0], hi = lohi_s[1];
+    DPOMP_CHECK_IDX(lo, a.n + 1);
+    DPOMP_CHECK_IDX(hi, a.n + 1);
+    DPOMP_CHECK_IDX(hi - lo, a.n + 1);
     int wprev_raw = -1;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
@@ -157,6 +160,9 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
                 if (am_all[mid] >= o) hq = mid; else lq = mid + 1;
             }
             const long long row = perm_pos(a.perm, lo + o - 1);
+            DPOMP_CHECK_IDX(lq, TILE);
+            DPOMP_CHECK_IDX(base_n + lq, a.n);
+            DPOMP_CHECK_IDX(row, a.n);
             for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + row] = (int)st_tile[(size_t)c * stride + lq];
             if (a.anc) a.anc[(size_t)b * a.n_pad + row] = (int32_t)(base_n + lq);
         }
@@ -170,7 +176,10 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             const int first = (k == 0) ? prev : emax[k - 1];
-            if (emax[k] > first && first < wlo + CHUNK && emax[k] > wlo) am_w[max(first - wlo, 0)] = lane * ITEMS + k;
+            if (emax[k] > first && first < wlo + CHUNK && emax[k] > wlo) {
+                DPOMP_CHECK_IDX(max(first - wlo, 0), CHUNK);
+                am_w[max(first - wlo, 0)] = lane * ITEMS + k;
+            }
         }
         __syncwarp();
         int am[ITEMS];
@@ -195,6 +204,13 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
         for (int j = 0; j < ITEMS; ++j) {
             const int pidx = j * 32 + lane;
             srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+            if (srcq[j] >= 0) {  // window entry: an ancestor of this warp's chunk; offspring row inside the filter
+                DPOMP_CHECK_IDX(srcq[j], CHUNK);
+                DPOMP_CHECK_IDX(base_n + warp * CHUNK + srcq[j], a.n);
+                DPOMP_CHECK_IDX(lo + wlo + pidx, a.n);
+            } else {
+                DPOMP_CHECK_IDX(wlo + pidx < wlast ? -1 : 0, 1);  // a live window slot must have an ancestor
+            }
         }
         if (!PERM || a.perm.ncf == 0) {  // the reference's row order: offspring i in row i
             for (int c = 0; c < a.n_comp; ++c) {
@@ -225,6 +241,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j) {
                     row[j] = (k < a.perm.ncf) ? ((chunk_sigma(a.perm, rr, qq) << 5) | (i0 & 31)) : i0 + j * 32;
+                    if (srcq[j] >= 0) DPOMP_CHECK_IDX(row[j], a.n);
                     ++k;
                     if (++rr == a.perm.m) { rr = 0; ++qq; }
                 }

@@ -177,6 +177,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         for (int c = 0; c < C; ++c)
             if (c < n_comp)
             {
+                DPOMP_CHECK_IDX(base_n + tid * ITEMS + ITEMS - 1, a.n_pad);
                 const Vec v = *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) st_s[c * TILE + tid * ITEMS + kk] = (SState)v.v[kk];
@@ -280,6 +281,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             const unsigned fmask = __ballot_sync(FULL, fin[s]);
             if (fmask) {  // warp-uniform: finished lanes park their particle and pull the next slot of the chunk
                 if (fin[s]) {
+                    DPOMP_CHECK_IDX(q[s], TILE);
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (c < n_comp) st_s[c * TILE + q[s]] = (SState)x[s][c];
@@ -292,6 +294,9 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     active[s] = slot < chunk_valid;
                     if (active[s]) {
                         q[s] = chunk0 + slot;
+                        DPOMP_CHECK_IDX(q[s], TILE);
+                        DPOMP_CHECK_IDX(slot, CHUNK);
+                        DPOMP_CHECK_IDX(base_n + q[s], a.n);
                         pc[s] = (uint32_t)(base_n + q[s]) ^ ss.a;
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;
@@ -388,6 +393,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                     const unsigned off = du[kk] - dmin;
                     av[kk] = du[kk] == kExcluded ? 0.0
                            : (off < (unsigned)kBlockThreads ? wtab_s[off] : exp(logw_of((double)du[kk]) - m_b));
+                    DPOMP_CHECK_IDX(du[kk] == kExcluded ? 0u : (off < (unsigned)kBlockThreads ? off : 0u), kBlockThreads);
                 }
             }
             if (a.record_logw) {
