@@ -75,6 +75,7 @@ _SIGS = {
     "dpomp_pf_set_max_events": (C.c_int, [_P, C.c_int64]),
     "dpomp_pf_set_batch_offset": (C.c_int, [_P, C.c_int64]),
     "dpomp_pf_set_fused": (C.c_int, [_P, C.c_int32]),
+    "dpomp_pf_set_persistent": (C.c_int, [_P, C.c_int32]),
     "dpomp_pf_set_scatter": (C.c_int, [_P, C.c_int32]),
     "dpomp_pf_set_filter_ids": (C.c_int, [_P, _P, C.c_int32]),
     "dpomp_pf_set_stream_key": (C.c_int, [_P, C.c_uint64]),

@@ -101,6 +101,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev); cudaFree(pf->work_counter); cudaFree(pf->filt_gen);
+    cudaFree(pf->rows_done); cudaFree(pf->gen_flags); cudaFree(pf->obs_haslik_dev);
     cudaFreeHost(pf->h_theta); cudaFreeHost(pf->h_ll); cudaFreeHost(pf->h_slots); cudaFreeHost(pf->h_cnt);
     for (cudaEvent_t e : pf->kev) cudaEventDestroy(e);
     if (pf->ev0) cudaEventDestroy(pf->ev0);
@@ -233,6 +234,11 @@ int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on) {
     pf->fused_mode = on >= 2 ? 2 : 1;
     return DPOMP_OK;
 }
+int dpomp_pf_set_persistent(dpomp_pf* pf, int32_t mode) {
+    if (!pf || mode < 0 || mode > 2) return fail(DPOMP_ERR_ARG, "persistent mode must be 0, 1 or 2");
+    pf->persist_mode = mode;
+    return DPOMP_OK;
+}
 int dpomp_pf_set_scatter(dpomp_pf* pf, int32_t mode) {
     if (!pf || (mode != DPOMP_SCATTER_REFERENCE && mode != DPOMP_SCATTER_INTERLEAVED)) return fail(DPOMP_ERR_ARG, "bad scatter mode");
     pf->scatter_mode = mode;
@@ -328,7 +334,64 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         // filter nothing waits and it wins slightly (1024 x 1024: 4.02 vs 4.10 ms).  fused_mode 2 forces it when it fits.
         fused_ok = cap >= pf->ntiles && (pf->ntiles == 1 || pf->fused_mode == 2);
     }
-    for (int oi = ymin; oi <= ymax; ++oi) {
+    // persistent path: ONE cooperative launch for all observations of the call (pf_sim.cuh, MODE 2) when every CTA of the
+    // launch is co-resident; otherwise the per-observation launch chain below
+    bool persist_ok = false;
+    if (pf->persist_mode != 0 && pf->rs_type != DPOMP_RS_MULTINOMIAL && pf->sim_precision == DPOMP_SIM_F32 && !pf->kernel_timing &&
+        make_chunk_perm(pf->scatter_mode, pf->n, pf->ntiles).ncf == 0 && (pf->persist_mode == 2 || ymax > ymin)) {
+        if (pf->persist_capacity < 0) pf->persist_capacity = sim_persist_capacity(mh, pf->sim_precision, pf->items);
+        persist_ok = (long long)nb * pf->ntiles <= pf->persist_capacity;
+    }
+    if (persist_ok) {
+        const size_t B = (size_t)pf->n_batch;
+        if (!pf->rows_done) {
+            std::vector<int> hl((size_t)pf->n_obs);
+            for (int t = 0; t < pf->n_obs; ++t) hl[(size_t)t] = mh.obs_id[(size_t)t] > 0;
+            CK(cudaMalloc((void**)&pf->rows_done, B * pf->ntiles * sizeof(unsigned int)));
+            CK(cudaMalloc((void**)&pf->gen_flags, B * pf->ngroups * 32 * sizeof(unsigned int)));
+            CK(cudaMalloc((void**)&pf->obs_haslik_dev, (size_t)pf->n_obs * sizeof(int)));
+            CK(cudaMemsetAsync(pf->gen_flags, 0, B * pf->ngroups * 32 * sizeof(unsigned int), st));
+            CK(cudaMemcpyAsync(pf->obs_haslik_dev, hl.data(), (size_t)pf->n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));  // hl is a stack vector
+        }
+        CK(cudaMemsetAsync(pf->rows_done, 0, (size_t)nb * pf->ntiles * sizeof(unsigned int), st));
+        SimLaunch a{};
+        a.pop = pf->pop[pf->cur]; a.pop_dst = pf->pop[pf->cur ^ 1];
+        a.logw = pf->logw; a.wtile = pf->wtile; a.record_logw = pf->record_anc ? 1 : 0;
+        a.theta = pf->theta_dev; a.obs_time = pf->obs_time_dev; a.obs_ysum = pf->obs_ysum_dev;
+        a.tile_m = pf->tile_m; a.tile_s = pf->tile_s; a.tile_f = pf->tile_f; a.tile_off = pf->tile_off;
+        a.filt_m = pf->filt_m; a.filt_s = pf->filt_s; a.ll_acc = pf->ll_acc;
+        a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
+        a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups; a.tile_counter = pf->tile_counter;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1;
+        a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
+        a.t = ymin - 1; a.t_last = ymax - 1; a.n_obs_total = pf->n_obs; a.obs_haslik = pf->obs_haslik_dev;
+        a.fresh = (ymin == 1); a.has_lik = 0; a.do_resample = 0;
+        a.rs_type = pf->rs_type; a.anc = pf->record_anc ? pf->anc : nullptr;
+        a.perm = make_chunk_perm(0, pf->n, pf->ntiles);
+        a.rows_done = pf->rows_done; a.gen_flags = pf->gen_flags; a.gen = pf->gen + 1;
+        a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
+        a.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
+        cudaError_t le = launch_sim_weight(mh, pf->sim_precision, pf->items, 3, a, st);
+        if (le == cudaSuccess) {
+            int flips = 0, last_rs = 0;
+            for (int oi = ymin; oi <= ymax; ++oi) {
+                last_rs = (mh.obs_id[(size_t)oi - 1] > 0) && oi < pf->n_obs;
+                flips += last_rs;
+            }
+            pf->gen += (unsigned int)(ymax - ymin + 1);
+            pf->cur ^= (flips & 1);
+            pf->last_resampled = last_rs != 0;
+            launches = 1;
+        } else if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+            (void)cudaGetLastError();  // not co-resident after all (another context holds SMs): per-observation chain
+            pf->persist_capacity = 0;
+            persist_ok = false;
+        } else {
+            return fail(DPOMP_ERR_CUDA, std::string("persistent launch: ") + cudaGetErrorString(le));
+        }
+    }
+    for (int oi = ymin; oi <= ymax && !persist_ok; ++oi) {
         const int t = oi - 1;
         const int has_lik = mh.obs_id[t] > 0;
         const int do_rs = has_lik && oi < pf->n_obs;  // src/hmm_particle_filter.jl:58,62

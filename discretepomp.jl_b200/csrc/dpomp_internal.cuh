@@ -74,6 +74,12 @@ struct SimLaunch {
     unsigned long long work_base;
     unsigned int* filt_gen;  // [B] set to `gen` by the CTA that finished the filter's combine
     unsigned int gen;
+    // persistent kernel (one cooperative launch for observations t .. t_last of the call): see pf_sim.cuh
+    int t_last;                  // last 0-based observation index of the call
+    int n_obs_total;             // T: resampling after observation t iff obs_haslik[t] and t + 1 < T
+    const int* obs_haslik;       // [T] obs_id[t] > 0
+    unsigned int* rows_done;     // [B][ntiles] offspring rows written into the tile by the resample phase (consumer resets)
+    unsigned int* gen_flags;     // [B][ngroups][32] generation of the last finished combine, one 128-byte line per group
     uint64_t key;
     uint32_t filter0;        // global id of local filter 0
     const uint32_t* filter_ids;  // optional explicit global ids [n_filters] (overrides filter0 + b)
@@ -151,6 +157,11 @@ struct dpomp_pf {
     unsigned int* filt_gen = nullptr;            // [n_batch] generation of the last finished combine
     unsigned int gen = 0;
     int scatter_mode = DPOMP_SCATTER_DEFAULT;    // offspring placement: 0 reference order, 1 chunk-interleaved over the tiles
+    int persist_mode = DPOMP_PERSIST_DEFAULT;   // one cooperative launch per call: 0 never, 1 for calls over several observations, 2 always
+    int persist_capacity = -1;                   // co-resident CTAs of the persistent kernel (lazy; 0 = unavailable)
+    unsigned int* rows_done = nullptr;           // [n_batch][ntiles]
+    unsigned int* gen_flags = nullptr;           // [n_batch][ngroups][32]
+    int* obs_haslik_dev = nullptr;               // [T]
     bool fused_enabled = true;
     int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
     int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
@@ -201,6 +212,9 @@ int comm_scratch(dpomp_comm* c, size_t slots, size_t send_bytes, size_t recv_byt
 
 // launchers implemented in the kernel TUs; all asynchronous on `stream`; return cudaGetLastError()
 cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, int fused, const SimLaunch& a, cudaStream_t stream);
+// fused: 0 plain, 1 fused step, 3 persistent (cooperative)
+// co-resident CTAs of the persistent kernel (0 = not instantiated for this model / precision / geometry)
+int sim_persist_capacity(const ModelHost& m, int sim_precision, int items);
 // co-resident CTAs of the fused step kernel for this model / geometry on the current device (0 = unavailable)
 int sim_fused_capacity(const ModelHost& m, int sim_precision, int items);
 int builtin_model_id(const dpomp_model_desc& d);  // 0 = generic rate table, > 0 = hand-specialised predefined model

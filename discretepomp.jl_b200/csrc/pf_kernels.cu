@@ -15,12 +15,17 @@ int sim_f32(const ModelHost& m, int items, const SimLaunch& a, cudaStream_t stre
 int sim_f64(const ModelHost& m, int items, const SimLaunch& a, cudaStream_t stream, int mode);
 
 cudaError_t launch_sim_weight(const ModelHost& m, int sim_precision, int items, int fused, const SimLaunch& a, cudaStream_t stream) {
-    const int mode = fused ? 1 : 0;
+    const int mode = fused;  // 0 plain, 1 fused step, 3 persistent
     return (cudaError_t)(sim_precision == DPOMP_SIM_F64 ? sim_f64(m, items, a, stream, mode) : sim_f32(m, items, a, stream, mode));
 }
 int sim_fused_capacity(const ModelHost& m, int sim_precision, int items) {
     SimLaunch dummy{};
     return sim_precision == DPOMP_SIM_F64 ? sim_f64(m, items, dummy, nullptr, 2) : sim_f32(m, items, dummy, nullptr, 2);
+}
+
+int sim_persist_capacity(const ModelHost& m, int sim_precision, int items) {
+    SimLaunch dummy{};
+    return sim_precision == DPOMP_SIM_F64 ? 0 : sim_f32(m, items, dummy, nullptr, 4);
 }
 
 // does the rate table equal one of the hand-specialised predefined models (pf_sim.cuh Builtin<>)?

@@ -113,13 +113,30 @@ __device__ __forceinline__ void chosen_transition(const DevModel<Real, C, E>& m,
 // the host only selects this variant when all tiles of a filter fit on the device at once, hence waiting for the
 // combine of the CTA's own filter cannot deadlock.  The tile's states and its scan stay in shared memory / registers
 // between the two phases: neither the states nor the scans of a resampling step go through HBM.
-template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, bool FUSED = false>
+//
+// PERSIST (MODE 2): ONE cooperative launch runs the observations a.t .. a.t_last.  CTA (filter, tile) keeps its tile for
+// the whole call; there is no kernel boundary and no grid-wide barrier besides the combine itself:
+//   wait until every row of my tile has been written by the resample phase of the previous observation
+//   (rows_done[filter][tile], a counter the producers add their row counts to) -> stage -> event loop -> weights ->
+//   ticket combine (the last tile publishes the filter's generation flag, replicated per group of tiles so that only
+//   kGroupTiles CTAs poll one address) -> wait for the flag -> resample my tile from shared memory, scatter the
+//   offspring rows, add my row counts to the counters of the destination tiles -> next observation.
+// A tile starts observation t+1 as soon as ITS rows are there (dataflow), not when the whole grid has finished t.
+// The host launches it cooperatively (all CTAs co-resident or the launch fails), so the waits cannot deadlock.
+constexpr int kModePlain = 0, kModeFused = 1, kModePersist = 2;
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, int MODE = kModePlain>
 __global__ void __launch_bounds__(kBlockThreads, sim_min_blocks<Real, C, E>())
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
     constexpr int CHUNK = 32 * ITEMS;  // particles owned by one warp
     constexpr bool kF32 = sizeof(Real) == 4;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool FUSED = MODE == kModeFused, PERSIST = MODE == kModePersist;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // staged compartment counts: f32 loop keeps them as floats (no conversions in the divergent refill path; exact
     // below 2^24), the f64 parity loop as int32
@@ -144,23 +161,50 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double* th = a.theta + (size_t)b * m.n_params;
-    const bool resample_here = FUSED && a.do_resample;
 
     Real par[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) par[e] = m.par[e] >= 0 ? (Real)th[m.par[e]] : (Real)1;
-    const double t_obs = a.obs_time[a.t];
-    const double t_prev = a.fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : a.obs_time[a.t - 1];
-    const double ysum = a.obs_ysum[a.t];
-    int32_t* pop_b = a.pop + (size_t)b * a.n_comp * a.n_pad;
     const uint32_t max_ev = (uint32_t)a.max_events;
+    // PERSIST: the loop over the observations of the call; the other modes run its body once (t_end == a.t)
+    const int t_end = PERSIST ? a.t_last : a.t;
+    int flip = 0;              // PERSIST: resampling steps done so far (ping-pong of the population buffers)
+    bool staged = false;       // PERSIST: the tile's states are still in shared memory from the previous observation
+    bool wait_rows = false;    // PERSIST: the previous observation resampled, my rows come from other CTAs
+    __shared__ int warp_max_s[kBlockThreads / 32];
+    __shared__ long long lohi_s[2];
+#pragma unroll 1
+    for (int t = a.t; t <= t_end; ++t) {
+    const bool fresh = a.fresh && t == a.t;
+    const int has_lik = PERSIST ? (a.obs_haslik[t] > 0) : a.has_lik;
+    const bool do_rs = PERSIST ? (has_lik && t + 1 < a.n_obs_total) : (a.do_resample != 0);
+    const bool resample_here = (FUSED || PERSIST) && do_rs;
+    const double t_obs = a.obs_time[t];
+    const double t_prev = fresh ? (m.t0_index > 0 ? th[m.t0_index - 1] : 0.0) : a.obs_time[t - 1];
+    const double ysum = a.obs_ysum[t];
+    int32_t* pop_b = ((PERSIST && (flip & 1)) ? a.pop_dst : a.pop) + (size_t)b * a.n_comp * a.n_pad;
+    int32_t* pop_other = ((PERSIST && (flip & 1)) ? a.pop : a.pop_dst);
+    const unsigned int gen_t = a.gen + (unsigned int)(t - a.t);
 
     DPOMP_STAMP(0, 0);
     if (tid == 0) {  // independent of the predecessor kernel: overlaps its tail
-        const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)a.t);
+        const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)t);
         stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;
     }
-    pdl_wait();  // everything below reads or writes buffers shared with the predecessor kernel
+    if constexpr (PERSIST) {
+        if (wait_rows) {  // every row of my tile must have been written by the resample phase of observation t - 1
+            if (tid == 0) {
+                const long long rem_rows = a.n - base_n;
+                const unsigned int want = (unsigned int)(rem_rows < TILE ? (rem_rows > 0 ? rem_rows : 0) : TILE);
+                unsigned int* cnt = a.rows_done + (size_t)b * a.ntiles + tile;
+                while (ld_acquire_u32(cnt) < want) __nanosleep(40);
+                *cnt = 0u;  // the next producers of this tile only run after my ticket of this observation
+            }
+        }
+        __syncthreads();  // also: the previous iteration is done with ovf_s (offspring windows) and st_s
+    } else {
+        pdl_wait();  // everything below reads or writes buffers shared with the predecessor kernel
+    }
     DPOMP_STAMP(0, 1);
     // stage the tile: each thread moves ITEMS consecutive particles per compartment with one vector access
     using Vec = IntVec<ITEMS>;
@@ -172,13 +216,29 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     }
     // compartments present: a compile-time constant for the predefined models
     const int n_comp = (MODEL != kModelGeneric) ? C : a.n_comp;
-    if (!a.fresh) {
+    if (PERSIST && staged) {
+        // no resampling at the previous observation: the tile's states are still in shared memory
+    } else if (!fresh) {
 #pragma unroll
         for (int c = 0; c < C; ++c)
             if (c < n_comp)
             {
                 DPOMP_CHECK_IDX(base_n + tid * ITEMS + ITEMS - 1, a.n_pad);
-                const Vec v = *reinterpret_cast<const Vec*>(pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS);
+                const int32_t* src = pop_b + (size_t)c * a.n_pad + base_n + tid * ITEMS;
+                Vec v;
+                if constexpr (PERSIST) {  // rows written by other SMs during this launch: bypass the (incoherent) L1
+#pragma unroll
+                    for (int kk = 0; kk < ITEMS; kk += (ITEMS % 4 == 0 ? 4 : 1)) {
+                        if constexpr (ITEMS % 4 == 0) {
+                            const int4 w4 = __ldcg(reinterpret_cast<const int4*>(src + kk));
+                            v.v[kk] = w4.x; v.v[kk + 1] = w4.y; v.v[kk + 2] = w4.z; v.v[kk + 3] = w4.w;
+                        } else {
+                            v.v[kk] = __ldcg(src + kk);
+                        }
+                    }
+                } else {
+                    v = *reinterpret_cast<const Vec*>(src);
+                }
 #pragma unroll
                 for (int kk = 0; kk < ITEMS; ++kk) st_s[c * TILE + tid * ITEMS + kk] = (SState)v.v[kk];
             }
@@ -493,7 +553,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         a.filt_s[b] = l2.big_s;
         a.filt_m[b] = l2.big_m;
         // log(cum_weight[end] / N) (:60) as log-sum-exp; one add per kernel and filter, so the RED is deterministic
-        if (a.has_lik) atomicAdd(&a.ll_acc[b], l2.big_m + log(l2.big_s / (double)a.n));
+        if (has_lik) atomicAdd(&a.ll_acc[b], l2.big_m + log(l2.big_s / (double)a.n));
         a.tile_counter[b] = 0u;
     }
     if constexpr (FUSED) {  // publish the combine to the CTAs of this filter that wait below
@@ -501,25 +561,61 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         __threadfence();
         if (tid == 0) atomicExch(&a.filt_gen[b], a.gen);
     }
+    if constexpr (PERSIST) {  // one flag per group of tiles (own 128-byte line): kGroupTiles pollers per address, not ntiles
+        __syncwarp();
+        __threadfence();
+        for (int g = tid; g < a.ngroups; g += 32)
+            *reinterpret_cast<volatile unsigned int*>(a.gen_flags + ((size_t)b * a.ngroups + g) * 32) = gen_t;
+    }
     }  // last_group
     }  // group-last warp
     DPOMP_STAMP(0, 6);
 
     if constexpr (FUSED) {
-        if (!a.do_resample) return;
+        if (!do_rs) return;
         // ---- wait for this filter's combine, then resample the tile from shared memory ---------------------------------
         if (tid == 0) {
             while (*reinterpret_cast<volatile unsigned int*>(a.filt_gen + b) != a.gen) __nanosleep(64);
             __threadfence();
         }
         __syncthreads();
-        __shared__ int warp_max_s[kBlockThreads / 32];
-        __shared__ long long lohi_s[2];
         const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
-                        a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
+                        a.ntiles, a.ngroups, a.n_comp, t, a.rs_type, a.key, a.perm};
         // ovf_s (TILE ints) is free after the weight pass: it becomes the per-warp offspring windows
         resample_tile<ITEMS, SState, true>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s, warp_max_s, lohi_s);
     }
+    if constexpr (PERSIST) {
+        // ---- wait for this filter's combine (also when this observation does not resample: the ticket counters are only
+        // reusable after it) ------------------------------------------------------------------------------------------------
+        if (tid == 0) {
+            const unsigned int* flag = a.gen_flags + ((size_t)b * a.ngroups + grp) * 32;
+            while (ld_acquire_u32(flag) != gen_t) __nanosleep(40);
+        }
+        __syncthreads();
+        if (do_rs) {
+            const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, pop_other, a.anc, a.n, a.n_pad,
+                            a.ntiles, a.ngroups, a.n_comp, t, a.rs_type, a.key, a.perm};
+            resample_tile<ITEMS, SState, true, 0, false>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s, warp_max_s, lohi_s);
+            // every offspring row of this tile is written: add the row counts to the counters of the destination tiles
+            __threadfence();
+            __syncthreads();
+            const long long lo = lohi_s[0], hi = lohi_s[1];
+            if (hi > lo) {
+                const int d0 = (int)(lo / TILE), d1 = (int)((hi - 1) / TILE);
+                for (int d = d0 + tid; d <= d1; d += kBlockThreads) {
+                    const long long from = max(lo, (long long)d * TILE), to = min(hi, (long long)(d + 1) * TILE);
+                    atomicAdd(a.rows_done + (size_t)b * a.ntiles + d, (unsigned int)(to - from));
+                }
+            }
+            ++flip;
+            wait_rows = true;
+            staged = false;
+        } else {
+            wait_rows = false;
+            staged = true;
+        }
+    }
+    }  // observations
 }
 
 // ---- host-side model padding and dispatch ---------------------------------------------------------------------
@@ -563,13 +659,14 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
     return m;
 }
 
-// mode 0: launch the plain kernel, 1: launch the fused kernel, 2: return the fused kernel's co-resident CTA capacity
+// mode 0: launch the plain kernel, 1: launch the fused kernel, 2: return the fused kernel's co-resident CTA capacity,
+// 3: launch the persistent kernel cooperatively (all observations of the call in one launch), 4: its co-resident capacity
 template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
 static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream, int mode) {
     constexpr int TILE = kBlockThreads * ITEMS;
     const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
-    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, false>;
-    auto kern_fused = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, true>;
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePlain>;
+    auto kern_fused = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModeFused>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -585,6 +682,39 @@ static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         return per_sm * sms;
     }
+    if constexpr (sizeof(Real) == 4 && ITEMS == kItemsLarge && MODEL != kModelGeneric) {
+        // the persistent kernel is instantiated for the f32 loop of the predefined models on 1024-particle tiles
+        auto kern_p = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePersist>;
+        static bool configured_p = false;
+        if (!configured_p) {
+            cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(kern_p, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            configured_p = true;
+        }
+        if (mode == 4) {
+            int per_sm = 0, dev = 0, sms = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_p, kBlockThreads, smem) != cudaSuccess) return 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return per_sm * sms;
+        }
+        if (mode == 3) {
+            const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(a.n_filters * a.ntiles));
+            cfg.blockDim = dim3(kBlockThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return (int)cudaLaunchKernelEx(&cfg, kern_p, m, a);
+        }
+    }
+    if (mode == 4) return 0;
+    if (mode == 3) return (int)cudaErrorInvalidValue;
     const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
     const unsigned grid = (unsigned)(a.n_filters * a.ntiles);
     return (int)(mode == 1 ? launch_pdl(kern_fused, grid, kBlockThreads, smem, stream, m, a)
@@ -613,7 +743,7 @@ static int sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStr
     }
     DPOMP_SIM_SHAPES(X)
 #undef X
-    return mode == 2 ? 0 : (int)cudaErrorInvalidValue;
+    return (mode == 2 || mode == 4) ? 0 : (int)cudaErrorInvalidValue;
 }
 
 }  // namespace dpomp

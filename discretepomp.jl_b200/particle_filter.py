@@ -119,6 +119,10 @@ class ParticleFilter:
         mode = 2 if mode is True else int(mode)
         _capi.check(_capi.lib().dpomp_pf_set_fused(self._h, mode))
 
+    def set_persistent(self, mode: int) -> None:
+        """One cooperative launch per call (all observations): 0 never, 1 for calls over several observations, 2 always."""
+        _capi.check(_capi.lib().dpomp_pf_set_persistent(self._h, int(mode)))
+
     def set_scatter(self, mode: int) -> None:
         """Row order of the offspring: 0 the reference's (offspring i in row i), 1 chunk-interleaved over the tiles."""
         _capi.check(_capi.lib().dpomp_pf_set_scatter(self._h, int(mode)))

@@ -124,6 +124,16 @@ int dpomp_pf_set_fused(dpomp_pf* pf, int32_t on);                     /* fused s
                                                                          Mode 2 spin-waits inside the kernel for the other tiles of the filter and
                                                                          therefore REQUIRES AN EXCLUSIVE DEVICE: with another handle, stream or
                                                                          process (MPS) holding SM slots the wait can hang; modes 0 and 1 never wait */
+/* Persistent launch: all observations of a call in ONE cooperative kernel launch; a tile starts the next observation as soon as
+ * its own rows have been written by the resample phase (no kernel boundaries, no grid-wide barrier besides the weight
+ * combine).  Used when every CTA of the call is co-resident (n_batch_used x tiles <= device capacity), the event loop is
+ * f32, the resampler systematic or stratified and the row order the reference's; otherwise the per-observation launch chain
+ * runs.  0 never, 1 for calls over more than one observation, 2 also for single-observation calls.  Results are bit-identical
+ * to the launch chain. */
+#ifndef DPOMP_PERSIST_DEFAULT
+#define DPOMP_PERSIST_DEFAULT 0
+#endif
+int dpomp_pf_set_persistent(dpomp_pf* pf, int32_t mode);
 /* Row order of the offspring after a resampling step.  The ancestors chosen for offspring i = 1..N are always those of the
  * reference's walk (src/hmm_pf_resample.jl:34-40); the mode only says where offspring i is stored:
  *   DPOMP_SCATTER_REFERENCE    row i, as `pop[i,:] = old_p[j,:]` (src/hmm_pf_resample.jl:38)

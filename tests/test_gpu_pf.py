@@ -434,3 +434,54 @@ def test_interleaved_scatter_estimate_has_the_same_law(dp):
         lls.append(pf.loglik(np.tile(theta[:, None], (1, 64))))
     z = (lls[0].mean() - lls[1].mean()) / np.sqrt(lls[0].var(ddof=1) / 64 + lls[1].var(ddof=1) / 64)
     assert abs(z) < 4.5, (lls[0].mean(), lls[1].mean(), z)
+
+
+@pytest.mark.parametrize("case,n,nb", [("sir_c2", 3000, 3), ("sir_c2", 1 << 17, 1), ("seir_c3", 70000, 2), ("lotka_c4", 2048, 4),
+                                       ("sis_pooley", 200, 5), ("sis_pooley", 1024, 1)])
+@pytest.mark.parametrize("rs_type", [1, 2])
+def test_persistent_kernel_equals_launch_chain(dp, case, n, nb, rs_type):
+    """One cooperative launch for all observations of a call (dataflow between tiles instead of kernel boundaries) is the
+    same computation as the per-observation launch chain: bit-identical log-likelihoods, populations, ancestors and event
+    counts; ragged tiles, several filters, several groups of tiles, partial calls that compose."""
+    model, y, hmm, theta = load_case(dp, case)
+    thetas = theta[:, None] * np.linspace(0.9, 1.1, nb)[None, :]
+    ymax = min(len(y), 12)
+    split = max(1, ymax // 2)
+    out = []
+    for mode in (2, 0):
+        pf = _pf(dp, hmm, n, nb, rs=rs_type, seed=4)
+        pf.set_persistent(mode)
+        pf.set_fused(0)
+        pf.set_stream_key(555)
+        ll1 = pf.partial(thetas, 1, split)
+        l1 = pf.last_timing()[1]
+        ev1 = pf.last_event_count()
+        pf.set_stream_key(556)
+        ll2 = pf.partial(thetas, split + 1, ymax) if split < ymax else np.zeros(nb)
+        out.append((ll1, ll2, [pf.get_pop(b + 1) for b in range(nb)], pf.last_ancestors(nb), ev1, pf.last_event_count(), l1, pf.overflow_count()))
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert all(np.array_equal(u, v) for u, v in zip(a[2], b[2]))
+    if ymax < len(y):  # the last observation of the call resampled: ancestors are defined
+        assert np.array_equal(a[3], b[3])
+    assert a[4] == b[4] and a[5] == b[5] and a[7] == b[7] == 0
+    assert a[6] == 1 and b[6] > 1  # one launch for the whole call
+
+
+def test_persistent_kernel_with_non_likelihood_observations(dp):
+    """obs_id <= 0 observations neither weight nor resample (src/hmm_particle_filter.jl:58): the persistent kernel keeps the
+    tile in shared memory across them; the call's last observation is the data set's last (no resampling after it)."""
+    model = dp.generate_model("SIR", [100, 1, 0])
+    ys = [(1.0, 1, 3), (2.0, 0, 0), (3.0, 1, 6), (4.0, 0, 0), (5.0, 0, 0), (6.0, 1, 12), (7.0, 1, 14)]
+    y = [dp.Observation(t, oid, 1.0, [0, v, 0]) for t, oid, v in ys]
+    hmm = dp.get_private_model(model, y)
+    res = []
+    for mode in (2, 0):
+        pf = _pf(dp, hmm, 5000, 2, seed=8)
+        pf.set_persistent(mode)
+        pf.set_stream_key(99)
+        ll = pf.loglik(np.array([[0.003, 0.0035], [0.1, 0.12]]))
+        res.append((ll, pf.get_pop(1), pf.get_pop(2), pf.last_logw(2)))
+    assert np.array_equal(res[0][0], res[1][0]) and np.all(np.isfinite(res[0][0]))
+    for k in (1, 2, 3):
+        assert np.array_equal(res[0][k], res[1][k])
