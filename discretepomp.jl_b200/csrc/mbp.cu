@@ -161,6 +161,20 @@ constexpr int kMbpWarpsPerCta = 4;
 // trajectories per launch up to which the warp-per-trajectory kernels are used (B200, SIS / pooley.csv, propose call,
 // warp vs thread per trajectory: 16 trajectories 1.04 vs 1.43 ms, 1024: 1.37 vs 1.96 ms, 4096: 2.53 vs 2.21 ms, 16384: 7.1 vs 2.9 ms)
 constexpr int kMbpWarpThreshold = 2048;
+// Growable trajectory store: the stores reserve `cap` (the current stride) events per trajectory, far fewer than the hard
+// limit cap_max (the reference's MAX_TRAJ = 196000, src/DiscretePOMP.jl:40).  A walk that reaches the stride before cap_max
+// does not commit its particle (no state, length or log-likelihood is written) and raises need_grow; the host doubles the
+// stride and re-launches the same kernel with the same key for the particles that have not committed (`done[p] != call_id`),
+// so the result is exactly that of a store with cap_max events per trajectory.  Reaching cap_max itself is the
+// reference's overflow: log-likelihood -Inf (src/hmm_sim.jl:17-20, src/hmm_mbp.jl:98-101).
+constexpr int kMbpInitialStride = 1024;
+struct MbpGrow {
+    int cap_max;
+    int call_id;
+    int* done;       // [n] id of the last call that committed the particle
+    int* need_grow;  // [1]
+};
+
 struct ThreadIO {
     const double* it; const unsigned char* iy; int ilen;   // old trajectory (unused by the simulator)
     double* ft; unsigned char* fy;                          // new trajectory
@@ -224,7 +238,7 @@ struct WarpShared {  // per warp
 template <class IO, class R>
 __device__ __forceinline__ void mbp_iterate_body(const MbpModel& m, MbpStore& st, IO& io, int p, bool writer, const double* theta,
                                                  const double* obs_time, const double* obs_ysum, int cap, int t, int fresh, int has_lik,
-                                                 uint64_t key, uint32_t id0, double* out_logg) {
+                                                 uint64_t key, uint32_t id0, double* out_logg, const MbpGrow& g) {
     const int nc = mbp_nc<R>(m), ne = mbp_ne<R>(m);
     const double* thp = theta + (size_t)p * m.n_params;
     double th[R::PMAX];
@@ -255,6 +269,10 @@ __device__ __forceinline__ void mbp_iterate_body(const MbpModel& m, MbpStore& st
     io.finish(len);
     const double out = overflow ? -INFINITY : mbp_obs_ll<R>(m, obs_ysum[t], x);
     if (!writer) return;
+    if (overflow && cap < g.cap_max) {  // the stride, not MAX_TRAJ: nothing is committed, the host grows the store and re-launches
+        *g.need_grow = 1;
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < R::CMAX; ++c)
         if (c < nc) st.fc[(size_t)p * nc + c] = x[c];
@@ -262,30 +280,32 @@ __device__ __forceinline__ void mbp_iterate_body(const MbpModel& m, MbpStore& st
     if (overflow) st.ll[2 * (size_t)p] = -INFINITY;
     else if (has_lik) st.ll[2 * (size_t)p] += out;
     out_logg[p] = out;
+    g.done[p] = g.call_id;
 }
 
 template <int MODEL>
 __global__ void __launch_bounds__(128) mbp_iterate_kernel(const __grid_constant__ MbpModel m, MbpStore st, const double* theta,
                                                            const double* obs_time, const double* obs_ysum, int n, int cap, int t,
-                                                           int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg) {
+                                                           int fresh, int has_lik, uint64_t key, uint32_t id0, double* out_logg,
+                                                           MbpGrow g) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= n || g.done[p] == g.call_id) return;
     ThreadIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap};
-    mbp_iterate_body<ThreadIO, MbpRates<MODEL>>(m, st, io, p, true, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg);
+    mbp_iterate_body<ThreadIO, MbpRates<MODEL>>(m, st, io, p, true, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key, id0, out_logg, g);
 }
 template <int MODEL>
 __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_iterate_warp_kernel(const __grid_constant__ MbpModel m, MbpStore st,
                                                            const double* theta, const double* obs_time, const double* obs_ysum, int n,
                                                            int cap, int t, int fresh, int has_lik, uint64_t key, uint32_t id0,
-                                                           double* out_logg) {
+                                                           double* out_logg, MbpGrow g) {
     __shared__ WarpShared sh[kMbpWarpsPerCta];
     const int warp = threadIdx.x >> 5, p = blockIdx.x * kMbpWarpsPerCta + warp;
-    if (p >= n) return;
+    if (p >= n || g.done[p] == g.call_id) return;
     WarpShared& w = sh[warp];
     const int len0 = st.len[p];
     WarpIO io{nullptr, nullptr, 0, st.ev_time + (size_t)p * cap, st.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, len0, cap};
     mbp_iterate_body<WarpIO, MbpRates<MODEL>>(m, st, io, p, (threadIdx.x & 31) == 0, theta, obs_time, obs_ysum, cap, t, fresh, has_lik, key,
-                                              id0, out_logg);
+                                              id0, out_logg, g);
 }
 
 // partial_model_based_proposal (src/hmm_mbp.jl:83-108): xi = current store (through io), xf = proposal store
@@ -293,7 +313,7 @@ template <class IO, class R>
 __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf, IO& io, int p, bool writer, bool is_valid,
                                                  const double* theta_i, const double* theta_f, const double* obs_time,
                                                  const double* obs_ysum, const int* obs_haslik, int cap, int ymax, uint64_t key,
-                                                 uint32_t id0, double* out_ll) {
+                                                 uint32_t id0, double* out_ll, const MbpGrow& g) {
     const int nc = mbp_nc<R>(m), ne = mbp_ne<R>(m);
     double ll0 = 0.0, ll1 = 0.0;
     int flen = 0;
@@ -391,6 +411,10 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
     }
     io.finish(flen);
     if (!writer) return;
+    if (flen >= cap && cap < g.cap_max && ll0 == -INFINITY && is_valid) {  // stopped at the stride, not at MAX_TRAJ: see MbpGrow
+        *g.need_grow = 1;
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < R::CMAX; ++c)
         if (c < nc) xf.fc[(size_t)p * nc + c] = xfc[c];
@@ -399,36 +423,38 @@ __device__ __forceinline__ void mbp_propose_body(const MbpModel& m, MbpStore& xf
     xf.ll[2 * (size_t)p + 1] = ll1;
     out_ll[2 * (size_t)p] = ll0;
     out_ll[2 * (size_t)p + 1] = ll1;
+    g.done[p] = g.call_id;
 }
 
 template <int MODEL>
 __global__ void __launch_bounds__(128) mbp_propose_kernel(const __grid_constant__ MbpModel m, MbpStore xi, MbpStore xf,
                                                            const double* theta_i, const double* theta_f, const unsigned char* valid,
                                                            const double* obs_time, const double* obs_ysum, const int* obs_haslik,
-                                                           int n, int cap, int ymax, uint64_t key, uint32_t id0, double* out_ll) {
+                                                           int n, int cap, int ymax, uint64_t key, uint32_t id0, double* out_ll,
+                                                           MbpGrow g) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= n || g.done[p] == g.call_id) return;
     ThreadIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
                 xf.ev_type + (size_t)p * cap};
     mbp_propose_body<ThreadIO, MbpRates<MODEL>>(m, xf, io, p, true, valid[p] != 0, theta_i, theta_f, obs_time, obs_ysum, obs_haslik, cap,
-                                                ymax, key, id0, out_ll);
+                                                ymax, key, id0, out_ll, g);
 }
 template <int MODEL>
 __global__ void __launch_bounds__(32 * kMbpWarpsPerCta) mbp_propose_warp_kernel(const __grid_constant__ MbpModel m, MbpStore xi,
                                                            MbpStore xf, const double* theta_i, const double* theta_f,
                                                            const unsigned char* valid, const double* obs_time, const double* obs_ysum,
                                                            const int* obs_haslik, int n, int cap, int ymax, uint64_t key, uint32_t id0,
-                                                           double* out_ll) {
+                                                           double* out_ll, MbpGrow g) {
     __shared__ WarpShared sh[kMbpWarpsPerCta];
     const int warp = threadIdx.x >> 5, p = blockIdx.x * kMbpWarpsPerCta + warp;
-    if (p >= n) return;
+    if (p >= n || g.done[p] == g.call_id) return;
     WarpShared& w = sh[warp];
     WarpIO io{xi.ev_time + (size_t)p * cap, xi.ev_type + (size_t)p * cap, xi.len[p], xf.ev_time + (size_t)p * cap,
               xf.ev_type + (size_t)p * cap, w.it, w.iy, w.ft, w.fy, 0, 0, cap};
     const bool is_valid = valid[p] != 0;
     if (is_valid) io.load(0);
     mbp_propose_body<WarpIO, MbpRates<MODEL>>(m, xf, io, p, (threadIdx.x & 31) == 0, is_valid, theta_i, theta_f, obs_time, obs_ysum,
-                                              obs_haslik, cap, ymax, key, id0, out_ll);
+                                              obs_haslik, cap, ymax, key, id0, out_ll, g);
 }
 
 // dst[dst_slot[k]] <- src[src_slot[k]] : one CTA per particle, only the live part of the trajectory moves
@@ -448,6 +474,17 @@ __global__ void __launch_bounds__(128) mbp_copy_kernel(MbpStore dst, MbpStore sr
     if (threadIdx.x < n_comp) dst.fc[(size_t)d * n_comp + threadIdx.x] = src.fc[(size_t)s * n_comp + threadIdx.x];
     if (threadIdx.x == 32) dst.len[d] = len;
     if (threadIdx.x == 64) { dst.ll[2 * d] = src.ll[2 * s]; dst.ll[2 * d + 1] = src.ll[2 * s + 1]; }
+}
+
+// growth of the stride: the live prefix of every trajectory moves to its place in the wider arrays
+__global__ void __launch_bounds__(128) mbp_restride_kernel(double* dt, unsigned char* dy, const double* st, const unsigned char* sy,
+                                                            const int* len, int old_cap, int new_cap) {
+    const size_t p = blockIdx.x;
+    const int l = min(max(len[p], 0), old_cap);
+    for (int i = threadIdx.x; i < l; i += blockDim.x) {
+        dt[p * new_cap + i] = st[p * old_cap + i];
+        dy[p * new_cap + i] = sy[p * old_cap + i];
+    }
 }
 
 // migration: pack / unpack whole particles.  fixed record = 16 int32 words: [0] length, [1..8] final state, [10..13] log_like[2]
@@ -500,7 +537,13 @@ using namespace dpomp;
 
 struct dpomp_mbp {
     const dpomp_model* model = nullptr;
-    int device = 0, n = 0, cap = 0;
+    int device = 0, n = 0;
+    int cap = 0;       // current stride of the stores (events reserved per trajectory); grows on demand up to cap_max
+    int cap_max = 0;   // MAX_TRAJ (src/DiscretePOMP.jl:40): the reference's hard limit, beyond which log-likelihood = -Inf
+    int call_id = 0;   // id of the current iterate / propose call (MbpGrow)
+    int* done = nullptr;       // [n]
+    int* need_grow = nullptr;  // [1] device
+    int* h_need_grow = nullptr;  // pinned
     cudaStream_t stream = nullptr;
     MbpModel dm{};
     MbpStore store[3]{};   // [cur], [cur ^ 1] (resample workspace), [2] proposal
@@ -540,9 +583,36 @@ static void mbp_free(dpomp_mbp* h) {
         cudaFree(h->store[s].fc); cudaFree(h->store[s].ll);
     }
     cudaFree(h->theta_i); cudaFree(h->theta_f); cudaFree(h->out); cudaFree(h->obs_time); cudaFree(h->obs_ysum);
-    cudaFree(h->obs_haslik); cudaFree(h->valid); cudaFree(h->slots);
+    cudaFree(h->obs_haslik); cudaFree(h->valid); cudaFree(h->slots); cudaFree(h->done); cudaFree(h->need_grow);
+    cudaFreeHost(h->h_need_grow);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+// widen the stride of all three stores to new_cap (<= cap_max); the live prefixes are copied on the store's stream
+static int mbp_grow(dpomp_mbp* h, int new_cap) {
+    if (new_cap > h->cap_max) new_cap = h->cap_max;
+    if (new_cap <= h->cap) return DPOMP_OK;
+    const size_t N = (size_t)h->n;
+    for (int s = 0; s < 3; ++s) {
+        double* nt = nullptr;
+        unsigned char* ny = nullptr;
+        if (cudaMalloc((void**)&nt, N * (size_t)new_cap * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&ny, N * (size_t)new_cap) != cudaSuccess) {
+            cudaFree(nt);
+            return dpomp_set_error(DPOMP_ERR_CUDA, std::string("growing the trajectory store: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        mbp_restride_kernel<<<(unsigned)h->n, 128, 0, h->stream>>>(nt, ny, h->store[s].ev_time, h->store[s].ev_type, h->store[s].len,
+                                                                   h->cap, new_cap);
+        MCK(cudaGetLastError());
+        MCK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->store[s].ev_time);
+        cudaFree(h->store[s].ev_type);
+        h->store[s].ev_time = nt;
+        h->store[s].ev_type = ny;
+    }
+    h->cap = new_cap;
+    return DPOMP_OK;
 }
 
 extern "C" {
@@ -561,7 +631,9 @@ int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_
     dpomp_mbp* h = new (std::nothrow) dpomp_mbp();
     if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "out of host memory");
     const dpomp_model_desc& d = model->h.desc;
-    h->model = model; h->device = device; h->n = n_particles; h->cap = max_traj; h->seed = seed;
+    h->model = model; h->device = device; h->n = n_particles; h->seed = seed;
+    h->cap_max = max_traj;
+    h->cap = max_traj < kMbpInitialStride ? max_traj : kMbpInitialStride;
     MbpModel& m = h->dm;
     m.n_comp = d.n_compartments; m.n_events = d.n_events; m.n_params = d.n_params; m.t0_index = d.t0_index;
     h->model_id = builtin_model_id(d);
@@ -576,7 +648,7 @@ int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_
     for (int c = 0; c < DPOMP_MAX_COMPARTMENTS; ++c) { m.xmask[c] = d.obs_xmask[c]; m.ic[c] = (int)d.initial_condition[c]; }
     m.obs_tmp1 = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * d.obs_sigma));
     m.obs_tmp2 = 2.0 * d.obs_sigma * d.obs_sigma;
-    const size_t N = (size_t)n_particles, CAP = (size_t)max_traj;
+    const size_t N = (size_t)n_particles, CAP = (size_t)h->cap;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; s < 3 && ok; ++s) {
         ok = cudaMalloc((void**)&h->store[s].ev_time, N * CAP * sizeof(double)) == cudaSuccess &&
@@ -594,6 +666,9 @@ int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_
          cudaMalloc((void**)&h->obs_ysum, d.n_obs * sizeof(double)) == cudaSuccess &&
          cudaMalloc((void**)&h->obs_haslik, d.n_obs * sizeof(int)) == cudaSuccess &&
          cudaMalloc((void**)&h->valid, N) == cudaSuccess && cudaMalloc((void**)&h->slots, 2 * N * sizeof(int64_t)) == cudaSuccess &&
+         cudaMalloc((void**)&h->done, N * sizeof(int)) == cudaSuccess && cudaMalloc((void**)&h->need_grow, sizeof(int)) == cudaSuccess &&
+         cudaMallocHost((void**)&h->h_need_grow, sizeof(int)) == cudaSuccess &&
+         cudaMemset(h->done, 0, N * sizeof(int)) == cudaSuccess &&
          cudaMemcpy(h->obs_time, model->h.obs_time.data(), d.n_obs * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->obs_ysum, model->h.obs_ysum.data(), d.n_obs * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->obs_haslik, haslik.data(), d.n_obs * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -644,22 +719,30 @@ int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_
     MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     const bool warps = mbp_use_warps(h, n);
     const int has_lik = h->model->h.obs_id[obs_i - 1] > 0;
+    const MbpGrow g{h->cap_max, ++h->call_id, h->done, h->need_grow};
 #define DPOMP_MBP_ITERATE(ID)                                                                                                  \
     if (h->model_id == ID) {                                                                                                   \
         if (warps)                                                                                                             \
             mbp_iterate_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
                 h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0, has_lik,   \
-                key, (uint32_t)h->batch_offset, h->out);                                                                       \
+                key, (uint32_t)h->batch_offset, h->out, g);                                                                    \
         else                                                                                                                   \
             mbp_iterate_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time,   \
                                                                            h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0,   \
-                                                                           has_lik, key, (uint32_t)h->batch_offset, h->out);   \
+                                                                           has_lik, key, (uint32_t)h->batch_offset, h->out, g); \
     }
-    DPOMP_MBP_MODELS(DPOMP_MBP_ITERATE)
+    for (;;) {  // re-launched (same key, uncommitted particles only) after the stride has grown: see MbpGrow
+        MCK(cudaMemsetAsync(h->need_grow, 0, sizeof(int), h->stream));
+        DPOMP_MBP_MODELS(DPOMP_MBP_ITERATE)
+        MCK(cudaGetLastError());
+        MCK(cudaMemcpyAsync(h->h_need_grow, h->need_grow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCK(cudaStreamSynchronize(h->stream));
+        if (!*h->h_need_grow) break;
+        const int rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
+        if (rc) return rc;
+    }
 #undef DPOMP_MBP_ITERATE
-    MCK(cudaGetLastError());
-    MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    MCK(cudaStreamSynchronize(h->stream));
     return DPOMP_OK;
 }
 
@@ -675,23 +758,31 @@ int dpomp_mbp_propose(dpomp_mbp* h, const double* theta_i, const double* theta_f
     MCK(cudaMemcpyAsync(h->theta_f, theta_f, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->valid, valid, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     const bool warps = mbp_use_warps(h, n);
+    const MbpGrow g{h->cap_max, ++h->call_id, h->done, h->need_grow};
 #define DPOMP_MBP_PROPOSE(ID)                                                                                                  \
     if (h->model_id == ID) {                                                                                                   \
         if (warps)                                                                                                             \
             mbp_propose_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
                 h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid, h->obs_time, h->obs_ysum,              \
-                h->obs_haslik, n, h->cap, ymax, key, (uint32_t)h->batch_offset, h->out);                                       \
+                h->obs_haslik, n, h->cap, ymax, key, (uint32_t)h->batch_offset, h->out, g);                                    \
         else                                                                                                                   \
             mbp_propose_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i,   \
                                                                            h->theta_f, h->valid, h->obs_time, h->obs_ysum,     \
                                                                            h->obs_haslik, n, h->cap, ymax, key,                \
-                                                                           (uint32_t)h->batch_offset, h->out);                 \
+                                                                           (uint32_t)h->batch_offset, h->out, g);              \
     }
-    DPOMP_MBP_MODELS(DPOMP_MBP_PROPOSE)
+    for (;;) {
+        MCK(cudaMemsetAsync(h->need_grow, 0, sizeof(int), h->stream));
+        DPOMP_MBP_MODELS(DPOMP_MBP_PROPOSE)
+        MCK(cudaGetLastError());
+        MCK(cudaMemcpyAsync(h->h_need_grow, h->need_grow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCK(cudaStreamSynchronize(h->stream));
+        if (!*h->h_need_grow) break;
+        const int rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
+        if (rc) return rc;
+    }
 #undef DPOMP_MBP_PROPOSE
-    MCK(cudaGetLastError());
-    MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    MCK(cudaStreamSynchronize(h->stream));
     return DPOMP_OK;
 }
 
@@ -801,10 +892,16 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     MCK(cudaStreamSynchronize(st));
     // phase 2: payload.  packed layout per direction: [fixed: n x 64 B][times: events x 8 B][types: events x 1 B]
     std::vector<int64_t> off_s(n_send + 1, 0), off_r(n_recv + 1, 0);
+    int max_recv = 0;
     for (size_t k = 0; k < n_send; ++k) off_s[k + 1] = off_s[k] + sc.h_int[k];
     for (size_t k = 0; k < n_recv; ++k) {
-        if (sc.h_int[n_send + k] < 0 || sc.h_int[n_send + k] > h->cap) return dpomp_set_error(DPOMP_ERR_COMM, "received trajectory length out of range");
+        if (sc.h_int[n_send + k] < 0 || sc.h_int[n_send + k] > h->cap_max) return dpomp_set_error(DPOMP_ERR_COMM, "received trajectory length out of range");
         off_r[k + 1] = off_r[k] + sc.h_int[n_send + k];
+        max_recv = sc.h_int[n_send + k] > max_recv ? sc.h_int[n_send + k] : max_recv;
+    }
+    while (max_recv > h->cap) {  // a trajectory grown on another rank: widen the local stride before it arrives
+        rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
+        if (rc) return rc;
     }
     const size_t ev_s = (size_t)off_s[n_send], ev_r = (size_t)off_r[n_recv];
     const size_t fixed_b = (size_t)kMbpFixedWords * sizeof(int);
@@ -852,6 +949,18 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     }
     MCK(cudaStreamSynchronize(st));
     return DPOMP_OK;
+}
+
+int dpomp_mbp_capacity(dpomp_mbp* h, int32_t* out_stride, int32_t* out_max_traj) {
+    if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "null handle");
+    if (out_stride) *out_stride = h->cap;
+    if (out_max_traj) *out_max_traj = h->cap_max;
+    return DPOMP_OK;
+}
+int dpomp_mbp_reserve(dpomp_mbp* h, int32_t stride) {
+    if (!h || stride < 1) return dpomp_set_error(DPOMP_ERR_ARG, "bad argument");
+    MCK(cudaSetDevice(h->device));
+    return mbp_grow(h, stride);
 }
 
 int dpomp_mbp_get_states(dpomp_mbp* h, int32_t n, int64_t* out) {

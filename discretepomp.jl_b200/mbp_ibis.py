@@ -11,7 +11,8 @@ Priors, MvNormal proposals, accept/reject and the evidence bookkeeping stay host
 Stated departures: (1) a mutation sweep proposes for all particles at once, so the random-walk scale `tj`
 (ind_prop = false, the MBP-IBIS default) is frozen within a sweep and updated afterwards with the same factors
 (SURVEY.md 7); (2) `outer_rs` may be rs_stratified (BASELINE config C5) where the reference hard-codes rs_systematic
-(:194); (3) the trajectory capacity `max_traj` defaults to 8192 events instead of MAX_TRAJ = 196000.
+(:194).  `max_traj` is the reference's MAX_TRAJ = 196000 (src/DiscretePOMP.jl:40): the device store reserves a small stride
+per trajectory and grows on demand, so the limit costs no memory (include/dpomp.h).
 """
 from __future__ import annotations
 
@@ -30,10 +31,13 @@ from .resample import rs_systematic
 from .structs import HiddenMarkovModel, ImportanceSample
 
 
+MAX_TRAJ = 196000  # src/DiscretePOMP.jl:40
+
+
 class MbpParticles:
     """dpomp_mbp handle: the trajectories of this process's theta-particles."""
 
-    def __init__(self, dmodel, n_particles: int, max_traj: int = 8192, seed: int = 1, device: int = -1):
+    def __init__(self, dmodel, n_particles: int, max_traj: int = MAX_TRAJ, seed: int = 1, device: int = -1):
         self.dmodel, self.n, self.cap = dmodel, int(n_particles), int(max_traj)
         self.n_params = int(dmodel.compiled.desc.n_params)
         self.n_comp = int(dmodel.compiled.desc.n_compartments)
@@ -61,6 +65,15 @@ class MbpParticles:
 
     def reset(self) -> None:
         _capi.check(_capi.lib().dpomp_mbp_reset(self._h))
+
+    def capacity(self):
+        """(current stride of the device store, hard limit max_traj) in events per trajectory."""
+        a, b = C.c_int32(), C.c_int32()
+        _capi.check(_capi.lib().dpomp_mbp_capacity(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def reserve(self, stride: int) -> None:
+        _capi.check(_capi.lib().dpomp_mbp_reserve(self._h, int(stride)))
 
     def _cols(self, theta) -> np.ndarray:
         return np.ascontiguousarray(np.asarray(theta, dtype=np.float64).T)  # (n, n_theta) == Julia column-major
@@ -122,6 +135,7 @@ class MbpParticles:
     def import_particles(self, slots, lens, fixed, times, types) -> None:
         s = _capi.as_i64(slots)
         if len(s):
+            self.reserve(int(np.max(lens)) if len(lens) else 1)  # trajectories that grew on another rank
             o = _capi.as_i64(np.concatenate(([0], np.cumsum(lens, dtype=np.int64)))[:-1])
             _capi.check(_capi.lib().dpomp_mbp_import(self._h, _capi.ptr(s), _capi.ptr(o), len(s), C.c_void_p(fixed.data_ptr()),
                                                      C.c_void_p(times.data_ptr()), C.c_void_p(types.data_ptr())))
@@ -135,15 +149,16 @@ class MbpParticles:
     def get_particle(self, p: int, proposal: bool = False):
         """(final_condition, times, types(1-based), log_like[2]) of particle p (1-based)."""
         fc = np.zeros(self.n_comp, dtype=np.int64); ln = C.c_int64()
-        times = np.zeros(self.cap); types = np.zeros(self.cap, dtype=np.int32); ll = np.zeros(2)
+        cap = self.capacity()[0]
+        times = np.zeros(cap); types = np.zeros(cap, dtype=np.int32); ll = np.zeros(2)
         _capi.check(_capi.lib().dpomp_mbp_get_particle(self._h, int(p), 1 if proposal else 0, _capi.ptr(fc), C.byref(ln),
-                                                       _capi.ptr(times), _capi.ptr(types), self.cap, _capi.ptr(ll)))
+                                                       _capi.ptr(times), _capi.ptr(types), cap, _capi.ptr(ll)))
         return fc, times[: ln.value].copy(), types[: ln.value].copy(), ll
 
 
 def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, n_props: int, ind_prop: bool,
                  alpha: float, msgs: bool = True, rng: Optional[np.random.Generator] = None, seed: int = 1,
-                 comm: Optional[Comm] = None, max_traj: int = 8192, outer_rs: Callable = rs_systematic,
+                 comm: Optional[Comm] = None, max_traj: int = MAX_TRAJ, outer_rs: Callable = rs_systematic,
                  particles_factory: Optional[Callable] = None, verbose: bool = True) -> ImportanceSample:
     """run_mbp_ibis(model, theta, ess_rs_crit, n_props, ind_prop, alpha, msgs = true) (src/hmm_ibis.jl:140-244).
     `theta` is (n_theta, outer_p).  With `comm`, theta-particles (and their trajectories) are partitioned over the ranks;

@@ -53,7 +53,7 @@ def generate_x0(model: HiddenMarkovModel, ptcls: MbpParticles, theta: np.ndarray
 
 
 def run_mbp_mcmc(model: HiddenMarkovModel, theta_init: np.ndarray, steps: int, adapt_period: int, fin_adapt: bool = False,
-                 seed: int = 1, comm: Optional[Comm] = None, max_traj: int = 8192,
+                 seed: int = 1, comm: Optional[Comm] = None, max_traj: int = 196000,
                  particles_factory: Optional[Callable] = None, verbose: bool = True) -> MCMCSample:
     """run_mbp_mcmc(model, theta_init, steps, adapt_period, fin_adapt) (src/hmm_mcmc.jl:330-345); theta_init is
     (n_theta, n_chains).  Returns MCMCSample with samples.theta of shape (n_theta, steps, n_chains)."""

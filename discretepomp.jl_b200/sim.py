@@ -52,8 +52,7 @@ def gillespie_sim(model: DPOMPModel, parameters, tmax: float = 100.0, num_obs: i
     mdl = get_private_model(model, y)
     if verbose:
         print(f"Running: {model.model_name} DGA for θ := {theta.tolist()}" + (f" x {n_sims}" if n_sims > 1 else ""), end="")
-    cap = max_traj if n_sims * max_traj <= (1 << 28) else max(4096, (1 << 28) // n_sims)  # bound the event store
-    ptcls = MbpParticles(device_model(mdl), n_sims, cap, seed)
+    ptcls = MbpParticles(device_model(mdl), n_sims, max_traj, seed)  # the store grows on demand up to max_traj
     th = np.tile(theta[:, None], (1, n_sims))
     c = len(model.initial_condition)
     states = np.zeros((n_sims, num_obs, c), dtype=np.int64)

@@ -208,6 +208,10 @@ int dpomp_pf_loglik_device(dpomp_pf* pf, const double* theta_dev, int32_t n_batc
  * list (struct Particle src/hmm_structs.jl:51-58) resident in HBM; max_traj plays MAX_TRAJ (src/DiscretePOMP.jl:40).
  */
 typedef struct dpomp_mbp dpomp_mbp;
+/* max_traj is the HARD limit of events per trajectory (MAX_TRAJ = 196000 in the reference): reaching it gives log-likelihood
+ * -Inf exactly like src/hmm_sim.jl:17-20 / src/hmm_mbp.jl:98-101.  The stores reserve far less (a stride of 1024 events per
+ * trajectory at creation) and grow on demand: a walk that reaches the stride is not committed, the stride doubles and the
+ * call is repeated for the uncommitted particles with the same random streams, so results never depend on the stride. */
 int dpomp_mbp_create(const dpomp_model* model, int32_t n_particles, int32_t max_traj, uint64_t seed, int32_t device,
                      dpomp_mbp** out_mbp);
 int dpomp_mbp_destroy(dpomp_mbp* mbp);
@@ -237,6 +241,10 @@ int dpomp_mbp_export(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offset
                      void* dev_times, void* dev_types);
 int dpomp_mbp_import(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
                      const void* dev_times, const void* dev_types);
+/* current stride of the stores and the hard limit; dpomp_mbp_reserve widens the stride ahead of time (e.g. before importing
+ * trajectories that grew elsewhere) */
+int dpomp_mbp_capacity(dpomp_mbp* mbp, int32_t* out_stride, int32_t* out_max_traj);
+int dpomp_mbp_reserve(dpomp_mbp* mbp, int32_t stride);
 /* final states of particles 1..n, row-major n x C */
 int dpomp_mbp_get_states(dpomp_mbp* mbp, int32_t n, int64_t* out);
 /* read back one particle (which: 0 current, 1 proposal): final state, event list (types 1-based), log_like[2] */

@@ -308,3 +308,39 @@ def test_warp_and_thread_per_trajectory_kernels_are_identical(dp, case, t0):
                 assert max(len(c[1]) for c in a[2]) > 256  # event lists longer than one shared-memory window
         elif case == "sis_pooley":
             assert np.isneginf(a[0]).any()  # the tiny capacity overflows
+
+
+@pytest.mark.parametrize("mode", [1, 2])  # one thread / one warp per trajectory
+def test_store_grows_on_demand_and_results_do_not_depend_on_the_stride(dp, mode):
+    """max_traj = MAX_TRAJ = 196000 (src/DiscretePOMP.jl:40) is the hard limit; the device store starts with a stride of 1024
+    events per trajectory and doubles when a walk reaches it (the walk is not committed and re-runs with the same random
+    streams).  LOTKA trajectories (~190 events per observation) cross 1024, 2048 and 4096 within 30 observations: every
+    trajectory, final state and log-likelihood equals the one of a store that reserved 16384 events from the start."""
+    model, y, hmm, theta = load_case(dp, "lotka_c4")
+    dm = dp.device_model(hmm)
+    n = 48
+    th = np.tile(theta[:, None], (1, n)) * np.linspace(0.9, 1.1, n)[None, :]
+    th_f = th * 1.03
+    res = []
+    for reserve in (None, 16384):
+        pt = dp.MbpParticles(dm, n, seed=5)
+        pt.set_mode(mode)
+        assert pt.capacity() == (1024, 196000)
+        if reserve:
+            pt.reserve(reserve)
+            assert pt.capacity()[0] == reserve
+        lg = []
+        for i in range(1, len(y) + 1):
+            pt.set_stream_key(1000 + i)
+            lg.append(pt.iterate(th, i, fresh=(i == 1)))
+        pt.set_stream_key(77)
+        ll = pt.propose(th, th_f, np.ones(n, dtype=np.uint8), len(y))
+        cur = [pt.get_particle(p + 1) for p in (0, 7, n - 1)]
+        prop = [pt.get_particle(p + 1, proposal=True) for p in (0, 7, n - 1)]
+        res.append((np.array(lg), ll, cur, prop, pt.capacity()[0]))
+    a, b = res
+    assert a[4] >= 4096 and b[4] == 16384 and max(len(c[1]) for c in a[2]) > 4096  # the store did grow past several strides
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.all(np.isfinite(a[0]))
+    for u, v in zip(a[2] + a[3], b[2] + b[3]):
+        for x, z in zip(u, v):
+            assert np.array_equal(x, z)
