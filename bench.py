@@ -93,7 +93,11 @@ def ncu_traffic():
     `ncu --set full` capture of this command (profiles/r1_ncu_full_metrics.csv); None when the file is missing."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_metrics.csv")
+    import glob
+
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_metrics.csv")))
+    path = cands[-1] if cands else os.path.join(ROOT, "profiles", "r1_ncu_full_metrics.csv")
+    ncu_traffic.source = os.path.relpath(path, ROOT)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         rows = {r[0]: r for r in csv.reader(open(path)) if r}
@@ -512,7 +516,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic.get(dom), "peak_source": peak_src,
-                         "traffic_source": "profiles/r1_ncu_full_metrics.csv (ncu --set full of this command; bytes per launch; the 33 MB working set is L2 resident)",
+                         "traffic_source": f"{getattr(ncu_traffic, 'source', 'profiles/')} (ncu --set full of this command; bytes per launch; the 33 MB working set is L2 resident)",
                          "note": "the simulate kernel is instruction-issue / latency bound, not HBM bound (DESIGN.md 4.1); frac is its HBM-roofline fraction, roofline_kernels[*].frac_of_issue_peak the issue-rate view (ncu warp instructions / measured launch time)"},
             "roofline_kernels": kernels,
             "roofline_kernels_note": "avg_launch_us / share_of_kernel_time come from a separate pass with CUDA events around EVERY launch, "

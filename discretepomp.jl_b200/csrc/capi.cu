@@ -98,7 +98,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaSetDevice(pf->device);
     cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->wtile); cudaFree(pf->cw); cudaFree(pf->anc);
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
-    cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter);
+    cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter); cudaFree(pf->tile_ev); cudaFree(pf->grp_ev);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev); cudaFree(pf->work_counter); cudaFree(pf->filt_gen);
     cudaFree(pf->rows_done); cudaFree(pf->gen_flags); cudaFree(pf->obs_haslik_dev);
@@ -169,6 +169,8 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->grp_f, B * NG * sizeof(double));
     ALLOC(pf->grp_off, B * NG * sizeof(double));
     ALLOC(pf->grp_counter, B * NG * sizeof(unsigned int));
+    ALLOC(pf->tile_ev, B * NT * sizeof(unsigned long long));
+    ALLOC(pf->grp_ev, B * NG * sizeof(unsigned long long));
     ALLOC(pf->filt_m, B * sizeof(double));
     ALLOC(pf->filt_s, B * sizeof(double));
     ALLOC(pf->ll_acc, B * sizeof(double));
@@ -363,7 +365,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         a.filt_m = pf->filt_m; a.filt_s = pf->filt_s; a.ll_acc = pf->ll_acc;
         a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
         a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups; a.tile_counter = pf->tile_counter;
-        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.tile_ev = pf->tile_ev; a.grp_ev = pf->grp_ev;
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = ymin - 1; a.t_last = ymax - 1; a.n_obs_total = pf->n_obs; a.obs_haslik = pf->obs_haslik_dev;
         a.fresh = (ymin == 1); a.has_lik = 0; a.do_resample = 0;
@@ -408,7 +410,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
         a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups;
         a.tile_counter = pf->tile_counter;
-        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.tile_ev = pf->tile_ev; a.grp_ev = pf->grp_ev;
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
         a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;

@@ -54,6 +54,8 @@ struct SimLaunch {
     double* filt_s;          // [B]
     double* ll_acc;          // [B]
     unsigned int* tile_counter;      // [B]
+    unsigned long long* tile_ev;     // [B][ntiles] Gillespie events simulated by the tile (summed along the combine tree)
+    unsigned long long* grp_ev;      // [B][ngroups]
     unsigned long long* ev_count;    // [1]
     unsigned long long* ovf_count;   // [1]
     long long n;             // particles per filter
@@ -147,6 +149,7 @@ struct dpomp_pf {
     double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
     double *grp_m = nullptr, *grp_s = nullptr, *grp_f = nullptr, *grp_off = nullptr;
     unsigned int* grp_counter = nullptr;
+    unsigned long long *tile_ev = nullptr, *grp_ev = nullptr;
     int ngroups = 0;
     unsigned int* tile_counter = nullptr;
     unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count

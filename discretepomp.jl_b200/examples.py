@@ -49,7 +49,10 @@ class UniformProduct:
     def logpdf_batch(self, theta: np.ndarray) -> np.ndarray:
         """logpdf of every column of an (n_theta, n) matrix (vectorised; same values as logpdf)."""
         theta = np.asarray(theta, dtype=np.float64)
-        inside = np.all((theta >= self.lower[:, None]) & (theta <= self.upper[:, None]), axis=0)
+        inside = np.ones(theta.shape[1], dtype=bool)
+        for k in range(theta.shape[0]):  # one pass per parameter: fast for either memory layout of the (n_theta, n) matrix
+            row = theta[k]
+            inside &= (row >= self.lower[k]) & (row <= self.upper[k])
         return np.where(inside, float(-np.sum(np.log(self.upper - self.lower))), -np.inf)
 
     def rand(self, n: int = 1, rng: Optional[np.random.Generator] = None) -> np.ndarray:

@@ -13,7 +13,7 @@ python bench.py --impl reference > gpurun_out/bench_ref_${TAG}.json 2> gpurun_ou
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err || exit 1
 # profiler passes only after the plain command exited 0; numbers printed under ncu are never bench values
 ncu --metrics gpu__time_duration.sum --clock-control none -c 440 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-smc2 > gpurun_out/ncu1_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-smc2 --no-outer > gpurun_out/ncu1_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pf_ -s 210 -c 4 -f -o gpurun_out/prof_${TAG} \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-smc2 > gpurun_out/ncu2_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-smc2 --no-outer > gpurun_out/ncu2_${TAG}.log 2>&1
 tail -3 gpurun_out/pytest_gpu_${TAG}.log 2>/dev/null; cat gpurun_out/smoke_${TAG}.log | tail -2; cat gpurun_out/bench_${TAG}.json | cut -c1-600
