@@ -129,7 +129,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, int MODE = kModePlain>
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, int MODE = kModePlain, int ILP = DPOMP_SIM_ILP>
 __global__ void __launch_bounds__(kBlockThreads, sim_min_blocks<Real, C, E>())
 pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __grid_constant__ SimLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -174,8 +174,9 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     bool wait_rows = false;    // PERSIST: the previous observation resampled, my rows come from other CTAs
     __shared__ int warp_max_s[kBlockThreads / 32];
     __shared__ long long lohi_s[2];
+    int t = a.t;
 #pragma unroll 1
-    for (int t = a.t; t <= t_end; ++t) {
+    do {  // (a do-while with a compile-time false condition outside PERSIST: the other modes carry no loop at all)
     const bool fresh = a.fresh && t == a.t;
     const int has_lik = PERSIST ? (a.obs_haslik[t] > 0) : a.has_lik;
     const bool do_rs = PERSIST ? (has_lik && t + 1 < a.n_obs_total) : (a.do_resample != 0);
@@ -256,8 +257,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const SimStream ss{stream_s[0], stream_s[1], stream_s[2]};
 
     // ---- event loop: each warp drains its chunk of CHUNK particles through a ballot-based work queue ----------
-    // A lane can work on S particles at once (DPOMP_SIM_ILP, default 1): independent instruction streams per lane.
-    constexpr int S = (kF32 && C <= 4 && E <= 3) ? DPOMP_SIM_ILP : 1;  // the wide generic shapes would spill
+    // A lane can work on S particles at once (template parameter ILP): independent instruction streams per lane.  Measured on
+    // B200: in the throughput regime S = 2 loses (C2 3.76 vs 3.66 ms; 4000 x 200 SIS 3.60 vs 3.17 ms: the loop is pipe bound),
+    // in the latency regime of a few small filters it wins (1 and 64 x 200 SIS: 0.350 / 0.370 vs 0.427 / 0.451 ms), so the
+    // 256-particle-tile kernels of the predefined models are instantiated for both and the host picks by the size of the grid.
+    constexpr int S = (kF32 && C <= 4 && E <= 3) ? ILP : 1;  // the wide generic shapes would spill
     const int chunk0 = warp * CHUNK;
     const long long left = a.n - (base_n + chunk0);
     const int chunk_valid = left < CHUNK ? (left > 0 ? (int)left : 0) : CHUNK;
@@ -421,7 +425,12 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         }
         // the event count rides on the combine tree (one RED per filter and launch instead of one per warp: 4096 REDs on
         // ONE address per C2 launch cost 0.9 us per observation); hitting the event cap is rare and keeps its own RED
+#ifdef DPOMP_EVCOUNT_RED  // A/B only: the round-1 form, one RED per warp
+        if (lane == 0) warp_ev_s[warp] = 0ull;
+        if (lane == 1 && ev_local) atomicAdd(a.ev_count, ev_local);
+#else
         if (lane == 0) warp_ev_s[warp] = ev_local;  // read by thread 0 after the barriers of the weight pass below
+#endif
         if (lane == 1 && ovf_local) atomicAdd(a.ovf_count, ovf_local);
 
         if (int_obs) {
@@ -627,7 +636,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             staged = true;
         }
     }
-    }  // observations
+    } while (PERSIST && ++t <= t_end);  // observations
 }
 
 // ---- host-side model padding and dispatch ---------------------------------------------------------------------
@@ -673,12 +682,12 @@ static DevModel<Real, C, E> make_dev_model(const ModelHost& mh) {
 
 // mode 0: launch the plain kernel, 1: launch the fused kernel, 2: return the fused kernel's co-resident CTA capacity,
 // 3: launch the persistent kernel cooperatively (all observations of the call in one launch), 4: its co-resident capacity
-template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric>
+template <typename Real, int C, int E, int ITEMS, int MODEL = kModelGeneric, int ILP = DPOMP_SIM_ILP>
 static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream, int mode) {
     constexpr int TILE = kBlockThreads * ITEMS;
     const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
-    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePlain>;
-    auto kern_fused = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModeFused>;
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePlain, ILP>;
+    auto kern_fused = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModeFused, ILP>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -696,7 +705,7 @@ static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream
     }
     if constexpr (sizeof(Real) == 4 && MODEL != kModelGeneric) {
         // the persistent kernel is instantiated for the f32 loop of the predefined models
-        auto kern_p = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePersist>;
+        auto kern_p = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePersist, ILP>;
         static bool configured_p = false;
         if (!configured_p) {
             cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -733,6 +742,7 @@ static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream
                            : launch_pdl(kern, grid, kBlockThreads, smem, stream, m, a));
 }
 
+constexpr int kLatencyRegimeCtas = 296;  // 2 CTAs per SM
 // the instantiated generic (C, E) shapes; a model runs on the smallest shape that covers it
 #define DPOMP_SIM_SHAPES(X) X(2, 1) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(4, 3) X(4, 6) X(8, 8)
 #define DPOMP_SIM_BUILTINS(X) X(kModelSI) X(kModelSIR) X(kModelSIS) X(kModelSEI) X(kModelSEIR) X(kModelSEIS) X(kModelLOTKA)
@@ -741,10 +751,16 @@ template <typename Real>
 static int sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStream_t stream, int mode) {
     const int c = mh.desc.n_compartments, e = mh.desc.n_events;
     const int model_id = builtin_model_id(mh.desc);
+    // latency regime: a few small filters (the reference's default 200 particles) leave most of the device idle, and a lane
+    // that interleaves its two particles halves the dependent chain of a step
+    const bool latency = sizeof(Real) == 4 && items == kItemsSmall && a.n_filters > 0 &&
+                         (long long)a.n_filters * a.ntiles <= kLatencyRegimeCtas;
 #define X(ID)                                                                                                             \
     if (model_id == ID) {                                                                                                 \
-        return items == kItemsSmall ? sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID>(mh, a, stream, mode)   \
-                                    : sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream, mode);  \
+        if (items == kItemsSmall)                                                                                         \
+            return latency ? sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID, 2>(mh, a, stream, mode)      \
+                           : sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID, 1>(mh, a, stream, mode);     \
+        return sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream, mode);                      \
     }
     DPOMP_SIM_BUILTINS(X)
 #undef X

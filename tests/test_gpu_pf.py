@@ -485,3 +485,24 @@ def test_persistent_kernel_with_non_likelihood_observations(dp):
     assert np.array_equal(res[0][0], res[1][0]) and np.all(np.isfinite(res[0][0]))
     for k in (1, 2, 3):
         assert np.array_equal(res[0][k], res[1][k])
+
+
+def test_small_filter_latency_kernel_equals_throughput_kernel(dp):
+    """Filters of <= 256 particles run two particles per lane at once when the launch is small (<= 296 CTAs: the latency
+    regime of the reference's default 200-particle filter) and one at a time in large batches: identical results, because the
+    random streams are keyed by (filter, particle, event), not by the schedule."""
+    model, y, hmm, theta = load_case(dp, "sis_pooley")
+    dm = dp.device_model(hmm)
+    nb_big = 400
+    thetas = theta[:, None] * np.linspace(0.8, 1.2, nb_big)[None, :]
+    big = dp.ParticleFilter(dm, 200, nb_big, 1, seed=3)
+    big.set_stream_key(4242)
+    ll_big = big.loglik(thetas)
+    ids = np.array([10, 11, 12, 399])
+    small = dp.ParticleFilter(dm, 200, len(ids), 1, seed=3)
+    small.set_filter_ids(ids)
+    small.set_stream_key(4242)
+    ll_small = small.loglik(thetas[:, ids])
+    assert np.array_equal(ll_small, ll_big[ids])
+    for j, b in enumerate(ids):
+        assert np.array_equal(small.get_pop(j + 1), big.get_pop(int(b) + 1))
