@@ -266,11 +266,12 @@ def run_mbp_ibis_c5(dp, world, rank, barrier):
     comm = dp.Comm() if world > 1 else None
     lo, hi = (comm.bounds(MBPI_OUTER) if comm is not None else (0, MBPI_OUTER))
     th0 = model.prior.rand(MBPI_OUTER, np.random.default_rng(3))
-    # warm-up on the first observations (reaches a resample-mutate step: NCCL sets up all-to-all connections lazily)
-    hmm_w = dp.get_private_model(model, y[:12])
-    dp.run_mbp_ibis(hmm_w, th0[:, : max(MBPI_OUTER // 8, 8 * world)], 0.5, 3, False, 1.002, seed=5, comm=comm, outer_rs=dp.rs_stratified, verbose=False)
+    ptcls = dp.MbpParticles(dp.device_model(hmm), max(hi - lo, 1), seed=4)
+    # warm-up = one full analysis on the same store (0.2 s): NCCL sets up its send / receive connections lazily at the first
+    # migration (0.3 s at two ranks), and a shortened data set does not reach a resample-move step
+    dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=5, comm=comm, outer_rs=dp.rs_stratified, verbose=False,
+                    particles_factory=lambda n, sd: ptcls)
     gc.collect()
-    ptcls = dp.MbpParticles(dp.device_model(hmm), max(hi - lo, 1), 8192, 4)
     barrier()
     t0 = time.perf_counter()
     r = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=4, comm=comm, outer_rs=dp.rs_stratified, verbose=False,

@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <stdlib.h>
+
 #include "dpomp_dev.cuh"
 #include "dpomp_internal.cuh"
 #include "dpomp_models.cuh"
@@ -862,6 +865,15 @@ int dpomp_mbp_import(dpomp_mbp* h, const int64_t* slots, const int64_t* offsets,
 // fixed records (64 B per particle), event times (f64) and event types (u8); local ancestors are copied on the device.
 int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx, int64_t n_total) {
     if (!h || !c || !nidx) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    static const bool trace = getenv("DPOMP_TRACE_MIGRATE") != nullptr;  // per-segment host times on stderr (diagnostics)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_seg = now();
+    auto seg = [&](const char* name) {
+        if (!trace) return;
+        const auto t1 = now();
+        fprintf(stderr, "[mbp_migrate] %-12s %8.1f us\n", name, std::chrono::duration<double, std::micro>(t1 - t_seg).count());
+        t_seg = t1;
+    };
     const int world = comm_world(c), rank = comm_rank(c);
     for (int64_t p = 0; p < n_total; ++p)
         if (nidx[p] < 1 || nidx[p] > n_total) return dpomp_set_error(DPOMP_ERR_ARG, "ancestor index out of range");
@@ -872,6 +884,7 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     const size_t n_send = pl.send_slots.size(), n_recv = pl.recv_slots.size(), n_loc = pl.local_src.size();
     if ((int)n_loc > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "this rank's block exceeds the store");
     cudaStream_t st = h->stream;
+    seg("plan");
     // phase 1: event counts
     std::vector<int> all_len((size_t)h->n);
     MCK(cudaMemcpyAsync(all_len.data(), h->store[h->cur].len, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -890,6 +903,7 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     if (rc) return rc;
     MCK(cudaMemcpyAsync(sc.h_int + n_send, sc.d_int + n_send, n_recv * sizeof(int), cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));
+    seg("lengths");
     // phase 2: payload.  packed layout per direction: [fixed: n x 64 B][times: events x 8 B][types: events x 1 B]
     std::vector<int64_t> off_s(n_send + 1, 0), off_r(n_recv + 1, 0);
     int max_recv = 0;
@@ -913,6 +927,7 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     for (size_t k = 0; k < n_loc; ++k) hs[2 * n_send + k] = pl.local_src[k];
     for (size_t k = 0; k < n_recv; ++k) { hs[2 * n_send + n_loc + k] = pl.recv_slots[k]; hs[2 * n_send + n_loc + n_recv + k] = off_r[k]; }
     MCK(cudaMemcpyAsync(sc.d_slots, hs, n_slots * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    seg("scratch");
     int* fx_s = (int*)sc.d_send; double* tm_s = (double*)(sc.d_send + n_send * fixed_b); unsigned char* ty_s = sc.d_send + n_send * fixed_b + ev_s * 8;
     int* fx_r = (int*)sc.d_recv; double* tm_r = (double*)(sc.d_recv + n_recv * fixed_b); unsigned char* ty_r = sc.d_recv + n_recv * fixed_b + ev_r * 8;
     if (n_send) {
@@ -937,6 +952,7 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
         rc = comm_alltoallv_bytes(c, sp, sb.data(), rp, rb.data(), st);
         if (rc) return rc;
     }
+    if (trace) { MCK(cudaStreamSynchronize(st)); seg("pack+nccl"); }
     if (n_loc) {
         mbp_copy_kernel<<<(unsigned)n_loc, 128, 0, st>>>(h->store[h->cur ^ 1], h->store[h->cur], nullptr, sc.d_slots + 2 * n_send, h->cap, h->dm.n_comp);
         MCK(cudaGetLastError());
@@ -948,6 +964,7 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
         MCK(cudaGetLastError());
     }
     MCK(cudaStreamSynchronize(st));
+    seg("copy+unpack");
     return DPOMP_OK;
 }
 
