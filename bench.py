@@ -142,8 +142,10 @@ def run_smc2(dp, world, rank, barrier):
     model.prior = dp.UniformProduct([0, 0, 0], [1.0, 0.01, 1.0])
     y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "lotka_c4.csv"))
     comm = dp.Comm() if world > 1 else None
-    # warm-up long enough to reach a resample-mutate step: NCCL sets up its all-to-all connections lazily on first use
-    dp.run_ibis_analysis(model, y[:12], np=max(SMC2_OUTER // 8, 8 * world), npf=SMC2_NPF, seed=3, comm=comm, verbose=False)
+    # warm-up with the SAME collective shapes as the timed run (all 8192 theta-particles, fewer state particles, enough
+    # observations to reach a resample-move step): NCCL connects lazily per algorithm / protocol / message size class, and a
+    # smaller warm-up left 0.15 s of connection set-up inside the timed region at 8 ranks
+    dp.run_ibis_analysis(model, y[:12], np=SMC2_OUTER, npf=256, seed=3, comm=comm, verbose=False)
     import gc
 
     gc.collect()  # release the warm-up handles now: cudaFree synchronises and must not land in the timed region
