@@ -111,6 +111,13 @@ _SIGS = {
     "dpomp_mbp_get_lengths": (C.c_int, [_P, _P, C.c_int32, _P]),
     "dpomp_mbp_export": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
     "dpomp_mbp_import": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
+    "dpomp_mbp_outer_begin": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "dpomp_mbp_outer_iterate": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "dpomp_mbp_outer_moments": (C.c_int, [_P, _P, _P]),
+    "dpomp_mbp_outer_resample": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P]),
+    "dpomp_mbp_outer_sweep": (C.c_int, [_P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P]),
+    "dpomp_mbp_outer_get": (C.c_int, [_P, _P, _P]),
+    "dpomp_mbp_outer_end": (C.c_int, [_P]),
     "dpomp_mbp_capacity": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dpomp_mbp_reserve": (C.c_int, [_P, C.c_int32]),
     "dpomp_mbp_get_states": (C.c_int, [_P, C.c_int32, _P]),

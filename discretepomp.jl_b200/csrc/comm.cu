@@ -226,6 +226,45 @@ int comm_alltoallv_bytes(dpomp_comm* c, const void* send, const size_t* send_byt
     return DPOMP_OK;
 }
 
+// rows of an all-gathered [world][maxn][width] block -> contiguous [n_total][width] (device)
+__global__ void compact_rows_kernel(const double* gathered, double* out, long long n_total, int world, long long maxn, int width) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total * width) return;
+    const long long row = i / width;
+    const int col = (int)(i % width);
+    const long long base = n_total / world, extra = n_total % world, cut = extra * (base + 1);
+    const long long r = row < cut ? row / (base + 1) : extra + (row - cut) / (base > 0 ? base : 1);
+    const long long lo = r * base + (r < extra ? r : extra);
+    out[i] = gathered[((size_t)r * maxn + (row - lo)) * width + col];
+}
+
+// all-gather of per-item rows between DEVICE buffers on `stream`: send = this rank's block [n_loc][width], out = all
+// [n_total][width] rows in global order on every rank (ncclAllGather of the padded blocks + a compaction kernel)
+int comm_allgather_rows_device(dpomp_comm* c, const double* send, long long n_total, int width, double* out, cudaStream_t stream) {
+    int64_t lo, hi;
+    bounds(n_total, c->world, c->rank, &lo, &hi);
+    const size_t nloc = (size_t)(hi - lo) * width;
+    if (c->world == 1) {
+        if (nloc) CCK(cudaMemcpyAsync(out, send, nloc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        return DPOMP_OK;
+    }
+    const int64_t maxn = max_block(n_total, c->world);
+    const size_t per = (size_t)maxn * width;
+    int rc = grow_f64(c, per);
+    if (rc) return rc;
+    if (nloc) CCK(cudaMemcpyAsync(c->d_send, send, nloc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    NCK(nccl_api()->AllGather(c->d_send, c->d_recv, per, ncclFloat64, c->nccl, stream));
+    const long long total = n_total * width;
+    compact_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(c->d_recv, out, n_total, c->world, maxn, width);
+    CCK(cudaGetLastError());
+    return DPOMP_OK;
+}
+void comm_bounds(const dpomp_comm* c, long long n_total, long long* lo, long long* hi) {
+    int64_t l, h;
+    bounds(n_total, c->world, c->rank, &l, &h);
+    *lo = l; *hi = h;
+}
+
 int comm_rank(const dpomp_comm* c) { return c->rank; }
 int comm_world(const dpomp_comm* c) { return c->world; }
 int comm_scratch(dpomp_comm* c, size_t slots, size_t send_bytes, size_t recv_bytes, size_t ints, CommScratch* out) {

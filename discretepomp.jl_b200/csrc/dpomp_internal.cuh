@@ -204,6 +204,8 @@ struct MigrationPlan {  // 1-based LOCAL slots; send / recv lists ordered by pee
 void migration_plan(const int64_t* nidx, int64_t n_total, int world, int rank, MigrationPlan& out);
 int comm_alltoallv_bytes(dpomp_comm* c, const void* send, const size_t* send_bytes, void* recv, const size_t* recv_bytes,
                          cudaStream_t stream);
+int comm_allgather_rows_device(dpomp_comm* c, const double* send, long long n_total, int width, double* out, cudaStream_t stream);
+void comm_bounds(const dpomp_comm* c, long long n_total, long long* lo, long long* hi);
 int comm_rank(const dpomp_comm* c);
 int comm_world(const dpomp_comm* c);
 struct CommScratch {

@@ -523,6 +523,206 @@ __global__ void mbp_reset_kernel(const __grid_constant__ MbpModel m, MbpStore st
     st.ll[2 * (size_t)p] = st.ll[2 * (size_t)p + 1] = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Device-resident outer layer of MBP-IBIS (run_mbp_ibis src/hmm_ibis.jl:140-244): theta, prior, log-likelihood, weights and
+// the marginal increments of ALL n_total theta-particles live on the device, REPLICATED on every rank; the replicated
+// kernels below are O(n_total) and deterministic (fixed reduction trees over the global arrays), so every rank takes
+// identical decisions and results do not depend on the number of ranks.  Only the trajectory kernels (iterate / propose /
+// accept copy) are sharded.  Proposal and accept draws: Philox4x32-10 keyed by the GLOBAL particle id.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kTagOuter = 3u;
+constexpr int kOuterThreads = 1024;
+
+// deterministic sum of k values per thread over a single CTA of kOuterThreads threads: thread-serial over its strided
+// elements, then a shared-memory tree
+template <int K>
+__device__ __forceinline__ void outer_block_sum(double (&v)[K], double* out /*[K] global*/) {
+    __shared__ double red[kOuterThreads];
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {  // one tree per value, the 8 KB buffer reused
+        double mine = v[0];
+#pragma unroll
+        for (int j = 1; j < K; ++j) mine = (k == j) ? v[j] : mine;  // (registers: no dynamic indexing)
+        red[tid] = mine;
+        __syncthreads();
+        for (int s = kOuterThreads / 2; s > 0; s >>= 1) {
+            if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+            __syncthreads();
+        }
+        if (tid == 0) out[k] = red[0];
+        __syncthreads();
+    }
+}
+
+// logpdf(Product(Uniform.(lo, hi)), theta) for every particle (src/hmm_ibis.jl:153); w = 1, log_like = 0
+__global__ void outer_init_kernel(const double* theta, const double* lo, const double* hi, int d, long long n, double* prior,
+                                  double* w, double* log_like) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double lp = 0.0;
+    bool inside = true;
+    for (int k = 0; k < d; ++k) {
+        const double v = theta[p * d + k];
+        inside = inside && v >= lo[k] && v <= hi[k];
+        lp -= log(hi[k] - lo[k]);
+    }
+    prior[p] = inside ? lp : -INFINITY;
+    w[p] = 1.0;
+    log_like[p] = 0.0;
+}
+
+// :181-185  gx = exp(lg); S0 = sum w, S1 = sum w gx; w *= gx; S2 = sum w, S3 = sum w^2; log_like += lg.  One CTA.
+__global__ void __launch_bounds__(kOuterThreads) outer_reweight_kernel(const double* lg, double* w, double* gx, double* log_like,
+                                                                        long long n, int has_lik, double* out5) {
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (long long p = threadIdx.x; p < n; p += kOuterThreads) {
+        if (!has_lik) continue;
+        const double g = exp(lg[p]);
+        const double w0 = w[p], w1 = w0 * g;
+        gx[p] = g;
+        log_like[p] += lg[p];  // -Inf propagates for overflowed trajectories (src/hmm_sim.jl:17-20)
+        w[p] = w1;
+        v[0] = __dadd_rn(v[0], w0);
+        v[1] = __dadd_rn(v[1], w0 * g);
+        v[2] = __dadd_rn(v[2], w1);
+        v[3] = __dadd_rn(v[3], w1 * w1);
+        v[4] = __dadd_rn(v[4], w1 * g);  // (:231 uses the already updated w, as written in the reference)
+    }
+    outer_block_sum<5>(v, out5);
+}
+
+// compute_is_mu_covar! (src/cmn.jl:91-99), pass 1: sum w and sum w theta_k; pass 2: sum w (theta_i - mu_i)(theta_j - mu_j)
+template <int DMAX>
+__global__ void __launch_bounds__(kOuterThreads) outer_moment1_kernel(const double* theta, const double* w, int d, long long n,
+                                                                       double* out /*[1 + DMAX]*/) {
+    double v[1 + DMAX];
+#pragma unroll
+    for (int k = 0; k < 1 + DMAX; ++k) v[k] = 0.0;
+    for (long long p = threadIdx.x; p < n; p += kOuterThreads) {
+        const double wp = w[p];
+        v[0] = __dadd_rn(v[0], wp);
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k)
+            if (k < d) v[1 + k] = __dadd_rn(v[1 + k], wp * theta[p * d + k]);
+    }
+    outer_block_sum<1 + DMAX>(v, out);
+}
+template <int DMAX>
+__global__ void __launch_bounds__(kOuterThreads) outer_moment2_kernel(const double* theta, const double* w, const double* mu, int d,
+                                                                       long long n, double* out /*[DMAX * (DMAX + 1) / 2]*/) {
+    constexpr int NT = DMAX * (DMAX + 1) / 2;
+    double v[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) v[k] = 0.0;
+    for (long long p = threadIdx.x; p < n; p += kOuterThreads) {
+        const double wp = w[p];
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j, ++t)
+                if (i < d) v[t] = __dadd_rn(v[t], wp * (theta[p * d + i] - mu[i]) * (theta[p * d + j] - mu[j]));
+    }
+    outer_block_sum<NT>(v, out);
+}
+
+// resample gather (:196-201 for the host-side fields): new[p] = old[nidx[p] - 1]
+__global__ void outer_gather_kernel(const int64_t* nidx, int d, long long n, const double* theta, const double* prior, const double* log_like,
+                                    const double* gx, double* theta2, double* prior2, double* log_like2, double* mtd_gx, double* w) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const long long s = nidx[p] - 1;
+    for (int k = 0; k < d; ++k) theta2[p * d + k] = theta[s * d + k];
+    prior2[p] = prior[s];
+    log_like2[p] = log_like[s];
+    mtd_gx[p] = gx[s];
+    w[p] = 1.0;  // :227
+}
+__global__ void __launch_bounds__(kOuterThreads) outer_sum_kernel(const double* x, long long n, double* out1) {
+    double v[1] = {0.0};
+    for (long long p = threadIdx.x; p < n; p += kOuterThreads) v[0] = __dadd_rn(v[0], x[p]);
+    outer_block_sum<1>(v, out1);
+}
+
+__device__ __forceinline__ double outer_u53_open(uint32_t hi, uint32_t lo) {  // (0, 1]
+    return 1.0 - u53(hi, lo);
+}
+// get_mv_param (src/hmm_cmn.jl:13-18) for every particle: theta_f = base + scale * (L z), z ~ N(0, I) by Box-Muller on
+// Philox draws keyed by the global particle id; base = mu (ind_prop) or the particle's theta; prior_f and valid (:204-206)
+template <int DMAX>
+__global__ void outer_propose_kernel(const double* theta, const double* mu, const double* chol /*[d][d] row-major lower*/, double scale,
+                                     int ind_prop, const double* lo, const double* hi, int d, long long n, uint64_t key,
+                                     double* theta_f, double* prior_f, unsigned char* valid) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double z[DMAX];
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 2) {
+        if (j < d) {
+            const Philox4 q = stream_draw(key, (uint32_t)p, (uint32_t)(j >> 1), 0u, kTagOuter, 0u);
+            const double r = sqrt(-2.0 * log(outer_u53_open(q.w0, q.w1)));
+            double sn, cs;
+            sincospi(2.0 * u53(q.w2, q.w3), &sn, &cs);
+            z[j] = r * cs;
+            if (j + 1 < DMAX) z[j + 1] = r * sn;
+        }
+    }
+    double lp = 0.0;
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+        if (i < d) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc += chol[i * d + j] * z[j];
+            const double v = (ind_prop ? mu[i] : theta[p * d + i]) + scale * acc;
+            theta_f[p * d + i] = v;
+            inside = inside && v >= lo[i] && v <= hi[i];
+            lp -= log(hi[i] - lo[i]);
+        }
+    }
+    prior_f[p] = inside ? lp : -INFINITY;
+    valid[p] = inside ? 1 : 0;
+}
+
+// :212-218 for every particle: accept iff exp(prior_f - prior) * exp(ll_f[0] - log_like) > rand()
+__global__ void outer_accept_kernel(const double* llf /*[n][2]*/, const double* theta_f, const double* prior_f, int d, long long n,
+                                    uint64_t key, double* theta, double* prior, double* log_like, double* mtd_gx, unsigned char* acc) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const Philox4 q = stream_draw(key, (uint32_t)p, 0xffffu, 0u, kTagOuter, 1u);
+    const double u = u53(q.w0, q.w1);
+    const double ratio = exp(prior_f[p] - prior[p]) * exp(llf[2 * p] - log_like[p]);
+    const bool a = ratio > u;  // NaN compares false, as in the reference
+    acc[p] = a ? 1 : 0;
+    if (a) {
+        for (int k = 0; k < d; ++k) theta[p * d + k] = theta_f[p * d + k];
+        prior[p] = prior_f[p];
+        log_like[p] = llf[2 * p];
+        mtd_gx[p] = exp(llf[2 * p + 1]);
+    }
+}
+__global__ void __launch_bounds__(kOuterThreads) outer_count_kernel(const unsigned char* acc, long long n, double* out1) {
+    double v[1] = {0.0};
+    for (long long p = threadIdx.x; p < n; p += kOuterThreads) v[0] += acc[p] ? 1.0 : 0.0;
+    outer_block_sum<1>(v, out1);
+}
+// ptcls[p] = xf for the accepted particles of this rank's block (:214): dst = current store, src = proposal store
+__global__ void __launch_bounds__(128) mbp_copy_flagged_kernel(MbpStore dst, MbpStore src, const unsigned char* acc, int cap, int n_comp) {
+    const int p = blockIdx.x;
+    if (!acc[p]) return;
+    const int len = src.len[p];
+    const double* st = src.ev_time + (size_t)p * cap;
+    double* dt = dst.ev_time + (size_t)p * cap;
+    const unsigned char* sy = src.ev_type + (size_t)p * cap;
+    unsigned char* dy = dst.ev_type + (size_t)p * cap;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) { dt[i] = st[i]; dy[i] = sy[i]; }
+    if (threadIdx.x < n_comp) dst.fc[(size_t)p * n_comp + threadIdx.x] = src.fc[(size_t)p * n_comp + threadIdx.x];
+    if (threadIdx.x == 32) dst.len[p] = len;
+    if (threadIdx.x == 64) { dst.ll[2 * p] = src.ll[2 * p]; dst.ll[2 * p + 1] = src.ll[2 * p + 1]; }
+}
+
 }  // namespace dpomp
 
 // ------------------------------------------------------------------------------------------------------------
@@ -538,7 +738,27 @@ using namespace dpomp;
         if (_e != cudaSuccess) return dpomp_set_error(DPOMP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// replicated device state of the outer layer (all n_total theta-particles; see the kernels above)
+struct MbpOuter {
+    dpomp_comm* comm = nullptr;
+    long long n_total = 0, lo = 0, hi = 0;
+    int d = 0;
+    double *theta = nullptr, *theta2 = nullptr, *theta_f = nullptr, *prior = nullptr, *prior2 = nullptr, *prior_f = nullptr;
+    double *log_like = nullptr, *log_like2 = nullptr, *w = nullptr, *gx = nullptr, *mtd_gx = nullptr, *lg_all = nullptr, *llf_all = nullptr;
+    double *box = nullptr;      // [2][d] prior bounds
+    double *par = nullptr;      // [d + d*d] mu, chol of the current sweep
+    double *red = nullptr;      // [64] reduction results
+    double *cw = nullptr, *u = nullptr;  // [n_total] cumulative weights / resampling draws
+    int64_t* nidx = nullptr;    // [n_total]
+    unsigned char *valid = nullptr, *acc = nullptr;
+    double* h_red = nullptr;    // pinned [64]
+    std::vector<double> h_w;    // host copies for the sequential cumsum
+    std::vector<int64_t> h_nidx;
+    uint64_t sweep = 0;
+};
+
 struct dpomp_mbp {
+    MbpOuter* outer = nullptr;
     const dpomp_model* model = nullptr;
     int device = 0, n = 0;
     int cap = 0;       // current stride of the stores (events reserved per trajectory); grows on demand up to cap_max
@@ -578,9 +798,20 @@ static uint64_t mbp_next_key(dpomp_mbp* h) {
 #define DPOMP_MBP_MODELS(X) X(kModelGeneric) X(kModelSI) X(kModelSIR) X(kModelSIS) X(kModelSEI) X(kModelSEIR) X(kModelSEIS) X(kModelLOTKA)
 // one warp per trajectory while the warps of a launch fit on the device a few times over, else one thread per trajectory
 static bool mbp_use_warps(const dpomp_mbp* h, int n) { return h->mode == 2 || (h->mode == 0 && n <= kMbpWarpThreshold); }
+static void mbp_outer_free(dpomp_mbp* h) {
+    MbpOuter* o = h->outer;
+    if (!o) return;
+    cudaFree(o->theta); cudaFree(o->theta2); cudaFree(o->theta_f); cudaFree(o->prior); cudaFree(o->prior2); cudaFree(o->prior_f);
+    cudaFree(o->log_like); cudaFree(o->log_like2); cudaFree(o->w); cudaFree(o->gx); cudaFree(o->mtd_gx); cudaFree(o->lg_all);
+    cudaFree(o->llf_all); cudaFree(o->box); cudaFree(o->par); cudaFree(o->red); cudaFree(o->cw); cudaFree(o->u); cudaFree(o->nidx);
+    cudaFree(o->valid); cudaFree(o->acc); cudaFreeHost(o->h_red);
+    delete o;
+    h->outer = nullptr;
+}
 static void mbp_free(dpomp_mbp* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    mbp_outer_free(h);
     for (int s = 0; s < 3; ++s) {
         cudaFree(h->store[s].ev_time); cudaFree(h->store[s].ev_type); cudaFree(h->store[s].len);
         cudaFree(h->store[s].fc); cudaFree(h->store[s].ll);
@@ -713,13 +944,9 @@ int dpomp_mbp_reset(dpomp_mbp* h) {
     return DPOMP_OK;
 }
 
-int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_i, int32_t fresh, double* out_logg) {
-    if (!h || !theta || !out_logg) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
-    const dpomp_model_desc& d = h->model->h.desc;
-    if (n < 1 || n > h->n || obs_i < 1 || obs_i > d.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "argument out of range");
-    MCK(cudaSetDevice(h->device));
-    const uint64_t key = mbp_next_key(h);
-    MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+// iterate_particle! for particles 1..n of this store, theta / outputs on the DEVICE (theta_dev [n][d], h->out [n]); the
+// launch repeats after the stride has grown (same key, uncommitted particles only: see MbpGrow); synchronises the stream
+static int mbp_launch_iterate(dpomp_mbp* h, const double* theta_dev, int n, int obs_i, int fresh, uint64_t key) {
     const bool warps = mbp_use_warps(h, n);
     const int has_lik = h->model->h.obs_id[obs_i - 1] > 0;
     const MbpGrow g{h->cap_max, ++h->call_id, h->done, h->need_grow};
@@ -727,25 +954,69 @@ int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_
     if (h->model_id == ID) {                                                                                                   \
         if (warps)                                                                                                             \
             mbp_iterate_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
-                h->dm, h->store[h->cur], h->theta_i, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0, has_lik,   \
+                h->dm, h->store[h->cur], theta_dev, h->obs_time, h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0, has_lik,    \
                 key, (uint32_t)h->batch_offset, h->out, g);                                                                    \
         else                                                                                                                   \
-            mbp_iterate_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->theta_i, h->obs_time,   \
+            mbp_iterate_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], theta_dev, h->obs_time,    \
                                                                            h->obs_ysum, n, h->cap, obs_i - 1, fresh ? 1 : 0,   \
                                                                            has_lik, key, (uint32_t)h->batch_offset, h->out, g); \
     }
-    for (;;) {  // re-launched (same key, uncommitted particles only) after the stride has grown: see MbpGrow
+    for (;;) {
         MCK(cudaMemsetAsync(h->need_grow, 0, sizeof(int), h->stream));
         DPOMP_MBP_MODELS(DPOMP_MBP_ITERATE)
         MCK(cudaGetLastError());
         MCK(cudaMemcpyAsync(h->h_need_grow, h->need_grow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         MCK(cudaStreamSynchronize(h->stream));
         if (!*h->h_need_grow) break;
         const int rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
         if (rc) return rc;
     }
 #undef DPOMP_MBP_ITERATE
+    return DPOMP_OK;
+}
+
+// partial_model_based_proposal for particles 1..n, all arguments on the DEVICE; result in h->out [n][2]
+static int mbp_launch_propose(dpomp_mbp* h, const double* theta_i_dev, const double* theta_f_dev, const unsigned char* valid_dev, int n,
+                              int ymax, uint64_t key) {
+    const bool warps = mbp_use_warps(h, n);
+    const MbpGrow g{h->cap_max, ++h->call_id, h->done, h->need_grow};
+#define DPOMP_MBP_PROPOSE(ID)                                                                                                  \
+    if (h->model_id == ID) {                                                                                                   \
+        if (warps)                                                                                                             \
+            mbp_propose_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
+                h->dm, h->store[h->cur], h->store[2], theta_i_dev, theta_f_dev, valid_dev, h->obs_time, h->obs_ysum,           \
+                h->obs_haslik, n, h->cap, ymax, key, (uint32_t)h->batch_offset, h->out, g);                                    \
+        else                                                                                                                   \
+            mbp_propose_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], theta_i_dev,  \
+                                                                           theta_f_dev, valid_dev, h->obs_time, h->obs_ysum,   \
+                                                                           h->obs_haslik, n, h->cap, ymax, key,                \
+                                                                           (uint32_t)h->batch_offset, h->out, g);              \
+    }
+    for (;;) {
+        MCK(cudaMemsetAsync(h->need_grow, 0, sizeof(int), h->stream));
+        DPOMP_MBP_MODELS(DPOMP_MBP_PROPOSE)
+        MCK(cudaGetLastError());
+        MCK(cudaMemcpyAsync(h->h_need_grow, h->need_grow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        MCK(cudaStreamSynchronize(h->stream));
+        if (!*h->h_need_grow) break;
+        const int rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
+        if (rc) return rc;
+    }
+#undef DPOMP_MBP_PROPOSE
+    return DPOMP_OK;
+}
+
+int dpomp_mbp_iterate(dpomp_mbp* h, const double* theta, int32_t n, int32_t obs_i, int32_t fresh, double* out_logg) {
+    if (!h || !theta || !out_logg) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const dpomp_model_desc& d = h->model->h.desc;
+    if (n < 1 || n > h->n || obs_i < 1 || obs_i > d.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "argument out of range");
+    MCK(cudaSetDevice(h->device));
+    const uint64_t key = mbp_next_key(h);
+    MCK(cudaMemcpyAsync(h->theta_i, theta, (size_t)n * d.n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int rc = mbp_launch_iterate(h, h->theta_i, n, obs_i, fresh, key);
+    if (rc) return rc;
+    MCK(cudaMemcpyAsync(out_logg, h->out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCK(cudaStreamSynchronize(h->stream));
     return DPOMP_OK;
 }
 
@@ -760,32 +1031,10 @@ int dpomp_mbp_propose(dpomp_mbp* h, const double* theta_i, const double* theta_f
     MCK(cudaMemcpyAsync(h->theta_i, theta_i, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->theta_f, theta_f, tb, cudaMemcpyHostToDevice, h->stream));
     MCK(cudaMemcpyAsync(h->valid, valid, (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    const bool warps = mbp_use_warps(h, n);
-    const MbpGrow g{h->cap_max, ++h->call_id, h->done, h->need_grow};
-#define DPOMP_MBP_PROPOSE(ID)                                                                                                  \
-    if (h->model_id == ID) {                                                                                                   \
-        if (warps)                                                                                                             \
-            mbp_propose_warp_kernel<ID><<<(n + kMbpWarpsPerCta - 1) / kMbpWarpsPerCta, 32 * kMbpWarpsPerCta, 0, h->stream>>>(  \
-                h->dm, h->store[h->cur], h->store[2], h->theta_i, h->theta_f, h->valid, h->obs_time, h->obs_ysum,              \
-                h->obs_haslik, n, h->cap, ymax, key, (uint32_t)h->batch_offset, h->out, g);                                    \
-        else                                                                                                                   \
-            mbp_propose_kernel<ID><<<(n + 127) / 128, 128, 0, h->stream>>>(h->dm, h->store[h->cur], h->store[2], h->theta_i,   \
-                                                                           h->theta_f, h->valid, h->obs_time, h->obs_ysum,     \
-                                                                           h->obs_haslik, n, h->cap, ymax, key,                \
-                                                                           (uint32_t)h->batch_offset, h->out, g);              \
-    }
-    for (;;) {
-        MCK(cudaMemsetAsync(h->need_grow, 0, sizeof(int), h->stream));
-        DPOMP_MBP_MODELS(DPOMP_MBP_PROPOSE)
-        MCK(cudaGetLastError());
-        MCK(cudaMemcpyAsync(h->h_need_grow, h->need_grow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        MCK(cudaStreamSynchronize(h->stream));
-        if (!*h->h_need_grow) break;
-        const int rc = mbp_grow(h, h->cap > h->cap_max / 2 ? h->cap_max : 2 * h->cap);
-        if (rc) return rc;
-    }
-#undef DPOMP_MBP_PROPOSE
+    const int rc = mbp_launch_propose(h, h->theta_i, h->theta_f, h->valid, n, ymax, key);
+    if (rc) return rc;
+    MCK(cudaMemcpyAsync(out_loglike, h->out, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCK(cudaStreamSynchronize(h->stream));
     return DPOMP_OK;
 }
 
@@ -965,6 +1214,185 @@ int dpomp_mbp_resample_migrate(dpomp_mbp* h, dpomp_comm* c, const int64_t* nidx,
     }
     MCK(cudaStreamSynchronize(st));
     seg("copy+unpack");
+    return DPOMP_OK;
+}
+
+// ---- device-resident outer layer (see the kernels "Device-resident outer layer of MBP-IBIS") -----------------------------
+#define OUTER_OR_FAIL(h)                                                                                   \
+    if (!(h) || !(h)->outer) return dpomp_set_error(DPOMP_ERR_STATE, "dpomp_mbp_outer_begin has not been called"); \
+    MbpOuter* o = (h)->outer;                                                                              \
+    MCK(cudaSetDevice((h)->device));                                                                       \
+    cudaStream_t st = (h)->stream
+
+int dpomp_mbp_outer_begin(dpomp_mbp* h, dpomp_comm* c, int64_t n_total, const double* theta_all, const double* prior_lo,
+                          const double* prior_hi) {
+    if (!h || !c || !theta_all || !prior_lo || !prior_hi) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const int d = h->dm.n_params;
+    if (d > 8) return dpomp_set_error(DPOMP_ERR_ARG, "the device-resident outer layer supports up to 8 parameters");
+    long long lo, hi;
+    comm_bounds(c, n_total, &lo, &hi);
+    if (hi - lo > h->n) return dpomp_set_error(DPOMP_ERR_ARG, "this rank's block exceeds the store");
+    MCK(cudaSetDevice(h->device));
+    mbp_outer_free(h);
+    MbpOuter* o = new (std::nothrow) MbpOuter();
+    if (!o) return dpomp_set_error(DPOMP_ERR_ARG, "out of host memory");
+    h->outer = o;
+    o->comm = c; o->n_total = n_total; o->lo = lo; o->hi = hi; o->d = d;
+    const size_t N = (size_t)n_total, D = (size_t)d;
+    bool ok = true;
+#define OA(ptr, count, T) ok = ok && cudaMalloc((void**)&o->ptr, (count) * sizeof(T)) == cudaSuccess
+    OA(theta, N * D, double); OA(theta2, N * D, double); OA(theta_f, N * D, double);
+    OA(prior, N, double); OA(prior2, N, double); OA(prior_f, N, double);
+    OA(log_like, N, double); OA(log_like2, N, double); OA(w, N, double); OA(gx, N, double); OA(mtd_gx, N, double);
+    OA(lg_all, N, double); OA(llf_all, 2 * N, double); OA(box, 2 * D, double); OA(par, D + D * D, double); OA(red, 64, double);
+    OA(cw, N, double); OA(u, N, double); OA(nidx, N, int64_t); OA(valid, N, unsigned char); OA(acc, N, unsigned char);
+#undef OA
+    ok = ok && cudaMallocHost((void**)&o->h_red, 64 * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        mbp_outer_free(h);
+        return dpomp_set_error(DPOMP_ERR_CUDA, std::string("dpomp_mbp_outer_begin: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    o->h_w.resize(N); o->h_nidx.resize(N);
+    cudaStream_t st = h->stream;
+    MCK(cudaMemcpyAsync(o->theta, theta_all, N * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(o->box, prior_lo, D * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(o->box + D, prior_hi, D * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemsetAsync(o->gx, 0, N * sizeof(double), st));
+    outer_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(o->theta, o->box, o->box + D, d, n_total, o->prior, o->w, o->log_like);
+    MCK(cudaGetLastError());
+    h->batch_offset = lo;
+    MCK(cudaStreamSynchronize(st));
+    return dpomp_mbp_reset(h);
+}
+
+// iterate_particle! for this rank's block (:176-179), all-gather of log g, then (if the observation carries a likelihood)
+// gx = exp(log g), w *= gx (:181-185).  out5 = { sum w_old, sum w_old gx, sum w_new, sum w_new^2, sum w_new gx } for lml, the
+// ESS and the non-resampling evidence update (:231).
+int dpomp_mbp_outer_iterate(dpomp_mbp* h, int32_t obs_i, int32_t fresh, double* out5) {
+    OUTER_OR_FAIL(h);
+    if (!out5 || obs_i < 1 || obs_i > h->model->h.desc.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "argument out of range");
+    const int n_loc = (int)(o->hi - o->lo);
+    const uint64_t key = mbp_next_key(h);
+    if (n_loc) {
+        const int rc = mbp_launch_iterate(h, o->theta + (size_t)o->lo * o->d, n_loc, obs_i, fresh, key);
+        if (rc) return rc;
+    }
+    int rc = comm_allgather_rows_device(o->comm, h->out, o->n_total, 1, o->lg_all, st);
+    if (rc) return rc;
+    const int has_lik = h->model->h.obs_id[obs_i - 1] > 0;
+    outer_reweight_kernel<<<1, kOuterThreads, 0, st>>>(o->lg_all, o->w, o->gx, o->log_like, o->n_total, has_lik, o->red);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(o->h_red, o->red, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    memcpy(out5, o->h_red, 5 * sizeof(double));
+    return DPOMP_OK;
+}
+
+// compute_is_mu_covar! (src/cmn.jl:91-99) on the device state: mu[d], cv[d][d]
+int dpomp_mbp_outer_moments(dpomp_mbp* h, double* out_mu, double* out_cv) {
+    OUTER_OR_FAIL(h);
+    if (!out_mu || !out_cv) return dpomp_set_error(DPOMP_ERR_ARG, "null argument");
+    const int d = o->d;
+    outer_moment1_kernel<8><<<1, kOuterThreads, 0, st>>>(o->theta, o->w, d, o->n_total, o->red);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(o->h_red, o->red, 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    const double sw = o->h_red[0];
+    double mu[8];
+    for (int k = 0; k < d; ++k) { mu[k] = o->h_red[1 + k] / sw; out_mu[k] = mu[k]; }
+    MCK(cudaMemcpyAsync(o->par, mu, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, st));
+    outer_moment2_kernel<8><<<1, kOuterThreads, 0, st>>>(o->theta, o->w, o->par, d, o->n_total, o->red);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(o->h_red, o->red, 36 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    int t = 0;
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j <= i; ++j, ++t)
+            if (i < d) out_cv[i * d + j] = out_cv[j * d + i] = o->h_red[t] / sw;
+    return DPOMP_OK;
+}
+
+// outer resample (:194-201): nidx = rs_systematic / rs_stratified (w) with the given rand() draws (cumsum sequential on the
+// host like the reference's, search on the device), gather of the replicated fields, migration of the trajectories, w = 1.
+// out2 = { mean(gx[nidx]), unused }
+int dpomp_mbp_outer_resample(dpomp_mbp* h, int32_t rs_type, const double* u, int64_t n_u, double* out2) {
+    OUTER_OR_FAIL(h);
+    if (!u || !out2 || (rs_type != DPOMP_RS_SYSTEMATIC && rs_type != DPOMP_RS_STRATIFIED)) return dpomp_set_error(DPOMP_ERR_ARG, "bad argument");
+    const long long n = o->n_total;
+    const int64_t need_u = rs_type == DPOMP_RS_SYSTEMATIC ? 1 : n;
+    if (n_u < need_u) return dpomp_set_error(DPOMP_ERR_ARG, "not enough uniforms");
+    MCK(cudaMemcpyAsync(o->h_w.data(), o->w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    for (long long i = 1; i < n; ++i) o->h_w[(size_t)i] = o->h_w[(size_t)i - 1] + o->h_w[(size_t)i];  // cumsum (src/hmm_resample.jl:45,67)
+    MCK(cudaMemcpyAsync(o->cw, o->h_w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(o->u, u, (size_t)need_u * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCK(launch_search_hook(rs_type, o->cw, n, o->u, n, o->nidx, st));
+    MCK(cudaMemcpyAsync(o->h_nidx.data(), o->nidx, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    outer_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(o->nidx, o->d, n, o->theta, o->prior, o->log_like, o->gx, o->theta2,
+                                                                    o->prior2, o->log_like2, o->mtd_gx, o->w);
+    MCK(cudaGetLastError());
+    std::swap(o->theta, o->theta2); std::swap(o->prior, o->prior2); std::swap(o->log_like, o->log_like2);
+    outer_sum_kernel<<<1, kOuterThreads, 0, st>>>(o->mtd_gx, n, o->red);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(o->h_red, o->red, sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    out2[0] = o->h_red[0] / (double)n;
+    out2[1] = 0.0;
+    return dpomp_mbp_resample_migrate(h, o->comm, o->h_nidx.data(), n);
+}
+
+// one mutation sweep over all particles (:203-219).  out2 = { accepted proposals, mean(mtd_gx) after the sweep }
+int dpomp_mbp_outer_sweep(dpomp_mbp* h, const double* mu, const double* chol, double scale, int32_t ind_prop, int32_t obs_i, double* out2) {
+    OUTER_OR_FAIL(h);
+    if (!mu || !chol || !out2 || obs_i < 1 || obs_i > h->model->h.desc.n_obs) return dpomp_set_error(DPOMP_ERR_ARG, "bad argument");
+    const int d = o->d;
+    const long long n = o->n_total;
+    const int n_loc = (int)(o->hi - o->lo);
+    const uint64_t key = mbp_next_key(h);
+    double par[8 + 64];
+    memcpy(par, mu, (size_t)d * sizeof(double));
+    memcpy(par + d, chol, (size_t)d * d * sizeof(double));
+    // (a pageable source is staged by the runtime before cudaMemcpyAsync returns)
+    MCK(cudaMemcpyAsync(o->par, par, (size_t)(d + d * d) * sizeof(double), cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    outer_propose_kernel<8><<<grid, 256, 0, st>>>(o->theta, o->par, o->par + d, scale, ind_prop, o->box, o->box + d, d, n,
+                                                 key ^ 0x9E3779B97F4A7C15ull, o->theta_f, o->prior_f, o->valid);
+    MCK(cudaGetLastError());
+    if (n_loc) {
+        const int rc = mbp_launch_propose(h, o->theta + (size_t)o->lo * d, o->theta_f + (size_t)o->lo * d, o->valid + o->lo, n_loc, obs_i, key);
+        if (rc) return rc;
+    }
+    int rc = comm_allgather_rows_device(o->comm, h->out, n, 2, o->llf_all, st);
+    if (rc) return rc;
+    outer_accept_kernel<<<grid, 256, 0, st>>>(o->llf_all, o->theta_f, o->prior_f, d, n, key ^ 0xD1B54A32D192ED03ull, o->theta, o->prior,
+                                              o->log_like, o->mtd_gx, o->acc);
+    MCK(cudaGetLastError());
+    if (n_loc) {
+        mbp_copy_flagged_kernel<<<(unsigned)n_loc, 128, 0, st>>>(h->store[h->cur], h->store[2], o->acc + o->lo, h->cap, h->dm.n_comp);
+        MCK(cudaGetLastError());
+    }
+    outer_count_kernel<<<1, kOuterThreads, 0, st>>>(o->acc, n, o->red);
+    outer_sum_kernel<<<1, kOuterThreads, 0, st>>>(o->mtd_gx, n, o->red + 1);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(o->h_red, o->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    out2[0] = o->h_red[0];
+    out2[1] = o->h_red[1] / (double)n;
+    return DPOMP_OK;
+}
+
+// theta [n_total][d] and w [n_total] of all particles
+int dpomp_mbp_outer_get(dpomp_mbp* h, double* out_theta, double* out_w) {
+    OUTER_OR_FAIL(h);
+    if (out_theta) MCK(cudaMemcpyAsync(out_theta, o->theta, (size_t)o->n_total * o->d * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_w) MCK(cudaMemcpyAsync(out_w, o->w, (size_t)o->n_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    return DPOMP_OK;
+}
+int dpomp_mbp_outer_end(dpomp_mbp* h) {
+    if (!h) return dpomp_set_error(DPOMP_ERR_ARG, "null handle");
+    MCK(cudaSetDevice(h->device));
+    mbp_outer_free(h);
     return DPOMP_OK;
 }
 

@@ -59,17 +59,33 @@ class Comm:
 
     def __del__(self):
         try:
-            if self._h:
-                from . import _capi
+            from . import _capi
 
-                _capi.lib().dpomp_comm_destroy(self._h)
-                self._h = None
+            for name in ("_h", "_h_single"):
+                h = getattr(self, name, None)
+                if h:
+                    _capi.lib().dpomp_comm_destroy(h)
+                    setattr(self, name, None)
         except Exception:
             pass
 
     @property
     def handle(self):
         """dpomp_comm handle (None when the exchanges run over torch.distributed / gloo or in a single process)."""
+        return self._h
+
+    def library_handle(self):
+        """dpomp_comm handle for entry points that always take one: the NCCL communicator under the nccl backend, a
+        world-size-1 communicator (no NCCL) in a single process, None under gloo."""
+        if self._h is None and self.dist is None:
+            import ctypes as C
+
+            from . import _capi
+
+            h = C.c_void_p()
+            _capi.check(_capi.lib().dpomp_comm_create(None, 0, 0, 1, -1, C.byref(h)))
+            self._h_single = h
+            return h
         return self._h
 
     # -- partition -------------------------------------------------------------------------------------------

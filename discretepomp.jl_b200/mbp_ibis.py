@@ -140,6 +140,41 @@ class MbpParticles:
             _capi.check(_capi.lib().dpomp_mbp_import(self._h, _capi.ptr(s), _capi.ptr(o), len(s), C.c_void_p(fixed.data_ptr()),
                                                      C.c_void_p(times.data_ptr()), C.c_void_p(types.data_ptr())))
 
+    # -- device-resident outer layer (dpomp_mbp_outer_*): theta, weights, priors of ALL particles on the device -------------
+    def outer_begin(self, comm_handle, theta: np.ndarray, prior_lo, prior_hi) -> None:
+        th = self._cols(theta)
+        lo, hi = _capi.as_f64(prior_lo), _capi.as_f64(prior_hi)
+        _capi.check(_capi.lib().dpomp_mbp_outer_begin(self._h, comm_handle, th.shape[0], _capi.ptr(th), _capi.ptr(lo), _capi.ptr(hi)))
+
+    def outer_iterate(self, obs_i: int, fresh: bool) -> np.ndarray:
+        out = np.empty(5)
+        _capi.check(_capi.lib().dpomp_mbp_outer_iterate(self._h, int(obs_i), 1 if fresh else 0, _capi.ptr(out)))
+        return out
+
+    def outer_moments(self):
+        mu = np.empty(self.n_params); cv = np.empty((self.n_params, self.n_params))
+        _capi.check(_capi.lib().dpomp_mbp_outer_moments(self._h, _capi.ptr(mu), _capi.ptr(cv)))
+        return mu, cv
+
+    def outer_resample(self, rs_type: int, u) -> float:
+        uu = _capi.as_f64(np.atleast_1d(u)); out = np.empty(2)
+        _capi.check(_capi.lib().dpomp_mbp_outer_resample(self._h, int(rs_type), _capi.ptr(uu), len(uu), _capi.ptr(out)))
+        return float(out[0])
+
+    def outer_sweep(self, mu, chol, scale: float, ind_prop: bool, obs_i: int):
+        m, l = _capi.as_f64(mu), _capi.as_f64(chol); out = np.empty(2)
+        _capi.check(_capi.lib().dpomp_mbp_outer_sweep(self._h, _capi.ptr(m), _capi.ptr(l), C.c_double(scale), 1 if ind_prop else 0,
+                                                      int(obs_i), _capi.ptr(out)))
+        return int(round(out[0])), float(out[1])
+
+    def outer_get(self, n_total: int):
+        th = np.empty((n_total, self.n_params)); w = np.empty(n_total)
+        _capi.check(_capi.lib().dpomp_mbp_outer_get(self._h, _capi.ptr(th), _capi.ptr(w)))
+        return np.ascontiguousarray(th.T), w
+
+    def outer_end(self) -> None:
+        _capi.check(_capi.lib().dpomp_mbp_outer_end(self._h))
+
     def final_conditions(self) -> np.ndarray:
         """(n, C) final states of all particles."""
         out = np.zeros((self.n, self.n_comp), dtype=np.int64)
@@ -156,10 +191,78 @@ class MbpParticles:
         return fc, times[: ln.value].copy(), types[: ln.value].copy(), ll
 
 
+def _run_mbp_ibis_device(model, theta, ess_rs_crit, n_props, ind_prop, alpha, rng, seed, comm, ptcls, rs_type, verbose):
+    """run_mbp_ibis with the outer layer resident on the device (dpomp_mbp_outer_*): the host keeps scalars only."""
+    d, outer_p = theta.shape
+    start_time = time.time_ns()
+    ess_crit = ess_rs_crit * outer_p
+    timers = {}
+
+    def tick(name: str, t0: float) -> float:
+        t1 = time.perf_counter()
+        timers[name] = timers.get(name, 0.0) + (t1 - t0)
+        return t1
+
+    call = 0
+
+    def next_key() -> int:
+        nonlocal call
+        call += 1
+        return splitmix64((seed & _M64) ^ splitmix64(0x4D42 + call))
+
+    t_ph = time.perf_counter()
+    ptcls.outer_begin(comm.library_handle(), theta, model.prior.lower, model.prior.upper)
+    t_ph = tick("begin", t_ph)
+    propd = ProposalDensity.identity(d)
+    tj = 0.2
+    k_log = np.zeros(2, dtype=np.int64)
+    bme = np.zeros(2)
+    for obs_i in range(1, len(model.obs_data) + 1):
+        ptcls.set_stream_key(next_key())
+        t_ph = time.perf_counter()
+        s0, s1, s2, s3, s4 = ptcls.outer_iterate(obs_i, fresh=(obs_i == 1))  # :176-185 on the device
+        t_ph = tick("iterate", t_ph)
+        if model.obs_data[obs_i - 1].obs_id > 0:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lml = np.log(s1 / s0)
+                ess = s2 * s2 / s3
+            bme[0] += lml
+            if ess < ess_crit:
+                mu, cv = ptcls.outer_moments()
+                propd = get_prop_density(cv, propd)
+                u = rng.random() if rs_type == 1 else rng.random(outer_p)
+                t_ph = time.perf_counter()
+                mean_gx = ptcls.outer_resample(rs_type, u)  # :194-201
+                t_ph = tick("resample_migrate", t_ph)
+                mlr = mean_gx * np.exp(lml)
+                mean_mtd = mean_gx
+                k_log[0] += outer_p * n_props
+                for _ in range(n_props):  # :203-219
+                    ptcls.set_stream_key(next_key())
+                    n_acc, mean_mtd = ptcls.outer_sweep(mu, propd.chol, 1.0 if ind_prop else tj, ind_prop, obs_i)
+                    k_log[1] += n_acc
+                    tj *= alpha ** n_acc * 0.999 ** (outer_p - n_acc)
+                tick("sweeps", t_ph)
+                bme[1] += np.log(mlr / mean_mtd)
+            else:
+                bme[1] += np.log(s4 / s2)  # :231, with the already updated w as written
+    mu, cv = ptcls.outer_moments()
+    theta_out, w = ptcls.outer_get(outer_p)
+    output = ImportanceSample(mu, cv, theta_out, w, time.time_ns() - start_time, -bme)
+    if verbose and comm.rank == 0:
+        ar = 100.0 * k_log[1] / k_log[0] if k_log[0] else float("nan")
+        print(f"- finished in {output.run_time / 1e9:.1f} seconds (AR := {ar:.3g}%)")
+    output.k_log = k_log
+    output.timers = timers
+    output.particles = ptcls
+    return output
+
+
 def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, n_props: int, ind_prop: bool,
                  alpha: float, msgs: bool = True, rng: Optional[np.random.Generator] = None, seed: int = 1,
                  comm: Optional[Comm] = None, max_traj: int = MAX_TRAJ, outer_rs: Callable = rs_systematic,
-                 particles_factory: Optional[Callable] = None, verbose: bool = True) -> ImportanceSample:
+                 particles_factory: Optional[Callable] = None, verbose: bool = True,
+                 device_outer: Optional[bool] = None) -> ImportanceSample:
     """run_mbp_ibis(model, theta, ess_rs_crit, n_props, ind_prop, alpha, msgs = true) (src/hmm_ibis.jl:140-244).
     `theta` is (n_theta, outer_p).  With `comm`, theta-particles (and their trajectories) are partitioned over the ranks;
     theta, weights and every host decision are replicated (same host RNG), trajectories migrate after the outer resample
@@ -179,6 +282,21 @@ def run_mbp_ibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float
     if particles_factory is not None and hasattr(ptcls, "reset"):
         ptcls.reset()  # a caller-provided (pre-allocated, possibly used) store starts from the initial condition
     ptcls.set_batch_offset(lo)
+    # Outer layer on the device (theta, weights, proposals, accept test as replicated kernels; the host keeps scalars) when
+    # the prior is a product of uniforms and the exchanges go through the C ABI; `device_outer=False` forces the host-driven
+    # loop below (same algorithm; host numpy draws instead of Philox streams for the proposals).
+    from .examples import UniformProduct
+    from .resample import rs_stratified as _rs_strat
+
+    can_device = (isinstance(model.prior, UniformProduct) and hasattr(ptcls, "outer_begin") and d <= 8
+                  and outer_rs in (rs_systematic, _rs_strat) and comm.library_handle() is not None)
+    if device_outer is None:
+        device_outer = can_device
+    if device_outer:
+        if not can_device:
+            raise ValueError("device_outer needs a UniformProduct prior, systematic / stratified outer resampling and the C-ABI communicator")
+        return _run_mbp_ibis_device(model, theta, ess_rs_crit, n_props, ind_prop, alpha, rng, seed, comm, ptcls,
+                                    2 if outer_rs is _rs_strat else 1, verbose)
 
     timers = {}  # seconds per phase on this rank
 

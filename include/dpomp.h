@@ -93,6 +93,7 @@ typedef struct dpomp_model_desc {
 
 typedef struct dpomp_model dpomp_model;
 typedef struct dpomp_pf dpomp_pf;
+typedef struct dpomp_comm dpomp_comm; /* multi-GPU communicator, see below */
 
 const char* dpomp_last_error(void);
 /* library/ABI version and the geometry of the deterministic scan tree (needed by the parity oracle) */
@@ -241,6 +242,32 @@ int dpomp_mbp_export(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offset
                      void* dev_times, void* dev_types);
 int dpomp_mbp_import(dpomp_mbp* mbp, const int64_t* slots, const int64_t* offsets, int32_t n, const void* dev_fixed,
                      const void* dev_times, const void* dev_types);
+/*
+ * Device-resident outer layer of run_mbp_ibis (src/hmm_ibis.jl:140-244).  theta, log prior, log-likelihood, weights and the
+ * marginal increments of ALL n_total theta-particles live on the device, replicated on every rank of `comm` (a world-size-1
+ * communicator for one GPU); the host keeps only scalars (lml, ESS, the proposal scale tj, mu / covariance for the Cholesky
+ * factor, the evidence).  The prior must be a product of uniforms (prior_lo / prior_hi), as generate_weak_prior
+ * (src/hmm_examples.jl:33-35) and the reference's tests use; other priors take the host-driven entry points above.
+ * Proposal and accept draws are Philox streams keyed by the GLOBAL particle id, so results do not depend on the rank count.
+ *   begin    theta_all is n_params x n_total column-major; every particle back to the initial condition, w = 1
+ *   iterate  iterate_particle! of the rank's block + all-gather + reweight (:176-185);
+ *            out5 = { sum w_old, sum w_old gx, sum w_new, sum w_new^2, sum w_new gx }
+ *   moments  compute_is_mu_covar! (src/cmn.jl:91-99)
+ *   resample rs_systematic / rs_stratified with the given rand() draws, gather, trajectory migration, w = 1 (:194-201);
+ *            out2[0] = mean(gx[nidx])
+ *   sweep    one mutation sweep over all particles (:203-219): theta_f = (ind_prop ? mu : theta) + scale * chol * z,
+ *            partial_model_based_proposal, accept test, accepted trajectories replace the current ones;
+ *            out2 = { accepted proposals, mean(mtd_gx) }
+ */
+int dpomp_mbp_outer_begin(dpomp_mbp* mbp, dpomp_comm* comm, int64_t n_total, const double* theta_all, const double* prior_lo,
+                          const double* prior_hi);
+int dpomp_mbp_outer_iterate(dpomp_mbp* mbp, int32_t obs_i, int32_t fresh, double* out5);
+int dpomp_mbp_outer_moments(dpomp_mbp* mbp, double* out_mu, double* out_cv);
+int dpomp_mbp_outer_resample(dpomp_mbp* mbp, int32_t rs_type, const double* u, int64_t n_u, double* out2);
+int dpomp_mbp_outer_sweep(dpomp_mbp* mbp, const double* mu, const double* chol, double scale, int32_t ind_prop, int32_t obs_i,
+                          double* out2);
+int dpomp_mbp_outer_get(dpomp_mbp* mbp, double* out_theta, double* out_w);
+int dpomp_mbp_outer_end(dpomp_mbp* mbp);
 /* current stride of the stores and the hard limit; dpomp_mbp_reserve widens the stride ahead of time (e.g. before importing
  * trajectories that grew elsewhere) */
 int dpomp_mbp_capacity(dpomp_mbp* mbp, int32_t* out_stride, int32_t* out_max_traj);
@@ -271,7 +298,6 @@ int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double*
  *   rank 0: dpomp_comm_unique_id -> host-side broadcast of the DPOMP_UNIQUE_ID_BYTES bytes -> every rank: dpomp_comm_create.
  * world == 1 communicators need no id and make every entry point below a local operation.
  */
-typedef struct dpomp_comm dpomp_comm;
 #define DPOMP_UNIQUE_ID_BYTES 128
 int dpomp_comm_unique_id(void* out_id, int32_t nbytes);
 int dpomp_comm_create(const void* id, int32_t nbytes, int32_t rank, int32_t world, int32_t device, dpomp_comm** out_comm);

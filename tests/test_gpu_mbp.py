@@ -344,3 +344,34 @@ def test_store_grows_on_demand_and_results_do_not_depend_on_the_stride(dp, mode)
     for u, v in zip(a[2] + a[3], b[2] + b[3]):
         for x, z in zip(u, v):
             assert np.array_equal(x, z)
+
+
+def test_device_resident_outer_layer_matches_the_host_driven_loop(dp):
+    """dpomp_mbp_outer_*: theta, weights, priors and the accept test on the device.  Without mutation sweeps (n_props = 0) both
+    drivers consume the same draws, so the resampled theta-particles are identical and the evidence agrees to rounding (the
+    reductions associate differently); with sweeps the proposals come from Philox streams instead of numpy, so the two are
+    compared by a z-test over replicates."""
+    model, y, hmm, theta = _setup(dp)
+    model.prior = dp.UniformProduct([0, 0], [0.01, 0.5])
+    hmm = dp.get_private_model(model, y)
+    th0 = model.prior.rand(3001, np.random.default_rng(2))
+    a = dp.run_mbp_ibis(hmm, th0, 0.5, 0, False, 1.002, rng=np.random.default_rng(3), seed=4, verbose=False, device_outer=True)
+    b = dp.run_mbp_ibis(hmm, th0, 0.5, 0, False, 1.002, rng=np.random.default_rng(3), seed=4, verbose=False, device_outer=False)
+    assert np.array_equal(a.theta, b.theta) and np.allclose(a.weight, b.weight, rtol=1e-12)
+    assert np.allclose(a.bme, b.bme, rtol=1e-11) and np.allclose(a.mu, b.mu, rtol=1e-11) and np.allclose(a.cv, b.cv, rtol=1e-9)
+    # determinism of the device path
+    a2 = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, rng=np.random.default_rng(3), seed=4, verbose=False, device_outer=True)
+    a3 = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, rng=np.random.default_rng(3), seed=4, verbose=False, device_outer=True)
+    assert np.array_equal(a2.theta, a3.theta) and np.array_equal(a2.bme, a3.bme) and a2.k_log[1] > 0
+    reps = 6
+    dev, host = [], []
+    for s in range(reps):
+        th = model.prior.rand(4000, np.random.default_rng(700 + s))
+        r1 = dp.run_mbp_ibis(hmm, th, 0.5, 3, False, 1.002, seed=720 + s, verbose=False, device_outer=True)
+        r2 = dp.run_mbp_ibis(hmm, th, 0.5, 3, False, 1.002, seed=740 + s, verbose=False, device_outer=False)
+        dev.append(np.concatenate([r1.bme, r1.mu, [r1.k_log[1] / r1.k_log[0]]]))
+        host.append(np.concatenate([r2.bme, r2.mu, [r2.k_log[1] / r2.k_log[0]]]))
+    dev, host = np.array(dev), np.array(host)
+    for j in range(dev.shape[1]):
+        z = (dev[:, j].mean() - host[:, j].mean()) / np.sqrt(dev[:, j].var(ddof=1) / reps + host[:, j].var(ddof=1) / reps + 1e-300)
+        assert abs(z) < 4.5, (j, dev[:, j], host[:, j])
