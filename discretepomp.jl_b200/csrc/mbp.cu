@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128) mbp_pack_kernel(MbpStore st, const int64_
         if (threadIdx.x < n_comp) fx[1 + threadIdx.x] = st.fc[(size_t)p * n_comp + threadIdx.x];
         if (threadIdx.x == 32) { double* l = reinterpret_cast<double*>(fx + 10); l[0] = st.ll[2 * p]; l[1] = st.ll[2 * p + 1]; }
     } else {
-        const int len = fx[0];
+        const int len = min(fx[0], cap);  // never past the stride: importers widen it first (dpomp_mbp_reserve / resample_migrate)
         for (int i = threadIdx.x; i < len; i += blockDim.x) { et[i] = times[off + i]; ey[i] = types[off + i]; }
         if (threadIdx.x == 0) st.len[p] = len;
         if (threadIdx.x < n_comp) st.fc[(size_t)p * n_comp + threadIdx.x] = fx[1 + threadIdx.x];

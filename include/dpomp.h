@@ -296,7 +296,8 @@ int dpomp_resample_indices(int32_t rs_type, int32_t on_cumulative, const double*
  * whose data it moves.  The reference is single-process; these entry points are what a sharded host (Julia with
  * Distributed / MPI.jl, or the Python host of this repository) calls around run_pibis / run_mbp_ibis:
  *   rank 0: dpomp_comm_unique_id -> host-side broadcast of the DPOMP_UNIQUE_ID_BYTES bytes -> every rank: dpomp_comm_create.
- * world == 1 communicators need no id and make every entry point below a local operation.
+ * world == 1 communicators need no id and make every entry point below a local operation.  Like the other handles a
+ * communicator is not thread-safe, and its staging buffers are shared by the calls that take it: one call at a time.
  */
 #define DPOMP_UNIQUE_ID_BYTES 128
 int dpomp_comm_unique_id(void* out_id, int32_t nbytes);

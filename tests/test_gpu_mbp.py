@@ -182,7 +182,8 @@ def _mbp_worker(rank, world, port, out_path):
     y = dp.get_observations(os.path.join(ROOT, "tests", "golden", "pooley.csv"))
     hmm = dp.get_private_model(model, y)
     th0 = model.prior.rand(501, np.random.default_rng(5))
-    res = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, rng=np.random.default_rng(6), seed=7, comm=comm, max_traj=4096, verbose=False)
+    res = dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, rng=np.random.default_rng(6), seed=7, comm=comm, max_traj=4096, verbose=False,
+                          device_outer=False)  # gloo exchanges = the host-driven loop on both sides; the device-resident loop over NCCL: test_gpu_multi.py
     if rank == 0:
         np.savez(out_path, bme=res.bme, mu=res.mu, theta=res.theta, w=res.weight)
     if world > 1:
