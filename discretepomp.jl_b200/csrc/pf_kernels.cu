@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x % a.ntiles;
-    const int b = blockIdx.x / a.ntiles;
+    const int b = a.order ? (int)a.order[blockIdx.x / a.ntiles] : (int)(blockIdx.x / a.ntiles);
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
 
@@ -190,6 +190,25 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
     const long long row = perm_pos(a.perm, i);
     for (int c = 0; c < a.n_comp; ++c) dst_b[(size_t)c * a.n_pad + row] = src_b[(size_t)c * a.n_pad + res];
     if (a.anc) a.anc[(size_t)b * a.n_pad + row] = (int32_t)res;
+}
+
+// Heaviest-first launch order for launches of several waves of CTAs: filters differ in cost (their theta differs), CTAs are
+// dispatched in block order, so the last wave of an unordered launch can end with a few heavy filters running alone.  The
+// cost estimate is the event count of the same filter in the previous launch.  rank by counting: n <= a few thousand.
+__global__ void __launch_bounds__(256) cost_order_kernel(const unsigned long long* cost, int n, uint32_t* order) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const unsigned long long cb = cost[b];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        const unsigned long long cj = cost[j];
+        rank += (cj > cb) || (cj == cb && j < b);
+    }
+    order[rank] = (uint32_t)b;
+}
+cudaError_t launch_cost_order(const unsigned long long* cost_dev, int n, uint32_t* order_dev, cudaStream_t stream) {
+    cost_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cost_dev, n, order_dev);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream) {

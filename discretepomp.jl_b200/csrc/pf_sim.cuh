@@ -158,7 +158,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         logical = logical_s;
     }
     const int tile = logical % a.ntiles;
-    const int b = logical / a.ntiles;
+    const int b = a.order ? (int)a.order[logical / a.ntiles] : (int)(logical / a.ntiles);  // heaviest filters first (multi-wave launches)
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double* th = a.theta + (size_t)b * m.n_params;
@@ -570,6 +570,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) evf += __shfl_xor_sync(0xffffffffu, evf, d);
     if (tid == 0) {
+        a.filt_cost[b] = evf;
         if (evf) atomicAdd(a.ev_count, evf);
         a.filt_s[b] = l2.big_s;
         a.filt_m[b] = l2.big_m;
