@@ -152,7 +152,10 @@ def lib() -> C.CDLL:
                 "There is no CPU fallback for the particle-filter path."
             )
         handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        lenient = os.environ.get("DPOMP_LIB_LENIENT") == "1"  # A/B of OLDER builds only (scripts/ab_commits.sh)
         for name, (res, args) in _SIGS.items():
+            if lenient and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args

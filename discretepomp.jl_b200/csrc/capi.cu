@@ -99,7 +99,7 @@ static void pf_free(dpomp_pf* pf) {
     cudaSetDevice(pf->device);
     cudaFree(pf->pop[0]); cudaFree(pf->pop[1]); cudaFree(pf->logw); cudaFree(pf->wtile); cudaFree(pf->cw); cudaFree(pf->anc);
     cudaFree(pf->theta_dev); cudaFree(pf->tile_m); cudaFree(pf->tile_s); cudaFree(pf->tile_f); cudaFree(pf->tile_off);
-    cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter); cudaFree(pf->tile_ev); cudaFree(pf->grp_ev); cudaFree(pf->filt_cost); cudaFree(pf->order_dev);
+    cudaFree(pf->grp_m); cudaFree(pf->grp_s); cudaFree(pf->grp_f); cudaFree(pf->grp_off); cudaFree(pf->grp_counter); cudaFree(pf->grp_ev);
     cudaFree(pf->filt_m); cudaFree(pf->filt_s); cudaFree(pf->ll_acc); cudaFree(pf->tile_counter); cudaFree(pf->counters);
     cudaFree(pf->obs_time_dev); cudaFree(pf->obs_ysum_dev); cudaFree(pf->slots_dev); cudaFree(pf->filter_ids_dev); cudaFree(pf->work_counter); cudaFree(pf->filt_gen);
     cudaFree(pf->rows_done); cudaFree(pf->gen_flags); cudaFree(pf->obs_haslik_dev);
@@ -131,7 +131,6 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     if (!pf) return fail(DPOMP_ERR_ARG, "out of host memory");
     pf->model = model;
     pf->device = device;
-    pf->lpt_enabled = getenv("DPOMP_NO_LPT") == nullptr;
     pf->n = n_particles;
     pf->n_batch = n_batch;
     pf->rs_type = rs_type;
@@ -171,9 +170,6 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     ALLOC(pf->grp_f, B * NG * sizeof(double));
     ALLOC(pf->grp_off, B * NG * sizeof(double));
     ALLOC(pf->grp_counter, B * NG * sizeof(unsigned int));
-    ALLOC(pf->filt_cost, B * sizeof(unsigned long long));
-    ALLOC(pf->order_dev, B * sizeof(uint32_t));
-    ALLOC(pf->tile_ev, B * NT * sizeof(unsigned long long));
     ALLOC(pf->grp_ev, B * NG * sizeof(unsigned long long));
     ALLOC(pf->filt_m, B * sizeof(double));
     ALLOC(pf->filt_s, B * sizeof(double));
@@ -329,6 +325,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
     }
     CK(cudaMemsetAsync(pf->ll_acc, 0, (size_t)nb * sizeof(double), st));
     CK(cudaMemsetAsync(pf->counters, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(pf->grp_ev, 0, (size_t)nb * pf->ngroups * sizeof(unsigned long long), st));
     int launches = 0;
     pf->kev_kind.clear();
     bool fused_ok = false;
@@ -369,7 +366,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         a.filt_m = pf->filt_m; a.filt_s = pf->filt_s; a.ll_acc = pf->ll_acc;
         a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
         a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups; a.tile_counter = pf->tile_counter;
-        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.tile_ev = pf->tile_ev; a.grp_ev = pf->grp_ev; a.filt_cost = pf->filt_cost;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.grp_ev = pf->grp_ev;
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = ymin - 1; a.t_last = ymax - 1; a.n_obs_total = pf->n_obs; a.obs_haslik = pf->obs_haslik_dev;
         a.fresh = (ymin == 1); a.has_lik = 0; a.do_resample = 0;
@@ -397,21 +394,6 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
             return fail(DPOMP_ERR_CUDA, std::string("persistent launch: ") + cudaGetErrorString(le));
         }
     }
-    // heaviest-first launch order when the launches have several waves of CTAs and the previous call measured the cost of
-    // exactly these filters (results do not depend on it: it only permutes which CTA works on which filter)
-    const uint32_t* order = nullptr;
-    if (!persist_ok && pf->lpt_enabled && pf->cost_valid_nb == nb && nb >= 32) {
-        if (pf->sim_capacity < 0) {
-            int dev = 0, sms = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            pf->sim_capacity = 7 * sms;  // resident CTAs of the simulate kernel (launch bounds: 7 per SM)
-        }
-        if ((long long)nb * pf->ntiles > 2ll * pf->sim_capacity) {
-            CK(launch_cost_order(pf->filt_cost, nb, pf->order_dev, st));
-            order = pf->order_dev;
-        }
-    }
     for (int oi = ymin; oi <= ymax && !persist_ok; ++oi) {
         const int t = oi - 1;
         const int has_lik = mh.obs_id[t] > 0;
@@ -429,12 +411,11 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         a.grp_m = pf->grp_m; a.grp_s = pf->grp_s; a.grp_f = pf->grp_f; a.grp_off = pf->grp_off;
         a.grp_counter = pf->grp_counter; a.ngroups = pf->ngroups;
         a.tile_counter = pf->tile_counter;
-        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.tile_ev = pf->tile_ev; a.grp_ev = pf->grp_ev; a.filt_cost = pf->filt_cost;
+        a.ev_count = pf->counters; a.ovf_count = pf->counters + 1; a.grp_ev = pf->grp_ev;
         a.n = pf->n; a.n_pad = pf->n_pad; a.ntiles = pf->ntiles; a.n_filters = nb; a.n_comp = pf->n_comp;
         a.t = t; a.fresh = (oi == 1); a.has_lik = has_lik;
         a.key = key; a.filter0 = (uint32_t)pf->batch_offset; a.max_events = pf->max_events;
         a.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
-        a.order = order;
         // one fused launch (simulate + resample) when every tile of a filter can be resident at once
         const bool fused = do_rs && fused_ok;
         if (fused) {
@@ -469,7 +450,6 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
             r.t = t; r.rs_type = pf->rs_type; r.key = key; r.filter0 = (uint32_t)pf->batch_offset;
             r.perm = make_chunk_perm(pf->scatter_mode, pf->n, pf->ntiles);
             r.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
-            r.order = order;
             if (pf->kernel_timing) CK(kernel_event(pf, 1, st));
             CK(launch_resample(pf->items, r, st));
             if (pf->kernel_timing) CK(kernel_event(pf, -1, st));
@@ -483,10 +463,10 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
     } else if (out_mode == 0) {
         CK(cudaMemcpyAsync(pf->h_ll, pf->ll_acc, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    CK(launch_sum_events(pf->grp_ev, (long long)nb * pf->ngroups, pf->counters, st));
     CK(cudaMemcpyAsync(pf->h_cnt, pf->counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(pf->ev1, st));
     pf->last_launches = launches;
-    pf->cost_valid_nb = nb;  // filt_cost now holds the event counts of the last launch for these nb filters
     return DPOMP_OK;
 }
 

@@ -54,10 +54,7 @@ struct SimLaunch {
     double* filt_s;          // [B]
     double* ll_acc;          // [B]
     unsigned int* tile_counter;      // [B]
-    const uint32_t* order;           // optional launch order: CTAs [k * ntiles, (k + 1) * ntiles) work on filter order[k] (heaviest first)
-    unsigned long long* filt_cost;   // [B] events of the filter in this launch: the cost estimate behind `order`
-    unsigned long long* tile_ev;     // [B][ntiles] Gillespie events simulated by the tile (summed along the combine tree)
-    unsigned long long* grp_ev;      // [B][ngroups]
+    unsigned long long* grp_ev;      // [B][ngroups] Gillespie events of the call, one counter per (filter, group of tiles)
     unsigned long long* ev_count;    // [1]
     unsigned long long* ovf_count;   // [1]
     long long n;             // particles per filter
@@ -110,7 +107,6 @@ struct ResampleLaunch {
     uint64_t key;
     uint32_t filter0;
     const uint32_t* filter_ids;
-    const uint32_t* order;   // optional launch order (see SimLaunch)
 };
 
 struct ModelHost {
@@ -152,12 +148,7 @@ struct dpomp_pf {
     double *filt_m = nullptr, *filt_s = nullptr, *ll_acc = nullptr;
     double *grp_m = nullptr, *grp_s = nullptr, *grp_f = nullptr, *grp_off = nullptr;
     unsigned int* grp_counter = nullptr;
-    unsigned long long *tile_ev = nullptr, *grp_ev = nullptr;
-    unsigned long long* filt_cost = nullptr;     // [n_batch] events per filter of the last launch
-    uint32_t* order_dev = nullptr;               // [n_batch] heaviest-first launch order of multi-wave launches
-    bool lpt_enabled = true;                     // DPOMP_NO_LPT=1 in the environment switches the launch order off (A/B)
-    int cost_valid_nb = 0;                       // filt_cost describes the first cost_valid_nb filters (0 = nothing yet)
-    int sim_capacity = -1;                       // co-resident CTAs of the plain simulate kernel (lazy)
+    unsigned long long* grp_ev = nullptr;        // [n_batch][ngroups] event counters of the current call
     int ngroups = 0;
     unsigned int* tile_counter = nullptr;
     unsigned long long* counters = nullptr;  // [0] events of the last call, [1] sticky overflow count
@@ -232,8 +223,7 @@ int sim_persist_capacity(const ModelHost& m, int sim_precision, int items);
 int sim_fused_capacity(const ModelHost& m, int sim_precision, int items);
 int builtin_model_id(const dpomp_model_desc& d);  // 0 = generic rate table, > 0 = hand-specialised predefined model
 cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t stream);
-// order[rank of filter b by (cost descending, b ascending)] = b for the first n filters
-cudaError_t launch_cost_order(const unsigned long long* cost_dev, int n, uint32_t* order_dev, cudaStream_t stream);
+cudaError_t launch_sum_events(const unsigned long long* grp_ev_dev, long long n, unsigned long long* out_dev, cudaStream_t stream);
 cudaError_t launch_gather_filters(int32_t* dst, const int32_t* src, const int64_t* dst_slots_dev,
                                   const int64_t* src_slots_dev, int n, long long filter_stride_words, cudaStream_t stream);
 cudaError_t launch_pack_filters(int32_t* dst_packed, const int32_t* pop, const int64_t* slots_dev, int n,

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x % a.ntiles;
-    const int b = a.order ? (int)a.order[blockIdx.x / a.ntiles] : (int)(blockIdx.x / a.ntiles);
+    const int b = blockIdx.x / a.ntiles;
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
 
@@ -192,22 +192,21 @@ __global__ void __launch_bounds__(kBlockThreads) pf_multinomial_gather_kernel(co
     if (a.anc) a.anc[(size_t)b * a.n_pad + row] = (int32_t)res;
 }
 
-// Heaviest-first launch order for launches of several waves of CTAs: filters differ in cost (their theta differs), CTAs are
-// dispatched in block order, so the last wave of an unordered launch can end with a few heavy filters running alone.  The
-// cost estimate is the event count of the same filter in the previous launch.  rank by counting: n <= a few thousand.
-__global__ void __launch_bounds__(256) cost_order_kernel(const unsigned long long* cost, int n, uint32_t* order) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    const unsigned long long cb = cost[b];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-        const unsigned long long cj = cost[j];
-        rank += (cj > cb) || (cj == cb && j < b);
+// sum of the per-(filter, group) event counters of a call into the call's counter
+__global__ void __launch_bounds__(256) sum_events_kernel(const unsigned long long* grp_ev, long long n, unsigned long long* out) {
+    __shared__ unsigned long long red[256];
+    unsigned long long v = 0;
+    for (long long i = threadIdx.x; i < n; i += 256) v += grp_ev[i];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
     }
-    order[rank] = (uint32_t)b;
+    if (threadIdx.x == 0) *out = red[0];
 }
-cudaError_t launch_cost_order(const unsigned long long* cost_dev, int n, uint32_t* order_dev, cudaStream_t stream) {
-    cost_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cost_dev, n, order_dev);
+cudaError_t launch_sum_events(const unsigned long long* grp_ev_dev, long long n, unsigned long long* out_dev, cudaStream_t stream) {
+    sum_events_kernel<<<1, 256, 0, stream>>>(grp_ev_dev, n, out_dev);
     return cudaGetLastError();
 }
 

@@ -147,7 +147,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     __shared__ unsigned warp_min_s[kBlockThreads / 32];
     __shared__ double wtab_s[kBlockThreads];  // exp(logw(d_min + j) - m_b), j = 0..kBlockThreads-1
     __shared__ uint32_t stream_s[3];
-    __shared__ unsigned long long warp_ev_s[kBlockThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int logical = blockIdx.x;
@@ -158,7 +157,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         logical = logical_s;
     }
     const int tile = logical % a.ntiles;
-    const int b = a.order ? (int)a.order[logical / a.ntiles] : (int)(logical / a.ntiles);  // heaviest filters first (multi-wave launches)
+    const int b = logical / a.ntiles;
     const long long base_n = (long long)tile * TILE;
     const uint32_t gfilter = a.filter_ids ? a.filter_ids[b] : a.filter0 + (uint32_t)b;
     const double* th = a.theta + (size_t)b * m.n_params;
@@ -423,14 +422,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
             ev_local += __shfl_xor_sync(0xffffffffu, ev_local, d);
             ovf_local += __shfl_xor_sync(0xffffffffu, ovf_local, d);
         }
-        // the event count rides on the combine tree (one RED per filter and launch instead of one per warp: 4096 REDs on
-        // ONE address per C2 launch cost 0.9 us per observation); hitting the event cap is rare and keeps its own RED
-#ifdef DPOMP_EVCOUNT_RED  // A/B only: the round-1 form, one RED per warp
-        if (lane == 0) warp_ev_s[warp] = 0ull;
-        if (lane == 1 && ev_local) atomicAdd(a.ev_count, ev_local);
-#else
-        if (lane == 0) warp_ev_s[warp] = ev_local;  // read by thread 0 after the barriers of the weight pass below
-#endif
+        // event statistics: one RED per warp, spread over one counter per (filter, group of tiles) -- round 1 put all 4096 REDs
+        // of a C2 launch on ONE address (0.8 us per observation), summing along the combine tree instead lengthened the serial
+        // tail by more than that; the counters are summed by a tiny kernel at the end of the call (capi.cu).  Issued by lane 1:
+        // thread 0 takes the tickets below, and its __threadfence would wait for its own RED
+        if (lane == 1 && ev_local) atomicAdd(a.grp_ev + (size_t)b * a.ngroups + tile / kGroupTiles, ev_local);
         if (lane == 1 && ovf_local) atomicAdd(a.ovf_count, ovf_local);
 
         if (int_obs) {
@@ -502,10 +498,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     if (tid == 0) {
         a.tile_m[(size_t)b * a.ntiles + tile] = m_b;
         a.tile_s[(size_t)b * a.ntiles + tile] = s_b;
-        unsigned long long ev_tile = 0;
-#pragma unroll
-        for (int w = 0; w < kBlockThreads / 32; ++w) ev_tile += warp_ev_s[w];
-        a.tile_ev[(size_t)b * a.ntiles + tile] = ev_tile;
         __threadfence();
         const unsigned int ticket = atomicAdd(&a.grp_counter[(size_t)b * a.ngroups + grp], 1u);
         grp_last = (ticket == (unsigned int)(grp_tiles - 1));
@@ -531,9 +523,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         const bool have = i < a.ntiles;
         const double mb = have ? __ldcg(a.tile_m + (size_t)b * a.ntiles + i) : -INFINITY;
         const double sb = have ? __ldcg(a.tile_s + (size_t)b * a.ntiles + i) : 0.0;
-        unsigned long long evg = have ? __ldcg(a.tile_ev + (size_t)b * a.ntiles + i) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) evg += __shfl_xor_sync(0xffffffffu, evg, d);
         double mg = mb;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, d));
@@ -553,7 +542,6 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         if (tid == 31) {
             a.grp_m[(size_t)b * a.ngroups + grp] = mg;
             a.grp_s[(size_t)b * a.ngroups + grp] = inc;
-            a.grp_ev[(size_t)b * a.ngroups + grp] = evg;
             a.grp_counter[(size_t)b * a.ngroups + grp] = 0u;
             __threadfence();
             const unsigned int ticket = atomicAdd(&a.tile_counter[b], 1u);
@@ -565,13 +553,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     // level 2: groups of the filter -> M, F_g = exp(m_g - M), O_g, S and the log-likelihood increment
     const Level2 l2 = combine_level2(a.grp_m + (size_t)b * a.ngroups, a.grp_s + (size_t)b * a.ngroups, a.ngroups,
                                      a.grp_f + (size_t)b * a.ngroups, a.grp_off + (size_t)b * a.ngroups);
-    unsigned long long evf = 0;
-    for (int g = tid; g < a.ngroups; g += 32) evf += __ldcg(a.grp_ev + (size_t)b * a.ngroups + g);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) evf += __shfl_xor_sync(0xffffffffu, evf, d);
     if (tid == 0) {
-        a.filt_cost[b] = evf;
-        if (evf) atomicAdd(a.ev_count, evf);
         a.filt_s[b] = l2.big_s;
         a.filt_m[b] = l2.big_m;
         // log(cum_weight[end] / N) (:60) as log-sum-exp; one add per kernel and filter, so the RED is deterministic

@@ -207,12 +207,17 @@ class FilterBank:
 def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, ind_prop: bool, alpha: float, np_: int,
               n_props: int = 1, rng: Optional[np.random.Generator] = None, seed: int = 1, comm: Optional[Comm] = None,
               pf_factory: Optional[Callable] = None, outer_rs: Callable = rs_systematic, verbose: bool = True,
-              hastings_correction: bool = False) -> ImportanceSample:
+              hastings_correction: bool = False, deal_offspring: bool = True) -> ImportanceSample:
     """run_pibis(model, theta, ess_rs_crit, ind_prop, alpha, np; n_props = 1) (src/hmm_ibis.jl:12-135).
     `theta` is (n_theta, outer_p); `np_` is the number of state particles per filter.
     `hastings_correction` (not in the reference, default off): with independent proposals the reference accepts with
     exp(aw_f - aw) (src/hmm_ibis.jl:104), which leaves out the proposal-density ratio q(theta) / q(theta_f) and biases the
-    evidence; True adds it."""
+    evidence; True adds it.
+    `deal_offspring` (default on): the resampled theta-particles are dealt over the slots with stride 64 instead of being
+    stored in ancestor order (`pop2[p] .= pop[nidx[p]]`, :71-79), so that the copies of a heavy ancestor -- filters of equal
+    cost -- spread over the ranks of a sharded run instead of landing on one.  The order of theta-particles is arbitrary
+    (nothing in run_pibis depends on it but the next systematic resampling, for which any order is valid); the permutation does
+    not depend on the number of ranks, so 1, 2, 4 and 8 ranks still agree bit for bit."""
     comm = comm or Comm(None)
     rng = rng or np.random.default_rng(seed)
     theta = np.array(theta, dtype=np.float64, order="C")
@@ -229,6 +234,7 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
     propd = ProposalDensity.identity(theta.shape[0])
     tj = 0.2
     mu, cv = compute_is_mu_covar(theta, w)
+    deal = np.argsort(np.arange(outer_p) % 64, kind="stable")  # slot p takes offspring deal[p]: consecutive offspring 1/64 of the slots apart
     obs_min = 1
     for obs_i in range(1, len(model.obs_data) + 1):
         if model.obs_data[obs_i - 1].obs_id > 0:
@@ -244,6 +250,8 @@ def run_pibis(model: HiddenMarkovModel, theta: np.ndarray, ess_rs_crit: float, i
                 mu, cv = compute_is_mu_covar(theta, w)
                 propd = get_prop_density(cv, propd)
                 nidx = outer_rs(w.copy(), rng)  # 1-based
+                if deal_offspring:
+                    nidx = nidx[deal]
                 theta = theta[:, nidx - 1]
                 aw = aw[nidx - 1]
                 bank.resample(nidx)

@@ -506,29 +506,3 @@ def test_small_filter_latency_kernel_equals_throughput_kernel(dp):
     assert np.array_equal(ll_small, ll_big[ids])
     for j, b in enumerate(ids):
         assert np.array_equal(small.get_pop(j + 1), big.get_pop(int(b) + 1))
-
-
-def test_heaviest_first_launch_order_does_not_change_results(dp):
-    """Launches of several waves of CTAs run the filters heaviest first (cost = event count of the same filter in the previous
-    launch, csrc/pf_kernels.cu cost_order_kernel): it only permutes which CTA works on which filter, so log-likelihoods and
-    populations are bit-identical to the unordered launches (DPOMP_NO_LPT=1)."""
-    import os
-    model, y, hmm, theta = load_case(dp, "lotka_c4")
-    dm = dp.device_model(hmm)
-    nb, n = 600, 4096  # 2400 CTAs > 2 x (7 x 148)
-    thetas = theta[:, None] * np.random.default_rng(3).uniform(0.8, 1.25, (3, nb))
-    res = []
-    for no_lpt in (False, True):
-        if no_lpt:
-            os.environ["DPOMP_NO_LPT"] = "1"
-        try:
-            pf = dp.ParticleFilter(dm, n, nb, 1, seed=5)
-        finally:
-            os.environ.pop("DPOMP_NO_LPT", None)
-        pf.set_stream_key(31)
-        a = pf.partial(thetas, 1, 1)
-        pf.set_stream_key(32)
-        b = pf.partial(thetas, 2, 4)  # the cost of the first call orders these launches
-        res.append((a, b, pf.get_pop(1), pf.get_pop(nb), pf.get_pop(nb // 2)))
-    for u, v in zip(res[0], res[1]):
-        assert np.array_equal(u, v)
