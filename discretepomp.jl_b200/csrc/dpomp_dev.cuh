@@ -40,8 +40,14 @@ __device__ __forceinline__ unsigned long long dpomp_gtime() {
     do {                                                                                                    \
         if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS && blockIdx.x < 4096) g_dpomp_phase[K][blockIdx.x][P] = dpomp_gtime(); \
     } while (0)
+// slot P of the simulate kernel of the FOLLOWING observation (the resample -> simulate boundary of the timeline)
+#define DPOMP_STAMP_NEXT(K, P)                                                                              \
+    do {                                                                                                    \
+        if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS + 1 && blockIdx.x < 4096) g_dpomp_phase[K][blockIdx.x][P] = dpomp_gtime(); \
+    } while (0)
 #else
 #define DPOMP_STAMP(K, P) do { } while (0)
+#define DPOMP_STAMP_NEXT(K, P) do { } while (0)
 #endif
 // Debug build only (-DDPOMP_BOUNDS_CHECK, lib/variants/libdpomp_bounds.so, tests/test_gpu_bounds.py): every shared / global
 // index of the resample phase, the warp work queue and the MBP windows is checked against its buffer and traps (the pool's

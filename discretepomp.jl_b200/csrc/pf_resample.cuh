@@ -74,11 +74,40 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     for (int k = 0; k < ITEMS; ++k) er[k] = (int)resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
 #else
     unsigned todo = 0;  // items whose closed-form guess needs the exact correction
+#ifndef DPOMP_NO_FUSED_GUESS
+    if constexpr (RS == DPOMP_RS_SYSTEMATIC) {
+        // Systematic: the count of an item is floor(t) + 1 with t = cw_q N / S - r unless t lies within 2^-12 of an integer
+        // (resample_ecount_guess).  For that decision t may come from ONE fused multiply-add per item,
+        //   t ~ K0 + K1 * incl_q,  K1 = F_g f_{b|g} N / S,  K0 = (O_g + F_g o_{b|g}) N / S - r:
+        // K0 and K1 carry a few ulp of relative error, so |t_fma - t| < 2 N 2^-50 <= 2^-18 index units for N <= 2^31, far
+        // inside the 2^-12 margin; the exactly rounded cw_q of the reference's expression order (tile_cw) is only formed for
+        // the items that fall inside the margin, by the correction path below (the same code as before: same counts).
+        if (ctx.s > 0.0) {
+            const double k1 = g_f * t_f * ctx.inv_s * ctx.dn;
+            const double k0 = ((g_off + g_f * t_off) * ctx.inv_s - ctx.r1_over_n) * ctx.dn;
+            const double t_hi = ctx.dn - 1.0;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        bool exact;
-        er[k] = resample_ecount_guess<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]), exact);
-        if (!exact) todo |= 1u << k;
+            for (int k = 0; k < ITEMS; ++k) {
+                const double t = fma(incl[k], k1, k0);
+                const double fl = floor(t);
+                const double frac = t - fl;
+                const bool exact = frac > 0x1.0p-12 && frac < 1.0 - 0x1.0p-12 && t > 0.0 && t < t_hi;
+                er[k] = (int)fl + 1;  // (garbage when !exact: replaced below)
+                if (!exact) todo |= 1u << k;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) er[k] = (int)ctx.n;
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            bool exact;
+            er[k] = resample_ecount_guess<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]), exact);
+            if (!exact) todo |= 1u << k;
+        }
     }
     // one copy of the correction code (not ITEMS inlined ones: instruction-cache footprint); the arrays stay in registers
     // (select chains instead of dynamic indexing).  Systematic: rare (|t - round(t)| < 2^-12); stratified: every item.
@@ -93,6 +122,11 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
             inc_k = (k == j) ? incl[j] : inc_k;
             e_k = (k == j) ? er[j] : e_k;
         }
+#ifndef DPOMP_NO_FUSED_GUESS
+        if constexpr (RS == DPOMP_RS_SYSTEMATIC) {  // the fused guess of this item was not usable: the full exact count
+            e_k = (int)resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, inc_k));
+        } else
+#endif
         e_k = resample_ecount_correct<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, inc_k), e_k);
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) er[j] = (k == j) ? e_k : er[j];
@@ -123,7 +157,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     if (threadIdx.x == 0 && a.t == DPOMP_PHASE_OBS && blockIdx.x < 4096) g_dpomp_phase[1][blockIdx.x][3] = dpomp_gtime();
 #endif
 
-    const long long lo = lohi_s[0], hi = lohi_s[1];
+    const int lo = (int)lohi_s[0], hi = (int)lohi_s[1];  // offspring counts of a filter: n_particles < 2^31
     DPOMP_CHECK_IDX(lo, a.n + 1);
     DPOMP_CHECK_IDX(hi, a.n + 1);
     DPOMP_CHECK_IDX(hi - lo, a.n + 1);
@@ -133,10 +167,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
         if (w < warp) wprev_raw = max(wprev_raw, warp_max_s[w]);
     prev_raw = max(prev_raw, wprev_raw);
     // clamp is monotone, so clamp(running max) == running max of the clamped counts; offsets are relative to lo
-    auto clamp_off = [&](int v) -> int {
-        const long long c = v < lo ? lo : (v > hi ? hi : (long long)v);
-        return (int)(c - lo);
-    };
+    auto clamp_off = [&](int v) -> int { return min(max(v, lo), hi) - lo; };
     int emax[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) emax[k] = clamp_off(max(er[k], prev_raw));
@@ -148,7 +179,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     // Heavy tile (weight collapse: this tile feeds far more offspring than it has ancestors): per-warp windows would leave
     // the warp that owns the heavy ancestors looping alone, so the whole CTA walks the tile's offspring range instead and
     // finds each ancestor by binary search over the running maxima (block-uniform decision: lo and hi are shared).
-    if (hi - lo > (long long)kHeavyFactor * TILE) {
+    if ((long long)hi - lo > (long long)kHeavyFactor * TILE) {
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) am_all[tid * ITEMS + k] = emax[k];
         __syncthreads();

@@ -188,6 +188,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const unsigned int gen_t = a.gen + (unsigned int)(t - a.t);
 
     DPOMP_STAMP(0, 0);
+    DPOMP_STAMP_NEXT(0, 7);
     if (tid == 0) {  // independent of the predecessor kernel: overlaps its tail
         const SimStream s0 = sim_stream_init(a.key, gfilter, (uint32_t)t);
         stream_s[0] = s0.k; stream_s[1] = s0.a; stream_s[2] = s0.b;

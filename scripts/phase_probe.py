@@ -22,7 +22,8 @@ def read(fn):
     buf = np.zeros((2, 4096, 8), dtype=np.uint64)
     rc = getattr(lib, fn)(buf.ctypes.data_as(C.c_void_p)); assert rc == 0
     return buf.astype(np.int64)
-sim = read("dpomp_debug_phases_sim")[0, :ncta, :7]
+sim_all = read("dpomp_debug_phases_sim")[0, :ncta, :8]
+sim, nxt = sim_all[:, :7], sim_all[:, 7]
 rs = read("dpomp_debug_phases_rs")[1, :ncta, :5]
 t0 = sim[:, 0].min()
 def stats(name, v):
@@ -34,6 +35,7 @@ for i, nm in enumerate(["sim: CTA start", "sim: after grid dependency wait", "si
     stats(nm, sim[:, i])
 for i, nm in enumerate(["resample: CTA start", "resample: after dependency wait", "resample: tile loaded", "resample: counts + barrier", "resample: gather done"]):
     stats(nm, rs[:, i])
+stats("next simulate kernel: CTA start", nxt)
 d = np.diff(sim, axis=1) / 1e3
 print("  per-CTA phase durations (us), median / p90 / max:")
 for i, nm in enumerate(["launch->wait", "staging", "event loop", "weights", "scan+stores", "tickets"]):
