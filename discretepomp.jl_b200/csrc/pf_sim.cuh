@@ -41,6 +41,9 @@ template <> struct Arith<double> {  // round-to-nearest, never contracted: the r
 #ifndef DPOMP_SIM_ILP
 #define DPOMP_SIM_ILP 1
 #endif
+#ifndef DPOMP_SIM_PIPE
+#define DPOMP_SIM_PIPE 1
+#endif
 // 256-thread CTAs: 4 resident (64 registers, no spills) beat 5 / 6 (48 / 40 registers) on B200; 128-thread CTAs: 7 resident
 #ifndef DPOMP_SIM_MINB
 #define DPOMP_SIM_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
@@ -275,6 +278,14 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     const Real tm0 = kF32 ? (Real)(t_obs - t_prev) : (Real)t_prev;  // f32: remaining time; f64: absolute time
     uint32_t k[S];
     uint32_t pc[S];  // first Philox counter word of the lane's particle: (global particle index) ^ A, fixed until the refill
+    // Latency regime (the two-particles-per-lane instantiation the host picks for a few small filters): the Philox words of
+    // attempt k + 1 depend on nothing the attempt k computes (an attempt either goes on to counter k + 1 or ends the
+    // particle), so they are drawn one attempt AHEAD and the loop-carried chain of an iteration is the float chain alone
+    // (rates -> rcp / lg2 -> compare -> state) instead of Philox (20 dependent integer operations) + float chain.  Same
+    // counters, same draws.  Not used in the throughput regime: the refill path would pay a second Philox call per particle
+    // and the loop is issue bound there.
+    constexpr bool PIPE = DPOMP_SIM_PIPE && kF32 && S == 2;
+    uint2 wn[S];
     unsigned long long ev_local = 0, ovf_local = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -284,6 +295,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         tm[s] = tm0;
         k[s] = 0;
         pc[s] = (uint32_t)(base_n + q[s]) ^ ss.a;
+        if constexpr (PIPE) wn[s] = philox2x32_10(pc[s], 0u ^ ss.b, ss.k);
 #pragma unroll
         for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;  // idle lanes: harmless values
     }
@@ -300,7 +312,13 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                 Real cum[E];
                 cum_rates<Real, C, E, MODEL>(m, par, x[s], cum);
                 const Real rtot = cum[E - 1];
-                const uint2 w = philox2x32_10(pc[s], k[s] ^ ss.b, ss.k);
+                uint2 w;
+                if constexpr (PIPE) {
+                    w = wn[s];
+                    wn[s] = philox2x32_10(pc[s], (k[s] + 1u) ^ ss.b, ss.k);  // the draws of the next attempt of this particle
+                } else {
+                    w = philox2x32_10(pc[s], k[s] ^ ss.b, ss.k);
+                }
                 // time -= log(rand()) / R  (:23) as remaining time; lg2.approx + rcp.approx on the XU pipe
                 const Real tmn = fmaf(__log2f(u32_wait_f32(w.x)), __fdividef(0.693147180559945f, rtot), tm[s]);
                 const bool capped = k[s] >= max_ev;  // event cap: documented divergence, the reference loop is unbounded
@@ -367,6 +385,7 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
                         for (int c = 0; c < C; ++c) x[s][c] = (c < n_comp) ? (Real)st_s[c * TILE + q[s]] : (Real)0;
                         tm[s] = tm0;
                         k[s] = 0;
+                        if constexpr (PIPE) wn[s] = philox2x32_10(pc[s], 0u ^ ss.b, ss.k);
                     }
                 }
                 const int nf = __popc(fmask);

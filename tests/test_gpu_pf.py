@@ -102,20 +102,36 @@ def test_partial_calls_compose_on_device(dp, orc):
         _pf(dp, hmm, n).partial(theta, 2, 3)  # ymin > 1 on a filter that was never started
 
 
-def test_f32_loop_trajectories_match_within_1e6(dp, orc):
-    # same Philox draws, f32 event loop: almost every trajectory is identical to the f64 oracle; on those the
-    # per-trajectory log-likelihood matches to <= 1e-6 relative (it is computed in f64 from identical integer states)
-    model, y, hmm, theta = load_case(dp, "sir_c2")
+@pytest.mark.parametrize("case,n_keys,min_same", [("sir_c2", 1, 0.999), ("sir_c2", 8, 0.999), ("seir_c3", 8, 0.999),
+                                                  ("sis_pooley", 1, 0.998), ("lotka_c4", 1, 0.998)])
+def test_f32_loop_trajectories_match_within_1e6(dp, orc, case, n_keys, min_same):
+    """Same Philox draws, f32 event loop against the f64 literal oracle over the first observation interval (n_keys
+    independent stream keys x 4096 trajectories).  A trajectory whose f32 waiting times / event choices never cross a decision
+    boundary ends in the identical integer state, and its log-weight -- f64 from integers -- is then identical (<= 1e-6
+    relative asserted); the others differ by an event.  The fraction of identical trajectories is the per-trajectory statement
+    of the f32 loop (2 events per interval for SIR / SEIR, ~200 for SIS-pooley and LOTKA); the f64 loop (DPOMP_SIM_F64) is
+    identical on ALL of them (tests above)."""
+    model, y, hmm, theta = load_case(dp, case)
     n = 4096
-    pf = _pf(dp, hmm, n)
     key = 31337
-    pf.set_stream_key(key)
-    pf.partial(theta, 1, 1)
-    o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 1, 1, key, 0, orc.MODE_LITERAL)
-    lw = pf.last_logw()
-    same = lw == o[1]
-    assert same.mean() > 0.999
-    assert np.all(np.abs(lw[same] - o[1][same]) <= 1e-6 * np.abs(o[1][same]))
+    same_all, lw_all, ref_all = [], [], []
+    for r in range(n_keys):
+        pf = _pf(dp, hmm, n)
+        pf.set_stream_key(key + r)
+        pf.partial(theta, 1, 1)
+        o = orc.pf_partial(pf.dmodel.compiled.desc, theta, n, None, 1, 1, 1, key + r, 0, orc.MODE_LITERAL)
+        lw = pf.last_logw()
+        same_all.append(lw == o[1]); lw_all.append(lw); ref_all.append(o[1])
+    same, lw, ref = np.concatenate(same_all), np.concatenate(lw_all), np.concatenate(ref_all)
+    print(f"{case}: {same.mean():.5f} of {same.size} f32 trajectories identical to the f64 oracle")
+    assert same.mean() > min_same, (case, same.mean())
+    fin = same & np.isfinite(ref)
+    assert np.all(np.abs(lw[fin] - ref[fin]) <= 1e-6 * np.abs(ref[fin]))
+    # the trajectories that differ do so by a few events: their log-weights stay finite and the weighted mean moves by << MC error
+    both = np.isfinite(lw) & np.isfinite(ref)
+    assert both.mean() > 0.999
+    w_gpu, w_ref = np.exp(lw[both] - ref[both].max()), np.exp(ref[both] - ref[both].max())
+    assert abs(np.log(w_gpu.mean()) - np.log(w_ref.mean())) < 5.0 / np.sqrt(both.sum())
 
 
 @pytest.mark.parametrize("case,n,reps", [("sis_pooley", 200, 512), ("sir_c2", 1024, 128), ("seir_c3", 1024, 128),
