@@ -73,7 +73,7 @@ int sim_kernel_supported(int n_comp, int n_events) {
 #ifndef DPOMP_RS_MINB
 #define DPOMP_RS_MINB (DPOMP_BLOCK_THREADS == 128 ? 7 : 4)
 #endif
-template <int ITEMS, int RS, bool PERM>
+template <int ITEMS, int RS, bool PERM, int NC>
 __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kernel(const __grid_constant__ ResampleLaunch a) {
     constexpr int TILE = kBlockThreads * ITEMS;
     constexpr int CHUNK = 32 * ITEMS;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
     const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
                     a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
     DPOMP_STAMP(1, 2);
-    resample_tile<ITEMS, int, false, RS, PERM>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
+    resample_tile<ITEMS, int, false, RS, PERM, NC>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);
     DPOMP_STAMP(1, 4);
 }
 
@@ -217,12 +217,17 @@ cudaError_t launch_resample(int items, const ResampleLaunch& a, cudaStream_t str
     // cw materialisation at the top of the kernel)
     const bool strat = a.rs_type == DPOMP_RS_STRATIFIED, perm = a.perm.ncf > 0;
     cudaError_t err;
-#define DPOMP_RS_LAUNCH(IT, RS, PM) launch_pdl(pf_resample_kernel<IT, RS, PM>, grid, kBlockThreads, smem, stream, a)
-#define DPOMP_RS_PICK(IT)                                                                                              \
-    (strat ? (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_STRATIFIED, true) : DPOMP_RS_LAUNCH(IT, DPOMP_RS_STRATIFIED, false))   \
-           : (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_SYSTEMATIC, true) : DPOMP_RS_LAUNCH(IT, DPOMP_RS_SYSTEMATIC, false)))
+    // the identity placement (the reference's row order) is instantiated per compartment count of the predefined models
+#define DPOMP_RS_LAUNCH(IT, RS, PM, NC) launch_pdl(pf_resample_kernel<IT, RS, PM, NC>, grid, kBlockThreads, smem, stream, a)
+#define DPOMP_RS_NC(IT, RS)                                                                      \
+    (a.n_comp == 2 ? DPOMP_RS_LAUNCH(IT, RS, false, 2) : a.n_comp == 3 ? DPOMP_RS_LAUNCH(IT, RS, false, 3) \
+     : a.n_comp == 4 ? DPOMP_RS_LAUNCH(IT, RS, false, 4) : DPOMP_RS_LAUNCH(IT, RS, false, 0))
+#define DPOMP_RS_PICK(IT)                                                                                  \
+    (strat ? (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_STRATIFIED, true, 0) : DPOMP_RS_NC(IT, DPOMP_RS_STRATIFIED))   \
+           : (perm ? DPOMP_RS_LAUNCH(IT, DPOMP_RS_SYSTEMATIC, true, 0) : DPOMP_RS_NC(IT, DPOMP_RS_SYSTEMATIC)))
     err = items == kItemsSmall ? DPOMP_RS_PICK(kItemsSmall) : DPOMP_RS_PICK(kItemsLarge);
 #undef DPOMP_RS_PICK
+#undef DPOMP_RS_NC
 #undef DPOMP_RS_LAUNCH
     if (err != cudaSuccess) return err;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {

@@ -4,6 +4,8 @@
 // Replaces rsp_systematic (src/hmm_pf_resample.jl:24-42) / the intended rsp_stratified (:46-63) and the `old_p .= pop`
 // copy of partial_log_likelihood! (src/hmm_particle_filter.jl:66).
 #pragma once
+#include <type_traits>
+
 #include "dpomp_dev.cuh"
 
 namespace dpomp {
@@ -36,7 +38,8 @@ __device__ __forceinline__ T ld_combine(const T* p) {  // CG: the value was writ
     if constexpr (CG) return __ldcg(p); else return *p;
 }
 
-template <int ITEMS, typename SrcT, bool CG, int RS = 0, bool PERM = true>
+// NC: compartments at compile time (the gather of the stand-alone kernel is instantiated for 2, 3 and 4), 0 = a.n_comp
+template <int ITEMS, typename SrcT, bool CG, int RS = 0, bool PERM = true, int NC = 0>
 __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, uint32_t gfilter, const double (&incl)[ITEMS],
                                               const SrcT* st_tile, int stride, int* am_all, int* warp_max_s, long long* lohi_s) {
     constexpr int TILE = kBlockThreads * ITEMS;
@@ -229,39 +232,54 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) am_w[lane * ITEMS + k] = max(am[k], aprev);
         __syncwarp();
-        // gather: striped over the window; per compartment the ITEMS loads of a lane are issued before its stores
-        int srcq[ITEMS];
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const int pidx = j * 32 + lane;
-            srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
-            if (srcq[j] >= 0) {  // window entry: an ancestor of this warp's chunk; offspring row inside the filter
-                DPOMP_CHECK_IDX(srcq[j], CHUNK);
-                DPOMP_CHECK_IDX(base_n + warp * CHUNK + srcq[j], a.n);
-                DPOMP_CHECK_IDX(lo + wlo + pidx, a.n);
-            } else {
-                DPOMP_CHECK_IDX(wlo + pidx < wlast ? -1 : 0, 1);  // a live window slot must have an ancestor
-            }
-        }
         if (!PERM || a.perm.ncf == 0) {  // the reference's row order: offspring i in row i
-            for (int c = 0; c < a.n_comp; ++c) {
-                const SrcT* sc = st_tile + (size_t)c * stride + warp * CHUNK;
-                int32_t* dc = dst_b + (size_t)c * a.n_pad + lo + wlo + lane;
-                int vals[ITEMS];
+            // gather: one row of 32 offspring per step (coalesced 128-byte stores), only the live rows of the window -- the
+            // second, nearly empty window of a warp with a few offspring more than CHUNK costs one row, not a full window
+            // (round 2: the ITEMS-wide predicated form was 79 SASS instructions per compartment and window, 30 % of the kernel)
+            const int nlive = min(wlast - wlo, CHUNK);  // warp-uniform, > 0
+            const SrcT* sw_ = st_tile + warp * CHUNK;
+            int32_t* d0 = dst_b + lo + wlo + lane;
+#pragma unroll 2
+            for (int r0 = 0; r0 < nlive; r0 += 32) {
+                const int pidx = r0 + lane;
+                const bool live = pidx < nlive;
+                const int sq = am_w[live ? pidx : 0];  // slot 0 of a non-empty window is live
+                if (live) {
+                    DPOMP_CHECK_IDX(sq, CHUNK);
+                    DPOMP_CHECK_IDX(base_n + warp * CHUNK + sq, a.n);
+                    DPOMP_CHECK_IDX(lo + wlo + pidx, a.n);
+                }
+                if constexpr (NC > 0) {
+                    int vals[NC];
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j)
-                    if (srcq[j] >= 0) vals[j] = (int)sc[srcq[j]];
+                    for (int c = 0; c < NC; ++c) vals[c] = (int)sw_[(size_t)c * stride + sq];
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j)
-                    if (srcq[j] >= 0) dc[j * 32] = vals[j];
-            }
-            if (a.anc) {
-#pragma unroll
-                for (int j = 0; j < ITEMS; ++j)
-                    if (srcq[j] >= 0)
-                        a.anc[(size_t)b * a.n_pad + lo + wlo + j * 32 + lane] = (int32_t)(base_n + warp * CHUNK + srcq[j]);
+                    for (int c = 0; c < NC; ++c)
+                        if (live) d0[(size_t)c * a.n_pad + r0] = vals[c];
+                } else {
+                    for (int c = 0; c < a.n_comp; ++c) {
+                        const int v = (int)sw_[(size_t)c * stride + sq];
+                        if (live) d0[(size_t)c * a.n_pad + r0] = v;
+                    }
+                }
+                if (a.anc && live) a.anc[(size_t)b * a.n_pad + lo + wlo + pidx] = (int32_t)(base_n + warp * CHUNK + sq);
             }
         } else {
+            // gather of the interleaved placement: striped over the window; per compartment the ITEMS loads of a lane are
+            // issued before its stores
+            int srcq[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const int pidx = j * 32 + lane;
+                srcq[j] = (wlo + pidx < wlast) ? am_w[pidx] : -1;
+                if (srcq[j] >= 0) {  // window entry: an ancestor of this warp's chunk; offspring row inside the filter
+                    DPOMP_CHECK_IDX(srcq[j], CHUNK);
+                    DPOMP_CHECK_IDX(base_n + warp * CHUNK + srcq[j], a.n);
+                    DPOMP_CHECK_IDX(lo + wlo + pidx, a.n);
+                } else {
+                    DPOMP_CHECK_IDX(wlo + pidx < wlast ? -1 : 0, 1);  // a live window slot must have an ancestor
+                }
+            }
             // Row of offspring i = lo + wlo + j * 32 + lane: consecutive j advance the chunk index by one, so
             // (k mod M, k div M) is kept incrementally (one division per window).  n_pad < 2^31: int rows.
             int row[ITEMS];
