@@ -270,8 +270,10 @@ def run_mbp_ibis_c5(dp, world, rank, barrier):
     th0 = model.prior.rand(MBPI_OUTER, np.random.default_rng(3))
     ptcls = dp.MbpParticles(dp.device_model(hmm), max(hi - lo, 1), seed=4)
     # warm-up = one full analysis on the same store (0.2 s): NCCL sets up its send / receive connections lazily at the first
-    # migration (0.3 s at two ranks), and a shortened data set does not reach a resample-move step
-    dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=5, comm=comm, outer_rs=dp.rs_stratified, verbose=False,
+    # migration (0.3 s at two ranks), and a shortened data set does not reach a resample-move step.  Same seed as the timed
+    # run, so the growable trajectory store has reached the capacity this analysis needs (the store is reset, nothing else
+    # is kept: the timed run simulates, proposes and migrates everything again)
+    dp.run_mbp_ibis(hmm, th0, 0.5, 3, False, 1.002, seed=4, comm=comm, outer_rs=dp.rs_stratified, verbose=False,
                     particles_factory=lambda n, sd: ptcls)
     gc.collect()
     barrier()
