@@ -351,9 +351,11 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
             std::vector<int> hl((size_t)pf->n_obs);
             for (int t = 0; t < pf->n_obs; ++t) hl[(size_t)t] = mh.obs_id[(size_t)t] > 0;
             CK(cudaMalloc((void**)&pf->rows_done, B * pf->ntiles * sizeof(unsigned int)));
-            CK(cudaMalloc((void**)&pf->gen_flags, B * pf->ngroups * 32 * sizeof(unsigned int)));
+            if (!pf->gen_flags) {
+                CK(cudaMalloc((void**)&pf->gen_flags, B * pf->ngroups * 32 * sizeof(unsigned int)));
+                CK(cudaMemsetAsync(pf->gen_flags, 0, B * pf->ngroups * 32 * sizeof(unsigned int), st));
+            }
             CK(cudaMalloc((void**)&pf->obs_haslik_dev, (size_t)pf->n_obs * sizeof(int)));
-            CK(cudaMemsetAsync(pf->gen_flags, 0, B * pf->ngroups * 32 * sizeof(unsigned int), st));
             CK(cudaMemcpyAsync(pf->obs_haslik_dev, hl.data(), (size_t)pf->n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
             CK(cudaStreamSynchronize(st));  // hl is a stack vector
         }
@@ -418,15 +420,24 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         a.filter_ids = pf->use_filter_ids ? pf->filter_ids_dev : nullptr;
         // one fused launch (simulate + resample) when every tile of a filter can be resident at once
         const bool fused = do_rs && fused_ok;
+        bool fused_tickets = false;
         if (fused) {
             a.do_resample = 1;
             a.rs_type = pf->rs_type;
             a.pop_dst = pf->pop[pf->cur ^ 1];
             a.anc = pf->record_anc ? pf->anc : nullptr;
             a.perm = make_chunk_perm(pf->scatter_mode, pf->n, pf->ntiles);
-            a.work_counter = pf->work_counter;
+            // arrival-order tickets only when the launch has more CTAs than the device holds at once
+            fused_tickets = (long long)nb * pf->ntiles > pf->fused_capacity[pf->sim_precision == DPOMP_SIM_F64 ? 1 : 0];
+            a.work_counter = fused_tickets ? pf->work_counter : nullptr;
             a.work_base = pf->work_base;
             a.filt_gen = pf->filt_gen;
+            if (!pf->gen_flags) {
+                const size_t fb = (size_t)pf->n_batch * pf->ngroups * 32 * sizeof(unsigned int);
+                CK(cudaMalloc((void**)&pf->gen_flags, fb));
+                CK(cudaMemsetAsync(pf->gen_flags, 0, fb, st));
+            }
+            a.gen_flags = pf->gen_flags;
             a.gen = pf->gen + 1;
         }
         if (pf->kernel_timing) CK(kernel_event(pf, 0, st));
@@ -437,7 +448,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
             // the host mirrors of the device ticket counter / generation advance only once the launch is enqueued: a failed
             // launch leaves the handle consistent (the device counter has not moved either)
             pf->gen += 1;
-            pf->work_base += (unsigned long long)nb * pf->ntiles;
+            if (fused_tickets) pf->work_base += (unsigned long long)nb * pf->ntiles;
             pf->cur ^= 1;
         } else if (do_rs) {
             ResampleLaunch r{};

@@ -77,8 +77,10 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     for (int k = 0; k < ITEMS; ++k) er[k] = (int)resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, incl[k]));
 #else
     unsigned todo = 0;  // items whose closed-form guess needs the exact correction
+    // (RS == 0, the fused step kernel: the resampler is a block-uniform run-time value)
+    const bool sys = RS == DPOMP_RS_SYSTEMATIC || (RS == 0 && a.rs_type == DPOMP_RS_SYSTEMATIC);
 #ifndef DPOMP_NO_FUSED_GUESS
-    if constexpr (RS == DPOMP_RS_SYSTEMATIC) {
+    if (sys) {
         // Systematic: the count of an item is floor(t) + 1 with t = cw_q N / S - r unless t lies within 2^-12 of an integer
         // (resample_ecount_guess).  For that decision t may come from ONE fused multiply-add per item,
         //   t ~ K0 + K1 * incl_q,  K1 = F_g f_{b|g} N / S,  K0 = (O_g + F_g o_{b|g}) N / S - r:
@@ -126,7 +128,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
             e_k = (k == j) ? er[j] : e_k;
         }
 #ifndef DPOMP_NO_FUSED_GUESS
-        if constexpr (RS == DPOMP_RS_SYSTEMATIC) {  // the fused guess of this item was not usable: the full exact count
+        if (sys) {  // the fused guess of this item was not usable: the full exact count
             e_k = (int)resample_ecount<RS>(ctx, tile_cw(g_off, g_f, t_off, t_f, inc_k));
         } else
 #endif

@@ -155,9 +155,12 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
     unsigned int logical = blockIdx.x;
     if constexpr (FUSED) {
         __shared__ unsigned int logical_s;
-        if (tid == 0) logical_s = (unsigned int)(atomicAdd(a.work_counter, 1ull) - a.work_base);
-        __syncthreads();
-        logical = logical_s;
+        // (work_counter == nullptr: every CTA of the launch is co-resident, the launch order does not matter)
+        if (a.work_counter) {
+            if (tid == 0) logical_s = (unsigned int)(atomicAdd(a.work_counter, 1ull) - a.work_base);
+            __syncthreads();
+            logical = logical_s;
+        }
     }
     const int tile = logical % a.ntiles;
     const int b = logical / a.ntiles;
@@ -580,10 +583,11 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         if (has_lik) atomicAdd(&a.ll_acc[b], l2.big_m + log(l2.big_s / (double)a.n));
         a.tile_counter[b] = 0u;
     }
-    if constexpr (FUSED) {  // publish the combine to the CTAs of this filter that wait below
-        __syncwarp();
+    if constexpr (FUSED) {  // publish the combine to the CTAs of this filter that wait below: one flag per group of tiles
+        __syncwarp();       // (own 128-byte line: kGroupTiles pollers per address instead of every tile of the filter on one)
         __threadfence();
-        if (tid == 0) atomicExch(&a.filt_gen[b], a.gen);
+        for (int g = tid; g < a.ngroups; g += 32)
+            *reinterpret_cast<volatile unsigned int*>(a.gen_flags + ((size_t)b * a.ngroups + g) * 32) = a.gen;
     }
     if constexpr (PERSIST) {  // one flag per group of tiles (own 128-byte line): kGroupTiles pollers per address, not ntiles
         __syncwarp();
@@ -599,14 +603,17 @@ pf_sim_weight_kernel(const __grid_constant__ DevModel<Real, C, E> m, const __gri
         if (!do_rs) return;
         // ---- wait for this filter's combine, then resample the tile from shared memory ---------------------------------
         if (tid == 0) {
-            while (*reinterpret_cast<volatile unsigned int*>(a.filt_gen + b) != a.gen) __nanosleep(64);
-            __threadfence();
+            const unsigned int* flag = a.gen_flags + ((size_t)b * a.ngroups + grp) * 32;
+            while (ld_acquire_u32(flag) != a.gen) __nanosleep(32);
         }
         __syncthreads();
+        DPOMP_STAMP(1, 1);
         const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
                         a.ntiles, a.ngroups, a.n_comp, t, a.rs_type, a.key, a.perm};
         // ovf_s (TILE ints) is free after the weight pass: it becomes the per-warp offspring windows
-        resample_tile<ITEMS, SState, true>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s, warp_max_s, lohi_s);
+        resample_tile<ITEMS, SState, true, 0, true, (MODEL != kModelGeneric ? C : 0)>(ra, b, tile, gfilter, incl, st_s, TILE, ovf_s,
+                                                                                      warp_max_s, lohi_s);
+        DPOMP_STAMP(1, 4);
     }
     if constexpr (PERSIST) {
         // ---- wait for this filter's combine (also when this observation does not resample: the ticket counters are only

@@ -12,6 +12,8 @@ cases = {"sir_c2": ("SIR", [100, 1, 0], [0.003, 0.1]), "seir_c3": ("SEIR", [100,
 mname, ic, theta = cases[case]
 model = dp.generate_model(mname, ic); y = dp.get_observations(f"tests/golden/{case}.csv")
 pf = dp.ParticleFilter(dp.device_model(dp.get_private_model(model, y)), n, nb, 1, seed=1)
+fused = os.environ.get("FUSED") == "1"  # fused step kernel whenever the tiles of a filter are co-resident (mode 2)
+if fused: pf.set_fused(2)
 th = torch.tensor(np.tile(np.asarray(theta)[None, :], (nb, 1)), dtype=torch.float64, device="cuda")
 out = torch.zeros(nb, dtype=torch.float64, device="cuda")
 for _ in range(4): pf.loglik_device(th.data_ptr(), nb, out.data_ptr())
@@ -24,7 +26,8 @@ def read(fn):
     return buf.astype(np.int64)
 sim_all = read("dpomp_debug_phases_sim")[0, :ncta, :8]
 sim, nxt = sim_all[:, :7], sim_all[:, 7]
-rs = read("dpomp_debug_phases_rs")[1, :ncta, :5]
+rs = read("dpomp_debug_phases_sim" if fused else "dpomp_debug_phases_rs")[1, :ncta, :5]
+if fused: rs[:, 0] = rs[:, 1]; rs[:, 2] = rs[:, 1]  # fused: only "after the wait" (1), "counts + barrier" (3) and "gather done" (4) exist
 t0 = sim[:, 0].min()
 def stats(name, v):
     v = (v - t0) / 1e3
