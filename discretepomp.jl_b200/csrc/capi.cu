@@ -142,6 +142,8 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     pf->n_comp = d.n_compartments;
     pf->n_params = d.n_params;
     pf->n_obs = d.n_obs;
+    if (const char* ev = getenv("DPOMP_DEFER_L2")) pf->defer_l2_enabled = atoi(ev) != 0;  // A/B knob (scripts/): 0 = two ticket levels
+    if (cudaDeviceGetAttribute(&pf->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) pf->sm_count = 148;
     if ((long long)n_batch * pf->ntiles > 0x7fffffffll) { delete pf; return fail(DPOMP_ERR_ARG, "n_batch * tiles exceeds the grid limit"); }
 
     const size_t B = (size_t)n_batch, NP = (size_t)pf->n_pad, NT = (size_t)pf->ntiles;
@@ -421,6 +423,13 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         // one fused launch (simulate + resample) when every tile of a filter can be resident at once
         const bool fused = do_rs && fused_ok;
         bool fused_tickets = false;
+        // two-kernel chain: level 2 of the combine runs in the resample kernel (no second ticket level in the simulate kernel)
+        // -- in the latency regime only (the launch is at most one wave of CTAs): measured on B200, C2 3.39 -> 3.26 ms and 8 x 65536
+        // SEIR 2.88 -> 2.76 ms, but 64 x 65536 SEIR 13.06 -> 13.55 ms (every CTA of a multi-wave launch repeats level 2, and the
+        // serial tail it removes is amortised over the waves anyway)
+        const bool defer_l2 = do_rs && !fused && pf->ngroups <= kDeferGroups && pf->defer_l2_enabled &&
+                              (long long)nb * pf->ntiles <= 8ll * pf->sm_count;
+        a.defer_l2 = defer_l2 ? 1 : 0;
         if (fused) {
             a.do_resample = 1;
             a.rs_type = pf->rs_type;
@@ -455,6 +464,9 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
             r.pop_src = pf->pop[pf->cur]; r.pop_dst = pf->pop[pf->cur ^ 1];
             r.wtile = pf->wtile; r.tile_m = pf->tile_m; r.tile_f = pf->tile_f; r.tile_off = pf->tile_off; r.filt_s = pf->filt_s;
             r.grp_f = pf->grp_f; r.grp_off = pf->grp_off; r.ngroups = pf->ngroups;
+            r.defer_l2 = defer_l2 ? 1 : 0; r.has_lik = has_lik;
+            r.grp_m = pf->grp_m; r.grp_s = pf->grp_s; r.grp_f_w = pf->grp_f; r.grp_off_w = pf->grp_off;
+            r.filt_s_w = pf->filt_s; r.filt_m_w = pf->filt_m; r.ll_acc = pf->ll_acc;
             r.anc = pf->record_anc ? pf->anc : nullptr;
             r.cw = pf->cw;
             r.n = pf->n; r.n_pad = pf->n_pad; r.ntiles = pf->ntiles; r.n_filters = nb; r.n_comp = pf->n_comp;

@@ -97,6 +97,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned bl
 // group that is combined by the last of its tiles to finish (one warp), the groups by the last group to finish.
 //   cw_q = O_g + F_g * (o_{b|g} + f_{b|g} * incl_q)
 constexpr int kGroupTiles = 32;
+// filters of at most this many groups (2^21 particles) leave level 2 of the combine to the resample kernel (pf_kernels.cu)
+constexpr int kDeferGroups = 64;
 __device__ __forceinline__ double tile_cw(double grp_off, double grp_f, double tile_o, double tile_f, double incl) {
     return __dadd_rn(grp_off, __dmul_rn(grp_f, __dadd_rn(tile_o, __dmul_rn(tile_f, incl))));
 }
@@ -108,20 +110,26 @@ __device__ __forceinline__ double tile_cw(double grp_off, double grp_f, double t
 struct Level2 {
     double big_m, big_s;
 };
+// CG: the group partials were written by other SMs during this launch (read from L2); otherwise plain loads (written
+// before the launch)
+template <bool CG = true>
 __device__ __forceinline__ Level2 combine_level2(const double* gm_b, const double* gs_b, int ngroups, double* grp_f_out,
                                                  double* grp_off_out) {
+    auto ld = [](const double* p) -> double {
+        if constexpr (CG) return __ldcg(p); else return *p;
+    };
     const int lane = threadIdx.x & 31;
     double big_m = -INFINITY;
-    for (int i = lane; i < ngroups; i += 32) big_m = fmax(big_m, __ldcg(gm_b + i));
+    for (int i = lane; i < ngroups; i += 32) big_m = fmax(big_m, ld(gm_b + i));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) big_m = fmax(big_m, __shfl_xor_sync(0xffffffffu, big_m, d));
     double carry = 0.0;
     for (int c0 = 0; c0 < ngroups; c0 += 32) {
         const int i = c0 + lane;
         const bool have = i < ngroups;
-        const double mg = have ? __ldcg(gm_b + i) : -INFINITY;
+        const double mg = have ? ld(gm_b + i) : -INFINITY;
         const double f = (mg == -INFINITY) ? 0.0 : exp(mg - big_m);
-        double inc = have ? __dmul_rn(f, __ldcg(gs_b + i)) : 0.0;
+        double inc = have ? __dmul_rn(f, ld(gs_b + i)) : 0.0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const double y = __shfl_up_sync(0xffffffffu, inc, d);

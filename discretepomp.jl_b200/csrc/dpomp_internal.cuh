@@ -66,6 +66,8 @@ struct SimLaunch {
     int fresh;               // 1: start from the initial condition at t_prev = 0 / theta[t0_index]
     int has_lik;             // obs_id[t] > 0
     // fused step (simulate + resample in ONE launch; all tiles of a filter must be co-resident): see pf_sim.cuh
+    int defer_l2;            // plain kernel followed by the resample kernel, ngroups <= kDeferGroups: level 2 of the combine
+                             // (and the log-likelihood increment) is left to the resample kernel, no second ticket level
     int do_resample;         // fused kernel only: resample after the combine
     int rs_type;
     int32_t* pop_dst;        // [B][C][n_pad] offspring populations
@@ -98,6 +100,16 @@ struct ResampleLaunch {
     const double* grp_off;
     int ngroups;
     const double* filt_s;
+    // deferred level 2 (defer_l2): the group partials of the simulate kernel, and where the filter totals / the group scales
+    // and offsets go (written by the tile-0 CTA of every filter for later consumers; every CTA combines for itself)
+    int defer_l2, has_lik;
+    const double* grp_m;
+    const double* grp_s;
+    double* grp_f_w;
+    double* grp_off_w;
+    double* filt_s_w;
+    double* filt_m_w;
+    double* ll_acc;
     int32_t* anc;            // [B][n_pad] 0-based ancestors, or nullptr
     double* cw;              // [B][n_pad] cumulative weights (multinomial only), or nullptr
     long long n, n_pad;
@@ -166,6 +178,8 @@ struct dpomp_pf {
     int* obs_haslik_dev = nullptr;               // [T]
     bool fused_enabled = true;
     int fused_mode = 1;                          // 1: automatic (one tile per filter), 2: whenever the tiles fit
+    int sm_count = 148;
+    bool defer_l2_enabled = true;                // two-kernel chain: level 2 of the combine in the resample kernel (DPOMP_DEFER_L2=0: off)
     int fused_capacity[2] = {-1, -1};            // co-resident CTAs of the fused kernel per sim precision (lazy)
     uint32_t* filter_ids_dev = nullptr;      // n_batch, valid when use_filter_ids
     bool use_filter_ids = false;

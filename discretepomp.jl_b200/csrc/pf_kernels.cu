@@ -126,8 +126,37 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
         for (int k = 0; k < ITEMS; ++k) incl[k] = wt[k];
     }
 
+    // Deferred level 2 of the combine (the simulate kernel stopped after the group level): warp 0 combines the <= 64 group
+    // partials of the filter while the tile loads above are in flight -- M, F_g = exp(m_g - M), O_g, S with exactly the tree
+    // of combine_level2 -- into shared memory (a prefetch of the partials at the top of the kernel made it 2 us SLOWER); the
+    // tile-0 CTA of the filter also stores them for later consumers and adds the log-likelihood increment
+    // log(cum_weight[end] / N) (src/hmm_particle_filter.jl:60) as M + log(S / N).
+    __shared__ double l2f_s[kDeferGroups], l2off_s[kDeferGroups];
+    __shared__ double l2s_s;
+    if (a.defer_l2) {
+        if (warp == 0) {
+            const Level2 l2 = combine_level2<false>(a.grp_m + (size_t)b * a.ngroups, a.grp_s + (size_t)b * a.ngroups, a.ngroups, l2f_s, l2off_s);
+            if (lane == 0) l2s_s = l2.big_s;
+            if (tile == 0) {
+                __syncwarp();
+                for (int g = lane; g < a.ngroups; g += 32) {
+                    a.grp_f_w[(size_t)b * a.ngroups + g] = l2f_s[g];
+                    a.grp_off_w[(size_t)b * a.ngroups + g] = l2off_s[g];
+                }
+                if (lane == 0) {
+                    a.filt_s_w[b] = l2.big_s;
+                    a.filt_m_w[b] = l2.big_m;
+                    if (a.has_lik) atomicAdd(&a.ll_acc[b], l2.big_m + log(l2.big_s / (double)a.n));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const double* l2_f = a.defer_l2 ? l2f_s : nullptr;
+    const double* l2_off = a.defer_l2 ? l2off_s : nullptr;
+    const double* l2_s = a.defer_l2 ? &l2s_s : nullptr;
     if (a.rs_type == DPOMP_RS_MULTINOMIAL) {  // materialise cw; the per-offspring search is a second kernel 
-        const double g_off = a.grp_off[(size_t)b * a.ngroups + grp], g_f = a.grp_f[(size_t)b * a.ngroups + grp];
+        const double g_off = l2_off ? l2_off[grp] : a.grp_off[(size_t)b * a.ngroups + grp], g_f = l2_f ? l2_f[grp] : a.grp_f[(size_t)b * a.ngroups + grp];
         const double t_off = a.tile_off[(size_t)b * a.ntiles + tile], t_f = a.tile_f[(size_t)b * a.ntiles + tile];
         double* cw = a.cw + (size_t)b * a.n_pad + base_n + (size_t)tid * ITEMS;
 #pragma unroll
@@ -135,7 +164,7 @@ __global__ void __launch_bounds__(kBlockThreads, DPOMP_RS_MINB) pf_resample_kern
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         return;
     }
-    const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, a.pop_dst, a.anc, a.n, a.n_pad,
+    const RsArgs ra{a.tile_f, a.tile_off, a.grp_f, a.grp_off, a.filt_s, l2_f, l2_off, l2_s, a.pop_dst, a.anc, a.n, a.n_pad,
                     a.ntiles, a.ngroups, a.n_comp, a.t, a.rs_type, a.key, a.perm};
     DPOMP_STAMP(1, 2);
     resample_tile<ITEMS, int, false, RS, PERM, NC>(ra, b, tile, gfilter, incl, st_dyn, TILE, &am_s[0][0], warp_max_s, lohi_s);

@@ -16,6 +16,11 @@ struct RsArgs {              // what the phase needs besides the tile's own data
     const double* grp_f;     // [B][ngroups]
     const double* grp_off;   // [B][ngroups]
     const double* filt_s;    // [B]
+    // filter-local views of level 2 computed by this CTA (deferred level 2 of the stand-alone kernel), or nullptr: then the
+    // arrays above, written by the simulate kernel, are read
+    const double* l2_f;      // [ngroups]
+    const double* l2_off;    // [ngroups]
+    const double* l2_s;      // [1]
     int32_t* pop_dst;        // [B][C][n_pad]
     int32_t* anc;            // [B][n_pad] or nullptr
     long long n, n_pad;
@@ -49,9 +54,11 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
     constexpr int kHeavyFactor = 8;  // offspring / ancestors of a tile above which the CTA-wide path is used
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base_n = (long long)tile * TILE;
-    const double big_s = ld_combine<double, CG>(a.filt_s + b);
+    const double big_s = a.l2_s ? *a.l2_s : ld_combine<double, CG>(a.filt_s + b);
     const int grp = tile / kGroupTiles;
-    const double g_off = ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + grp), g_f = ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + grp);
+    auto grp_off_of = [&](int g) -> double { return a.l2_off ? a.l2_off[g] : ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + g); };
+    auto grp_f_of = [&](int g) -> double { return a.l2_f ? a.l2_f[g] : ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + g); };
+    const double g_off = grp_off_of(grp), g_f = grp_f_of(grp);
     const double t_off = ld_combine<double, CG>(a.tile_off + (size_t)b * a.ntiles + tile), t_f = ld_combine<double, CG>(a.tile_f + (size_t)b * a.ntiles + tile);
 
     const Philox4 p = stream_draw(a.key, 0u, gfilter, (uint32_t)a.t, kTagResample, 0u);
@@ -63,7 +70,7 @@ __device__ __forceinline__ void resample_tile(const RsArgs& a, int b, int tile, 
         long long hi_b = a.n;
         if (tile != a.ntiles - 1) {
             const int g2 = (tile + 1) / kGroupTiles;
-            hi_b = resample_ecount<RS>(ctx, tile_cw(ld_combine<double, CG>(a.grp_off + (size_t)b * a.ngroups + g2), ld_combine<double, CG>(a.grp_f + (size_t)b * a.ngroups + g2),
+            hi_b = resample_ecount<RS>(ctx, tile_cw(grp_off_of(g2), grp_f_of(g2),
                                                 ld_combine<double, CG>(a.tile_off + (size_t)b * a.ntiles + tile + 1), 1.0, 0.0));
         }
         lohi_s[1] = hi_b;
