@@ -305,11 +305,13 @@ def test_degenerate_weights_collapse_to_few_ancestors(dp, orc):
 
 
 @pytest.mark.parametrize("case,n,nb,f64", [("sir_c2", 3000, 3, True), ("sir_c2", 200, 5, False), ("seir_c3", 70000, 2, False),
-                                            ("lotka_c4", 1024, 4, False), ("sis_pooley", 1 << 18, 1, False)])
+                                            ("lotka_c4", 1024, 4, False), ("sis_pooley", 1 << 18, 1, False),
+                                            ("sis_pooley", 200, 1300, False)])
 @pytest.mark.parametrize("rs_type", [1, 2])
 def test_fused_step_kernel_equals_two_kernel_path(dp, case, n, nb, f64, rs_type):
     """The fused simulate+resample launch and the two-kernel path are the same computation: bit-identical log-likelihoods,
-    populations and ancestors (f32 and f64 loops, ragged tiles, several filters)."""
+    populations and ancestors (f32 and f64 loops, ragged tiles, several filters; 1300 one-tile filters = more CTAs than the
+    device holds at once: the arrival-order tickets of the fused kernel, which co-resident launches skip)."""
     model, y, hmm, theta = load_case(dp, case)
     thetas = theta[:, None] * np.linspace(0.9, 1.1, nb)[None, :]
     out = []
@@ -323,6 +325,28 @@ def test_fused_step_kernel_equals_two_kernel_path(dp, case, n, nb, f64, rs_type)
     assert np.array_equal(ll_a, ll_b) and np.array_equal(anc_a, anc_b)
     assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
     assert launches_a < launches_b  # one launch per resampling observation instead of two
+
+
+@pytest.mark.parametrize("case,n,nb", [("sir_c2", 70000, 3), ("seir_c3", 1 << 20, 1), ("sis_pooley", 3000, 7)])
+@pytest.mark.parametrize("rs_type", [1, 2, 3])
+def test_deferred_level2_equals_two_ticket_levels(dp, case, n, nb, rs_type, monkeypatch):
+    """Latency regime: level 2 of the weight combine runs in the resample kernel (every CTA for itself, same tree) instead of
+    behind a second ticket level in the simulate kernel.  DPOMP_DEFER_L2=0 (read when the handle is created) switches it off:
+    log-likelihoods, populations and ancestors are bit-identical for all three resamplers (multinomial: the gather kernel
+    reads the totals the tile-0 CTA of the resample kernel stored)."""
+    model, y, hmm, theta = load_case(dp, case)
+    thetas = theta[:, None] * np.linspace(0.95, 1.05, nb)[None, :]
+    out = []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("DPOMP_DEFER_L2", knob)
+        pf = _pf(dp, hmm, n, nb, rs=rs_type, seed=8)
+        pf.set_fused(0)
+        pf.set_stream_key(4242)
+        ll = pf.partial(thetas, 1, min(len(y), 5))
+        out.append((ll, [pf.get_pop(b + 1) for b in range(nb)], pf.last_ancestors(nb)))
+    (ll_a, pops_a, anc_a), (ll_b, pops_b, anc_b) = out
+    assert np.array_equal(ll_a, ll_b) and np.array_equal(anc_a, anc_b)
+    assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
 
 
 @pytest.mark.parametrize("variant", ["wide_spread", "huge_observation", "tiny_sigma"])
