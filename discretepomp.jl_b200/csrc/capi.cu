@@ -143,6 +143,7 @@ int dpomp_pf_create(const dpomp_model* model, int64_t n_particles, int32_t n_bat
     pf->n_params = d.n_params;
     pf->n_obs = d.n_obs;
     if (const char* ev = getenv("DPOMP_DEFER_L2")) pf->defer_l2_enabled = atoi(ev) != 0;  // A/B knob (scripts/): 0 = two ticket levels
+    if (const char* ev = getenv("DPOMP_TWO_PER_LANE")) pf->two_per_lane_mode = atoi(ev);   // A/B and test knob: 0 never, 1 always
     if (cudaDeviceGetAttribute(&pf->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) pf->sm_count = 148;
     if ((long long)n_batch * pf->ntiles > 0x7fffffffll) { delete pf; return fail(DPOMP_ERR_ARG, "n_batch * tiles exceeds the grid limit"); }
 
@@ -430,6 +431,11 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
         const bool defer_l2 = do_rs && !fused && pf->ngroups <= kDeferGroups && pf->defer_l2_enabled &&
                               (long long)nb * pf->ntiles <= 8ll * pf->sm_count;
         a.defer_l2 = defer_l2 ? 1 : 0;
+        // two particles per lane on 1024-particle tiles: event-heavy model (>= 16 events per particle-step in the previous call of
+        // this handle) in a launch of at most 4 CTAs per SM (pf_sim.cuh, sim_plain_two_per_lane)
+        a.two_per_lane = pf->two_per_lane_mode >= 0 ? pf->two_per_lane_mode
+                         : ((long long)nb * pf->ntiles <= 4ll * pf->sm_count && pf->last_steps > 0 &&
+                            pf->last_events >= 16 * pf->last_steps);
         if (fused) {
             a.do_resample = 1;
             a.rs_type = pf->rs_type;
@@ -490,6 +496,7 @@ int dpomp_run_partial_enqueue(dpomp_pf* pf, const double* theta, bool theta_on_d
     CK(cudaMemcpyAsync(pf->h_cnt, pf->counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(pf->ev1, st));
     pf->last_launches = launches;
+    pf->enqueued_steps = (long long)nb * pf->n * (ymax - ymin + 1);
     return DPOMP_OK;
 }
 
@@ -498,6 +505,7 @@ int dpomp_run_partial_finish(dpomp_pf* pf, double* out, int nb, int out_mode) {
     if (out_mode == 0) memcpy(out, pf->h_ll, (size_t)nb * sizeof(double));
     CK(cudaEventElapsedTime(&pf->last_ms, pf->ev0, pf->ev1));
     pf->last_events = (long long)*pf->h_cnt;
+    pf->last_steps = pf->enqueued_steps;
     pf->kernel_ms[0] = pf->kernel_ms[1] = 0.f;
     pf->kernel_launches[0] = pf->kernel_launches[1] = 0;
     for (size_t i = 0; i < pf->kev_kind.size(); ++i) {

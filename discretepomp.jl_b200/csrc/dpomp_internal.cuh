@@ -66,6 +66,7 @@ struct SimLaunch {
     int fresh;               // 1: start from the initial condition at t_prev = 0 / theta[t0_index]
     int has_lik;             // obs_id[t] > 0
     // fused step (simulate + resample in ONE launch; all tiles of a filter must be co-resident): see pf_sim.cuh
+    int two_per_lane;        // plain kernel, 1024-particle tiles of a predefined model: the two-particles-per-lane loop (pf_sim.cuh)
     int defer_l2;            // plain kernel followed by the resample kernel, ngroups <= kDeferGroups: level 2 of the combine
                              // (and the log-likelihood increment) is left to the resample kernel, no second ticket level
     int do_resample;         // fused kernel only: resample after the combine
@@ -190,6 +191,9 @@ struct dpomp_pf {
     float last_ms = 0.f;
     int last_launches = 0;
     long long last_events = 0;
+    long long enqueued_steps = 0;                // particle-observation steps of the call in flight
+    long long last_steps = 0;                    // particle-observation steps of the last call (event intensity = last_events / last_steps)
+    int two_per_lane_mode = -1;                  // -1 automatic, 0 never, 1 always (DPOMP_TWO_PER_LANE: A/B and test knob)
     // optional per-kernel timing (bench.py roofline): events around every launch of the last call
     bool kernel_timing = false;
     std::vector<cudaEvent_t> kev;      // 2 events per launch slot

@@ -757,6 +757,26 @@ static int sim_inst(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream
                            : launch_pdl(kern, grid, kBlockThreads, smem, stream, m, a));
 }
 
+// Plain kernel of a predefined model on 1024-particle tiles with TWO particles per lane and the Philox words drawn one attempt
+// ahead (the loop of the latency regime): for event-heavy models (>= ~16 events per particle and interval: rare refills) in
+// launches that under-fill the device it is the faster loop -- 64 x 4096 LOTKA 9.24 -> 7.20 ms -- and the slower one for every
+// ~2-events-per-interval model and for full launches (profiles/r2_experiments.md 15, 16); the host selects it per call from
+// the event intensity of the handle's previous call (SimLaunch::two_per_lane).  Same counters, same draws: bit-identical.
+template <typename Real, int C, int E, int ITEMS, int MODEL>
+static int sim_plain_two_per_lane(const ModelHost& mh, const SimLaunch& a, cudaStream_t stream) {
+    constexpr int TILE = kBlockThreads * ITEMS;
+    const size_t smem = (size_t)TILE * (1 + C) * sizeof(int);
+    auto kern = pf_sim_weight_kernel<Real, C, E, ITEMS, MODEL, kModePlain, 2>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    const DevModel<Real, C, E> m = make_dev_model<Real, C, E>(mh);
+    return (int)launch_pdl(kern, (unsigned)(a.n_filters * a.ntiles), kBlockThreads, smem, stream, m, a);
+}
+
 constexpr int kLatencyRegimeCtas = 296;  // 2 CTAs per SM
 // the instantiated generic (C, E) shapes; a model runs on the smallest shape that covers it
 #define DPOMP_SIM_SHAPES(X) X(2, 1) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(4, 3) X(4, 6) X(8, 8)
@@ -775,6 +795,10 @@ static int sim_typed(const ModelHost& mh, int items, const SimLaunch& a, cudaStr
         if (items == kItemsSmall)                                                                                         \
             return latency ? sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID, 2>(mh, a, stream, mode)      \
                            : sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsSmall, ID, 1>(mh, a, stream, mode);     \
+        if constexpr (sizeof(Real) == 4 && DPOMP_SIM_ILP == 1) {                                                          \
+            if (mode == 0 && a.two_per_lane)                                                                              \
+                return sim_plain_two_per_lane<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream);      \
+        }                                                                                                                 \
         return sim_inst<Real, Builtin<ID>::C, Builtin<ID>::E, kItemsLarge, ID>(mh, a, stream, mode);                      \
     }
     DPOMP_SIM_BUILTINS(X)

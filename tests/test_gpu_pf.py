@@ -349,6 +349,33 @@ def test_deferred_level2_equals_two_ticket_levels(dp, case, n, nb, rs_type, monk
     assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
 
 
+@pytest.mark.parametrize("case,n,nb", [("lotka_c4", 4096, 6), ("sir_c2", 5000, 3), ("seir_c3", 70000, 2), ("sis_pooley", 3000, 4)])
+@pytest.mark.parametrize("knob", ["1", "auto"])
+def test_two_per_lane_loop_on_large_tiles_is_bit_identical(dp, case, n, nb, knob, monkeypatch):
+    """1024-particle tiles of the predefined models: the two-particles-per-lane loop with the Philox words drawn ahead (picked
+    for event-heavy models in under-filled launches from the event intensity of the handle's previous call) uses the same
+    counters and draws as the one-particle-per-lane loop: log-likelihoods, populations and ancestors are bit-identical, forced
+    (DPOMP_TWO_PER_LANE=1) and selected automatically (second call of the handle; LOTKA / SIS-pooley qualify, SIR / SEIR do not)."""
+    model, y, hmm, theta = load_case(dp, case)
+    thetas = theta[:, None] * np.linspace(0.95, 1.05, nb)[None, :]
+    out = []
+    for k in (knob, "0"):
+        if k == "auto":
+            monkeypatch.delenv("DPOMP_TWO_PER_LANE", raising=False)
+        else:
+            monkeypatch.setenv("DPOMP_TWO_PER_LANE", k)
+        pf = _pf(dp, hmm, n, nb, seed=8)
+        res = []
+        for call in range(2):  # the second call of a handle knows the event intensity of the first
+            pf.set_stream_key(900 + call)
+            ll = pf.partial(thetas, 1, min(len(y), 4))
+            res.append((ll, [pf.get_pop(b + 1) for b in range(nb)], pf.last_ancestors(nb)))
+        out.append(res)
+    for (ll_a, pops_a, anc_a), (ll_b, pops_b, anc_b) in zip(*out):
+        assert np.array_equal(ll_a, ll_b) and np.array_equal(anc_a, anc_b)
+        assert all(np.array_equal(u, v) for u, v in zip(pops_a, pops_b))
+
+
 @pytest.mark.parametrize("variant", ["wide_spread", "huge_observation", "tiny_sigma"])
 def test_weight_pass_paths_are_bit_exact_against_oracle(dp, orc, variant):
     """The integer-domain weight pass of the simulate kernel (tile maximum by integer min, per-CTA exp table indexed by
