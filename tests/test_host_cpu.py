@@ -142,3 +142,93 @@ def test_c_driver_compiles_and_links_against_the_header(built_lib, tmp_path):
     if not torch.cuda.is_available():
         res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
         assert res.returncode == 1 and "FAIL" in res.stderr
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        depth += ch in "({["
+        depth -= ch in ")}]"
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_agrees_with_the_header(built_lib, dp):
+    """The ccall shim a DiscretePOMP.jl maintainer adds (untested here: no Julia in the image) must at least agree with
+    include/dpomp.h symbol for symbol: every ccall names an exported entry point, passes as many arguments as the C
+    declaration takes, with Julia types of the C argument's width and kind, and the `DpompModelDesc` struct lists the
+    fields of `dpomp_model_desc` in order with the same element types and counts."""
+    import re
+
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "dpomp.h")).read(), flags=re.S)
+    jl = open(os.path.join(ROOT, "discretepomp.jl_b200", "julia", "DiscretePOMPGPU.jl")).read()
+    decls = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s+(dpomp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).split(",")]
+        decls[m.group(1)] = [] if args in (["void"], [""]) else args
+    assert set(decls) == set(dp._capi.EXPORTED_SYMBOLS)  # the regex sees what the ctypes table lists
+
+    def kind(c_arg):
+        c = re.sub(r"\bconst\b", "", c_arg).strip()
+        base = re.sub(r"\s+\w+$", "", c).replace(" ", "")  # drop the parameter name
+        return base
+
+    ok = {
+        "int32_t": {"Int32", "Cint"}, "int64_t": {"Int64"}, "uint64_t": {"UInt64"},
+        "double*": {"Ptr{Float64}", "Ref{Float64}"}, "int64_t*": {"Ptr{Int64}", "Ref{Int64}"},
+        "int32_t*": {"Ptr{Int32}", "Ref{Int32}"}, "uint8_t*": {"Ptr{UInt8}"}, "void*": {"Ptr{UInt8}", "Ptr{Cvoid}"},
+        "dpomp_model_desc*": {"Ref{DpompModelDesc}"},
+    }
+    calls = 0
+    for m in re.finditer(r"ccall\(\(:(dpomp_[a-z0-9_]+),\s*LIBDPOMP\),\s*(\w+),\s*\(", jl):
+        name, ret = m.group(1), m.group(2)
+        assert name in decls, name
+        i = j = m.end()
+        depth = 1
+        while depth:
+            depth += jl[j] == "("
+            depth -= jl[j] == ")"
+            j += 1
+        jtypes = _split_top(jl[i:j - 1])
+        cargs = decls[name]
+        assert len(jtypes) == len(cargs), (name, jtypes, cargs)
+        assert ret == ("Cstring" if name == "dpomp_last_error" else "Cint"), (name, ret)
+        for jt, ca in zip(jtypes, cargs):
+            k = kind(ca)
+            if re.fullmatch(r"dpomp_(model|pf|comm|mbp)\*", k):
+                assert jt == "Ptr{Cvoid}", (name, jt, ca)  # opaque handle
+            elif re.fullmatch(r"dpomp_(model|pf|comm|mbp)\*\*", k):
+                assert jt == "Ref{Ptr{Cvoid}}", (name, jt, ca)
+            else:
+                assert jt in ok[k], (name, jt, ca)
+        calls += 1
+    assert calls >= 25
+    # struct dpomp_model_desc vs struct DpompModelDesc: same fields, order, element type and count
+    body = re.search(r"typedef struct dpomp_model_desc \{(.*?)\} dpomp_model_desc;", hdr, flags=re.S).group(1)
+    dims = {"DPOMP_MAX_EVENTS": 8, "DPOMP_MAX_COMPARTMENTS": 8, "DPOMP_MAX_OBS_VALS": 8}
+    for k in dims:
+        assert re.search(rf"#define {k}\s+{dims[k]}\b", hdr), k
+    c_fields = []
+    for m in re.finditer(r"(const\s+)?(\w+)\s*(\*)?\s*(\w+)((?:\[\w+\])*)\s*;", body):
+        n = 1
+        for d in re.findall(r"\[(\w+)\]", m.group(5)):
+            n *= dims[d]
+        c_fields.append((m.group(4), m.group(2) + ("*" if m.group(3) else ""), n))
+    jbody = re.search(r"struct DpompModelDesc\n(.*?)\nend", jl, flags=re.S).group(1)
+    jmap = {"Int32": "int32_t", "Int64": "int64_t", "Float64": "double", "Ptr{Float64}": "double*", "Ptr{Int32}": "int32_t*",
+            "Ptr{Int64}": "int64_t*"}
+    j_fields = []
+    for f in re.split(r"[;\n]", jbody):
+        f = f.strip()
+        if not f:
+            continue
+        nm, ty = f.split("::")
+        t = re.fullmatch(r"NTuple\{(\d+),(\w+)\}", ty)
+        j_fields.append((nm, jmap[t.group(2)], int(t.group(1))) if t else (nm, jmap[ty], 1))
+    assert j_fields == c_fields, (j_fields, c_fields)
